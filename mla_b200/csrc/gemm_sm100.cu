@@ -1,0 +1,373 @@
+// bf16 GEMM on 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM), operands fed by TMA.
+//
+//   C[M,N] = epilogue( alpha * A_op[M,K] . B_op[K,N] )
+//
+// A is either K-contiguous ([M,K] row-major, "K-major") or M-contiguous ([K,M] row-major, "MN-major");
+// B is either K-contiguous ([N,K] row-major, i.e. an nn.Linear weight) or N-contiguous ([K,N] row-major).
+// The four combinations cover forward (x.W^T), dgrad (dy.W) and wgrad (dy^T.x) of every linear layer on the
+// hot path (reference: transformers/models/llama/modeling_llama.py:240,:435-437,:495 run as cuBLAS calls).
+//
+// Kernel shape: persistent, one CTA per SM, 192 threads:
+//   warp 0    TMA producer      (cp.async.bulk.tensor -> 128B-swizzled smem ring, 4 stages x 48 KB)
+//   warp 1    MMA issuer        (one elected lane issues tcgen05.mma 128x256x16; owns the TMEM allocation)
+//   warps 2-5 epilogue          (tcgen05.ld 32x32b -> registers -> fused bias/activation/residual -> global)
+// Two 128x256 fp32 accumulators (2 x 256 TMEM columns) are double-buffered so the epilogue of tile i overlaps
+// the main loop of tile i+1.
+#include "mla_internal.cuh"
+#include "ptx.cuh"
+
+namespace mla {
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int GEMM_THREADS = 192;
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = 512;
+constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct GemmEpilogue {
+  void* c;
+  int64_t ldc;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* residual;
+  int64_t ldr;
+  __nv_bfloat16* pre_act;
+  int64_t ldp;
+  float alpha;
+  int c_dtype;      // 0 bf16, 1 fp32
+  int accumulate;   // fp32 only: C += value
+  int activation;   // MLA_ACT_*
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case MLA_ACT_RELU: return v > 0.f ? v : 0.f;
+    case MLA_ACT_GELU_ERF: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    case MLA_ACT_GELU_TANH: {
+      const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+      float u = k0 * (v + k1 * v * v * v);
+      return 0.5f * v * (1.f + tanhf(u));
+    }
+    case MLA_ACT_SILU: return v / (1.f + __expf(-v));
+    default: return v;
+  }
+}
+
+// Tile rasterisation: groups of GROUP_M row-tiles sweep all column-tiles, so the CTAs that run concurrently share
+// a small set of A row-panels while B streams through L2.
+constexpr int GROUP_M = 16;
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
+  int group_size = GROUP_M * tiles_n;
+  int g = tile / group_size;
+  int first_m = g * GROUP_M;
+  int gm = min(GROUP_M, tiles_m - first_m);
+  int r = tile - g * group_size;
+  tm = first_m + r % gm;
+  tn = r / gm;
+}
+
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 int M, int N, int K, GemmEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + ACC_STAGES;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tiles_m = (M + BM - 1) / BM;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_base_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int tm, tn;
+        tile_coords(tile, tiles_m, tiles_n, tm, tn);
+        const int m0 = tm * BM, n0 = tn * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          const int k0 = kb * BK;
+          if (A_MN == 0) {
+            tma_load_2d(sa, &map_a, &full_bar[stage], k0, m0);  // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)  // box {64 m, 64 k-rows}, one 8 KB slab per 64 columns of M
+              tma_load_2d(sa + j * (BK * 128), &map_a, &full_bar[stage], m0 + j * 64, k0);
+          }
+          if (B_MN == 0) {
+            tma_load_2d(sb, &map_b, &full_bar[stage], k0, n0);  // box {64 k, 256 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * (BK * 128), &map_b, &full_bar[stage], n0 + j * 64, k0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: rows are 128 B apart, 8-row groups 1024 B apart; a 16-element K step is +32 B.
+            // MN-major: k-rows are 128 B apart, 8-k groups 1024 B apart (SBO), 64-element MN slabs BK*128 B apart
+            //           (LBO); a 16-element K step is two 8-k groups = +2048 B.
+            uint64_t da = A_MN == 0 ? umma_smem_desc_sw128(sa + k * 32, 16, 1024)
+                                    : umma_smem_desc_sw128(sa + k * 2048, BK * 128, 1024);
+            uint64_t db = B_MN == 0 ? umma_smem_desc_sw128(sb + k * 32, 16, 1024)
+                                    : umma_smem_desc_sw128(sb + k * 2048, BK * 128, 1024);
+            umma_f16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int tm, tn;
+      tile_coords(tile, tiles_m, tiles_n, tm, tn);
+      const int64_t row = int64_t(tm) * BM + quarter * 32 + lane;
+      const int n0 = tn * BN;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
+      const bool row_ok = row < M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        const bool full = (col0 + 32 <= N);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
+        if (ep.c_dtype == 1) {
+          // fp32 output (weight gradients): optional accumulate, no activation path.
+          float* crow = reinterpret_cast<float*>(ep.c) + row * ep.ldc + col0;
+          if (full && (ep.ldc & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (ep.accumulate) {
+                float4 p = *reinterpret_cast<const float4*>(crow + j);
+                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+              }
+              *reinterpret_cast<float4*>(crow + j) = o;
+            }
+          } else {
+            #pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) crow[j] = ep.accumulate ? crow[j] + v[j] : v[j];
+          }
+          continue;
+        }
+        // bf16 output: replicate the reference's rounding points (linear -> bf16, act -> bf16, +residual -> bf16).
+        if (ep.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || col0 + j < N) v[j] += __bfloat162float(ep.bias[col0 + j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
+        if (ep.pre_act != nullptr) {
+          __nv_bfloat16* prow = ep.pre_act + row * ep.ldp + col0;
+          if (full && (ep.ldp & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              *reinterpret_cast<uint4*>(prow + j) = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+                                                              pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+          } else {
+            #pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) prow[j] = __float2bfloat16_rn(v[j]);
+          }
+        }
+        if (ep.activation != MLA_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = bf16_round(apply_act(v[j], ep.activation));
+        }
+        if (ep.residual != nullptr) {
+          const __nv_bfloat16* rrow = ep.residual + row * ep.ldr + col0;
+          if (full && (ep.ldr & 7) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 q = *reinterpret_cast<const uint4*>(rrow + j);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                float2 f = __bfloat1622float2(h[t]);
+                v[j + 2 * t] += f.x;
+                v[j + 2 * t + 1] += f.y;
+              }
+            }
+          } else {
+            #pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < N) v[j] += __bfloat162float(rrow[j]);
+          }
+        }
+        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(ep.c) + row * ep.ldc + col0;
+        if (full && (ep.ldc & 7) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8)
+            *reinterpret_cast<uint4*>(crow + j) = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+                                                            pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+        } else {
+          #pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) crow[j] = __float2bfloat16_rn(v[j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int encode_operand_map(CUtensorMap* map, const void* ptr, int mn_major, int64_t rows_mn, int64_t k,
+                              int64_t ld, int tile_mn) {
+  // K-major:  global [rows_mn, k] (k contiguous):  dims {k, rows_mn}, box {64, tile_mn}
+  // MN-major: global [k, rows_mn] (mn contiguous): dims {rows_mn, k}, box {64, 64}
+  uint64_t dims[2];
+  uint64_t strides[1] = {uint64_t(ld) * 2};
+  uint32_t box[2];
+  if (!mn_major) {
+    dims[0] = uint64_t(k); dims[1] = uint64_t(rows_mn);
+    box[0] = BK; box[1] = uint32_t(tile_mn);
+  } else {
+    dims[0] = uint64_t(rows_mn); dims[1] = uint64_t(k);
+    box[0] = 64; box[1] = BK;
+  }
+  return encode_tmap_2d_bf16(map, ptr, dims, strides, box);
+}
+
+template <int A_MN, int B_MN>
+static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const GemmEpilogue& ep,
+                       cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = gemm_bf16_kernel<A_MN, B_MN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "cudaFuncSetAttribute(gemm smem): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ma, mb, M, N, K, ep);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return MLA_OK;
+}
+
+}  // namespace mla
+
+using namespace mla;
+
+extern "C" int mla_gemm_bf16(const mla_gemm_args* g, void* stream_) {
+  if (g == nullptr) return set_error(MLA_ERR_ARG, "gemm: null args");
+  if (int rc = device_check()) return rc;
+  if (g->m <= 0 || g->n <= 0 || g->k <= 0) return set_error(MLA_ERR_ARG, "gemm: empty problem %lld x %lld x %lld",
+                                                           (long long)g->m, (long long)g->n, (long long)g->k);
+  if (g->m > INT32_MAX || g->n > INT32_MAX || g->k > INT32_MAX) return set_error(MLA_ERR_ARG, "gemm: dims exceed int32");
+  if ((g->lda & 7) || (g->ldb & 7)) return set_error(MLA_ERR_ARG, "gemm: lda/ldb must be multiples of 8 elements (TMA 16-byte stride)");
+  if ((reinterpret_cast<uintptr_t>(g->a) & 15) || (reinterpret_cast<uintptr_t>(g->b) & 15) ||
+      (reinterpret_cast<uintptr_t>(g->c) & 15))
+    return set_error(MLA_ERR_ARG, "gemm: pointers must be 16-byte aligned");
+  if (g->c_dtype != 0 && g->c_dtype != 1) return set_error(MLA_ERR_ARG, "gemm: c_dtype must be 0 (bf16) or 1 (fp32)");
+  if (g->c_dtype == 1 && (g->bias || g->residual || g->pre_act || g->activation != MLA_ACT_NONE))
+    return set_error(MLA_ERR_ARG, "gemm: fp32 output supports only alpha/accumulate");
+  if (g->c_dtype == 0 && g->accumulate) return set_error(MLA_ERR_ARG, "gemm: accumulate requires fp32 output");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  CUtensorMap ma, mb;
+  if (int rc = encode_operand_map(&ma, g->a, g->a_mn_major, g->m, g->k, g->lda, BM)) return rc;
+  if (int rc = encode_operand_map(&mb, g->b, g->b_mn_major, g->n, g->k, g->ldb, BN)) return rc;
+  GemmEpilogue ep;
+  ep.c = g->c; ep.ldc = g->ldc;
+  ep.bias = static_cast<const __nv_bfloat16*>(g->bias);
+  ep.residual = static_cast<const __nv_bfloat16*>(g->residual); ep.ldr = g->ldr;
+  ep.pre_act = static_cast<__nv_bfloat16*>(g->pre_act); ep.ldp = g->ldp;
+  ep.alpha = g->alpha; ep.c_dtype = g->c_dtype; ep.accumulate = g->accumulate; ep.activation = g->activation;
+  const int M = int(g->m), N = int(g->n), K = int(g->k);
+  if (!g->a_mn_major && !g->b_mn_major) return launch_gemm<0, 0>(ma, mb, M, N, K, ep, stream);
+  if (!g->a_mn_major && g->b_mn_major) return launch_gemm<0, 1>(ma, mb, M, N, K, ep, stream);
+  if (g->a_mn_major && !g->b_mn_major) return launch_gemm<1, 0>(ma, mb, M, N, K, ep, stream);
+  return launch_gemm<1, 1>(ma, mb, M, N, K, ep, stream);
+}
