@@ -68,6 +68,83 @@ typedef struct mla_gemm_args {
 } mla_gemm_args;
 int mla_gemm_bf16(const mla_gemm_args* args, void* stream);
 
+/* ---- RMSNorm ----------------------------------------------------------------------------------------------
+ * y = w * bf16(x * rsqrt(mean(x^2) + eps))   (modeling_llama.py:85-90, LlamaRMSNorm; x,y,w bf16, stats f32).
+ * mode 1 divides by the unbiased variance instead (timm 0.9.x RmsNorm hazard) — used only by
+ * FinalLayer.norm_final (models/diffusion/models.py:179) when that arithmetic is selected.
+ * rstd (f32 [rows]) may be NULL.  bwd: dx = rmsnorm'(dy) (+ dres if non-NULL), dw (f32 [h]) += sum_rows dy * n. */
+int mla_rmsnorm_fwd(const void* x, const void* w, void* y, void* rstd, int64_t rows, int32_t h, int64_t ldx,
+                    int64_t ldy, float eps, int32_t mode, void* stream);
+int mla_rmsnorm_bwd(const void* dy, const void* x, const void* w, const void* dres, void* dx, void* dw,
+                    int64_t rows, int32_t h, float eps, void* stream);
+
+/* ---- RoPE ------------------------------------------------------------------------------------------------
+ * In-place rotation of `heads` consecutive heads of width d in each row of a [tokens, ld] buffer
+ * (modeling_llama.py:184-208, apply_rotary_pos_emb on the bf16 path; position = token index mod seq, as
+ * position_ids = arange(S) for every sample, :985-990).  cos_t/sin_t: bf16 [seq, d/2] tables.
+ * transpose != 0 applies the inverse rotation (the backward). */
+int mla_rope_inplace(void* base, const void* cos_t, const void* sin_t, int64_t tokens, int32_t seq, int32_t heads,
+                     int32_t d, int64_t ld, int32_t transpose, void* stream);
+
+/* ---- SwiGLU ----------------------------------------------------------------------------------------------
+ * gu = [rows, 2f] (gate | up).  out[rows,f] = bf16(silu(gate)) * up   (modeling_llama.py:240).
+ * bwd: dgu[rows,2f] from dact[rows,f] and gu. */
+int mla_swiglu_fwd(const void* gu, void* out, int64_t rows, int32_t f, void* stream);
+int mla_swiglu_bwd(const void* dact, const void* gu, void* dgu, int64_t rows, int32_t f, void* stream);
+
+/* ---- causal attention ------------------------------------------------------------------------------------
+ * Replaces flash_attn_func / flash_attn_varlen_func + unpad/pad_input (modeling_llama.py:540-557).
+ * q,k,v: row t = b*seq+s, head hd at column hd*head_dim, row pitch ld_qkv (so the fused QKV projection buffer is
+ * consumed in place); o/d_o: [batch*seq, heads*head_dim] pitch ld_o; lse/delta: f32 [batch, heads, seq];
+ * mask: uint8 [batch, seq] (attention_mask) or NULL.  Key j visible to query i iff j <= i and mask[b,j];
+ * rows with mask 0 output zeros and get zero gradient.  head_dim in {32, 64, 128}. */
+typedef struct mla_attn_args {
+  const void *q, *k, *v;
+  int64_t ld_qkv;
+  void* o;
+  int64_t ld_o;
+  void* lse;
+  const void* mask;
+  int32_t batch, seq, heads, head_dim;
+  float scale;
+  /* backward only */
+  const void* d_o;
+  void* delta;
+  void *dq, *dk, *dv;
+  int64_t ld_dqkv;
+} mla_attn_args;
+int mla_attn_fwd(const mla_attn_args* args, void* stream);
+int mla_attn_bwd(const mla_attn_args* args, void* stream);
+
+/* ---- small row/elementwise kernels around the GEMMs ---------------------------------------------------------
+ * (ATen glue in the reference: dtype casts under autocast, activation backward, bias gradients, torch.cat / index
+ *  splices in models/vlm/prismatic.py:949-1040, nn.Embedding, nn.LayerNorm in vision_tokenizer.py:21-24.) */
+int mla_cast_f32_bf16(const void* src, void* dst, int64_t n, void* stream);
+/* dst bf16 [rows, cols] <- src f32 [rows_src, cols_src] (pitch lds), zero padded */
+int mla_cast_pad_f32_bf16(const void* src, void* dst, int64_t rows, int64_t cols, int64_t rows_src, int64_t cols_src,
+                          int64_t lds, void* stream);
+/* dx = bf16(dy * act'(pre)) */
+int mla_act_bwd(const void* dy, const void* pre, void* dx, int64_t n, int32_t act, void* stream);
+/* out f32 [cols] += column sums of x bf16 [rows, cols] (pitch ld) */
+int mla_colsum_bf16(const void* x, void* out, int64_t rows, int32_t cols, int64_t ld, void* stream);
+/* dst[i,:] = idx[i] >= 0 ? src[idx[i],:] : 0 ; idx int32 (idx_is_i64 = 0) or int64 */
+int mla_gather_rows(const void* src, const void* idx, void* dst, int64_t n, int32_t h, int64_t lds,
+                    int32_t idx_is_i64, void* stream);
+/* dsrc[idx[i],:] = ddst[i,:] for idx[i] >= 0 (idx injective) */
+int mla_scatter_rows(void* dsrc, const void* idx, const void* ddst, int64_t n, int32_t h, int64_t lds, void* stream);
+/* grad f32 [V,h]: grad[ids[i],:] += dout[i,:] unless ids[i] == pad_id (nn.Embedding backward) */
+int mla_embedding_bwd(void* grad, const void* ids, const void* dout, int64_t n, int32_t h, int64_t pad_id,
+                      void* stream);
+int mla_layernorm_fwd(const void* x, const void* w, const void* b, void* y, int64_t rows, int32_t h, float eps,
+                      void* stream);
+/* x_t = sqrt_ac[t]*a + sqrt_1mac[t]*noise (models/diffusion/gaussian_diffusion.py:214-229); f32, t int64 [n/per_sample] */
+int mla_q_sample(const void* a, const void* noise, const void* t, const void* sqrt_ac, const void* sqrt_1mac,
+                 void* out, int64_t n, int32_t per_sample, void* stream);
+/* loss[0] = mean((pred - target)^2), pred bf16, target f32 (models/mla/model_mla.py:215); bwd: dpred = g*2(pred-target)/n */
+int mla_mse_fwd(const void* pred, const void* target, void* loss, int64_t n, void* stream);
+int mla_mse_bwd(const void* pred, const void* target, const void* gscale, void* dpred, int64_t n, void* stream);
+int mla_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

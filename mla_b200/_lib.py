@@ -50,3 +50,14 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(lib().mla_launch_count())
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("ld_qkv", C.c_int64),
+        ("o", C.c_void_p), ("ld_o", C.c_int64), ("lse", C.c_void_p), ("mask", C.c_void_p),
+        ("batch", C.c_int32), ("seq", C.c_int32), ("heads", C.c_int32), ("head_dim", C.c_int32),
+        ("scale", C.c_float),
+        ("d_o", C.c_void_p), ("delta", C.c_void_p),
+        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("ld_dqkv", C.c_int64),
+    ]

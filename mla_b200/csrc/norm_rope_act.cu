@@ -1,0 +1,321 @@
+// Bandwidth-bound row kernels of the decoder layer: RMSNorm fwd/bwd, RoPE (in place, fwd and transposed for bwd),
+// SwiGLU fwd/bwd.  One pass over HBM each, 16-byte vector accesses, fp32 math, and the reference's bf16 rounding
+// points reproduced (each PyTorch op on the bf16 autocast path rounds its result to bf16).
+#include "mla_internal.cuh"
+#include "ptx.cuh"
+
+namespace mla {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024; result broadcast to every thread.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();  // protect red[] reuse across consecutive calls
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = lane < nw ? red[lane] : 0.f;
+  return warp_sum(t);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    float2 p = __bfloat1622float2(h[t]);
+    f[2 * t] = p.x;
+    f[2 * t + 1] = p.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------------------------------------ RMSNorm fwd
+// modeling_llama.py:85-90:  xf = x.float(); n = xf * rsqrt(mean(xf^2) + eps); y = w * n.to(bf16)
+// mode 1 ("var", timm 0.9.x RmsNorm hazard): divide by the unbiased variance instead of the mean square.
+__global__ void rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                                   __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out, int64_t rows, int h,
+                                   int64_t ldx, int64_t ldy, float eps, int mode) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const __nv_bfloat16* xr = x + row * ldx;
+  const int nvec = h >> 3;
+  float ss = 0.f, s1 = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + i * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ss += f[j] * f[j]; s1 += f[j]; }
+  }
+  ss = block_sum(ss, red);
+  float rstd;
+  if (mode == 0) {
+    rstd = rsqrtf(ss / float(h) + eps);
+  } else {
+    s1 = block_sum(s1, red);
+    float mean = s1 / float(h);
+    float var = (ss - float(h) * mean * mean) / float(h - 1);
+    rstd = rsqrtf(var + eps);
+  }
+  if (threadIdx.x == 0 && rstd_out) rstd_out[row] = rstd;
+  __nv_bfloat16* yr = y + row * ldy;
+  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+    float f[8], g[8];
+    unpack8(*reinterpret_cast<const uint4*>(xr + i * 8), f);
+    unpack8(*reinterpret_cast<const uint4*>(w + i * 8), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = g[j] * bf16_round(f[j] * rstd);
+    *reinterpret_cast<uint4*>(yr + i * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ RMSNorm bwd
+// dn = dy*w ; dx = rstd*(dn - n*mean(dn*n)) (+ dres) ; dw += sum_rows dy*n.   Each CTA walks rows blockIdx.x,
+// +gridDim.x, ... keeping its dw partial in registers, then does one fp32 atomicAdd per column.
+template <int VPT>  // uint4 vectors per thread (h <= blockDim*8*VPT)
+__global__ void rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                   const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ dres,
+                                   __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, int64_t rows, int h,
+                                   float eps) {
+  __shared__ float red[32];
+  const int nvec = h >> 3;
+  float wv[VPT][8];
+  float dwacc[VPT][8];
+#pragma unroll
+  for (int v = 0; v < VPT; ++v) {
+    int i = threadIdx.x + v * blockDim.x;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dwacc[v][j] = 0.f; wv[v][j] = 0.f; }
+    if (i < nvec) unpack8(*reinterpret_cast<const uint4*>(w + i * 8), wv[v]);
+  }
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const __nv_bfloat16* xr = x + row * h;
+    const __nv_bfloat16* dyr = dy + row * h;
+    float xf[VPT][8], dn[VPT][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      int i = threadIdx.x + v * blockDim.x;
+      if (i < nvec) {
+        unpack8(*reinterpret_cast<const uint4*>(xr + i * 8), xf[v]);
+        unpack8(*reinterpret_cast<const uint4*>(dyr + i * 8), dn[v]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { xf[v][j] = 0.f; dn[v][j] = 0.f; }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += xf[v][j] * xf[v][j];
+    }
+    ss = block_sum(ss, red);
+    const float rstd = rsqrtf(ss / float(h) + eps);
+    float dot = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float n = xf[v][j] * rstd;
+        dwacc[v][j] += dn[v][j] * bf16_round(n);  // dy * n (n is what forward multiplied by w)
+        dn[v][j] *= wv[v][j];                     // dn = dy * w
+        dot += dn[v][j] * n;
+        xf[v][j] = n;
+      }
+    dot = block_sum(dot, red) / float(h);
+    __nv_bfloat16* dxr = dx + row * h;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      int i = threadIdx.x + v * blockDim.x;
+      if (i < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = bf16_round(rstd * (dn[v][j] - xf[v][j] * dot));
+        if (dres) {
+          float r[8];
+          unpack8(*reinterpret_cast<const uint4*>(dres + row * h + i * 8), r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
+        *reinterpret_cast<uint4*>(dxr + i * 8) = pack8(o);
+      }
+    }
+  }
+  if (dw) {
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      int i = threadIdx.x + v * blockDim.x;
+      if (i < nvec)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dw + i * 8 + j, dwacc[v][j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ RoPE
+// modeling_llama.py:184-208 on the bf16 path: out = bf16(bf16(x*cos) + bf16(rotate_half(x)*sin)), cos/sin bf16.
+// Applied in place to the q and k column blocks of the fused [T, ld] projection buffer.  sign=-1 is the transpose
+// (the backward of the rotation).  One thread per (token, head, 8-wide chunk of the first half).
+__global__ void rope_kernel(__nv_bfloat16* __restrict__ base, const __nv_bfloat16* __restrict__ cos_t,
+                            const __nv_bfloat16* __restrict__ sin_t, int64_t tokens, int seq, int heads, int d,
+                            int64_t ld, float sign) {
+  const int half = d >> 1;
+  const int cpr = half >> 3;  // chunks per (token, head)
+  const int64_t total = tokens * heads * cpr;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(idx % cpr);
+    const int hd = int((idx / cpr) % heads);
+    const int64_t t = idx / (int64_t(cpr) * heads);
+    const int pos = int(t % seq);
+    __nv_bfloat16* p = base + t * ld + int64_t(hd) * d + c * 8;
+    float x1[8], x2[8], cs[8], sn[8];
+    unpack8(*reinterpret_cast<const uint4*>(p), x1);
+    unpack8(*reinterpret_cast<const uint4*>(p + half), x2);
+    unpack8(*reinterpret_cast<const uint4*>(cos_t + int64_t(pos) * half + c * 8), cs);
+    unpack8(*reinterpret_cast<const uint4*>(sin_t + int64_t(pos) * half + c * 8), sn);
+    float o1[8], o2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = sign * sn[j];
+      o1[j] = bf16_round(x1[j] * cs[j]) + bf16_round(-x2[j] * s);
+      o2[j] = bf16_round(x2[j] * cs[j]) + bf16_round(x1[j] * s);
+    }
+    *reinterpret_cast<uint4*>(p) = pack8(o1);
+    *reinterpret_cast<uint4*>(p + half) = pack8(o2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ SwiGLU
+// modeling_llama.py:240: act_fn(gate_proj(x)) * up_proj(x) with bf16 rounding after silu and after the product.
+// gu is the fused [T, 2f] projection (gate columns [0,f), up columns [f,2f)).
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+__global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ out,
+                                  int64_t rows, int f) {
+  const int cpr = f >> 3;
+  const int64_t total = rows * cpr;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = idx / cpr;
+    const int c = int(idx % cpr);
+    float g[8], u[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(gu + r * 2 * f + c * 8), g);
+    unpack8(*reinterpret_cast<const uint4*>(gu + r * 2 * f + f + c * 8), u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = bf16_round(g[j] * sigmoidf_(g[j])) * u[j];
+    *reinterpret_cast<uint4*>(out + r * f + c * 8) = pack8(o);
+  }
+}
+
+// d_gu[:, :f] = d_act*u*silu'(g) ; d_gu[:, f:] = d_act*silu(g)
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dact, const __nv_bfloat16* __restrict__ gu,
+                                  __nv_bfloat16* __restrict__ dgu, int64_t rows, int f) {
+  const int cpr = f >> 3;
+  const int64_t total = rows * cpr;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t r = idx / cpr;
+    const int c = int(idx % cpr);
+    float g[8], u[8], d[8], dg[8], du[8];
+    unpack8(*reinterpret_cast<const uint4*>(gu + r * 2 * f + c * 8), g);
+    unpack8(*reinterpret_cast<const uint4*>(gu + r * 2 * f + f + c * 8), u);
+    unpack8(*reinterpret_cast<const uint4*>(dact + r * f + c * 8), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = sigmoidf_(g[j]);
+      const float a = bf16_round(g[j] * s);
+      du[j] = d[j] * a;
+      const float da = bf16_round(d[j] * u[j]);
+      dg[j] = da * (s * (1.f + g[j] * (1.f - s)));
+    }
+    *reinterpret_cast<uint4*>(dgu + r * 2 * f + c * 8) = pack8(dg);
+    *reinterpret_cast<uint4*>(dgu + r * 2 * f + f + c * 8) = pack8(du);
+  }
+}
+
+static inline int ew_grid(int64_t total, int block) {
+  int64_t g = (total + block - 1) / block;
+  int64_t cap = int64_t(num_sms()) * 16;
+  return int(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace mla
+
+using namespace mla;
+
+extern "C" int mla_rmsnorm_fwd(const void* x, const void* w, void* y, void* rstd, int64_t rows, int32_t h, int64_t ldx,
+                               int64_t ldy, float eps, int32_t mode, void* stream) {
+  if (int rc = device_check()) return rc;
+  if (rows <= 0) return MLA_OK;
+  if (h <= 0 || (h & 7) || (ldx & 7) || (ldy & 7)) return set_error(MLA_ERR_ARG, "rmsnorm_fwd: h, ldx, ldy must be multiples of 8");
+  if (mode != 0 && mode != 1) return set_error(MLA_ERR_ARG, "rmsnorm_fwd: mode must be 0 (mean-square) or 1 (variance)");
+  int block = (h / 8 + 31) / 32 * 32;
+  block = block > 256 ? 256 : block;
+  rmsnorm_fwd_kernel<<<(unsigned)rows, block, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, (float*)rstd, rows, h, ldx, ldy, eps, mode);
+  MLA_CHECK_LAUNCH("rmsnorm_fwd");
+  return MLA_OK;
+}
+
+extern "C" int mla_rmsnorm_bwd(const void* dy, const void* x, const void* w, const void* dres, void* dx, void* dw,
+                               int64_t rows, int32_t h, float eps, void* stream) {
+  if (int rc = device_check()) return rc;
+  if (rows <= 0) return MLA_OK;
+  if (h <= 0 || (h & 7)) return set_error(MLA_ERR_ARG, "rmsnorm_bwd: h must be a multiple of 8");
+  if (h > 256 * 8 * 4) return set_error(MLA_ERR_ARG, "rmsnorm_bwd: h > 8192 unsupported");
+  const int nvec = h / 8;
+  int block = (nvec + 31) / 32 * 32;
+  block = block > 256 ? 256 : block;
+  const int vpt = (nvec + block - 1) / block;
+  int grid = int(rows < int64_t(num_sms()) * 2 ? rows : int64_t(num_sms()) * 2);
+  auto s = (cudaStream_t)stream;
+#define LAUNCH_RB(V)                                                                                              \
+  rmsnorm_bwd_kernel<V><<<grid, block, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,                 \
+                                                (const __nv_bfloat16*)w, (const __nv_bfloat16*)dres,              \
+                                                (__nv_bfloat16*)dx, (float*)dw, rows, h, eps)
+  if (vpt == 1) LAUNCH_RB(1);
+  else if (vpt == 2) LAUNCH_RB(2);
+  else if (vpt == 3) LAUNCH_RB(3);
+  else LAUNCH_RB(4);
+#undef LAUNCH_RB
+  MLA_CHECK_LAUNCH("rmsnorm_bwd");
+  return MLA_OK;
+}
+
+extern "C" int mla_rope_inplace(void* base, const void* cos_t, const void* sin_t, int64_t tokens, int32_t seq,
+                                int32_t heads, int32_t d, int64_t ld, int32_t transpose, void* stream) {
+  if (int rc = device_check()) return rc;
+  if (tokens <= 0 || heads <= 0) return MLA_OK;
+  if (d <= 0 || (d & 15) || (ld & 7)) return set_error(MLA_ERR_ARG, "rope: head dim must be a multiple of 16 and ld of 8");
+  if (seq <= 0) return set_error(MLA_ERR_ARG, "rope: seq must be positive");
+  const int64_t total = tokens * heads * (d / 16);
+  rope_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)base, (const __nv_bfloat16*)cos_t,
+                                                                     (const __nv_bfloat16*)sin_t, tokens, seq, heads, d,
+                                                                     ld, transpose ? -1.f : 1.f);
+  MLA_CHECK_LAUNCH("rope");
+  return MLA_OK;
+}
+
+extern "C" int mla_swiglu_fwd(const void* gu, void* out, int64_t rows, int32_t f, void* stream) {
+  if (int rc = device_check()) return rc;
+  if (rows <= 0) return MLA_OK;
+  if (f <= 0 || (f & 7)) return set_error(MLA_ERR_ARG, "swiglu_fwd: f must be a multiple of 8");
+  swiglu_fwd_kernel<<<ew_grid(rows * (f / 8), 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)gu,
+                                                                                    (__nv_bfloat16*)out, rows, f);
+  MLA_CHECK_LAUNCH("swiglu_fwd");
+  return MLA_OK;
+}
+
+extern "C" int mla_swiglu_bwd(const void* dact, const void* gu, void* dgu, int64_t rows, int32_t f, void* stream) {
+  if (int rc = device_check()) return rc;
+  if (rows <= 0) return MLA_OK;
+  if (f <= 0 || (f & 7)) return set_error(MLA_ERR_ARG, "swiglu_bwd: f must be a multiple of 8");
+  swiglu_bwd_kernel<<<ew_grid(rows * (f / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dact, (const __nv_bfloat16*)gu, (__nv_bfloat16*)dgu, rows, f);
+  MLA_CHECK_LAUNCH("swiglu_bwd");
+  return MLA_OK;
+}

@@ -1,0 +1,301 @@
+"""Llama-2 decoder stack of the MLA hot path on libmla_b200 kernels.
+
+Mirrors the reference's module tree and parameter names (transformers/models/llama/modeling_llama.py:
+LlamaRMSNorm :76, LlamaMLP :211, LlamaFlashAttention2 :405, LlamaDecoderLayer :695, LlamaModel :912) so a
+`state_dict()` is interchangeable, but the compute is one autograd node per decoder layer that launches our CUDA
+kernels directly:
+
+    rmsnorm -> [q|k|v] GEMM -> RoPE (in place) -> flash attention -> o GEMM (+residual)
+            -> rmsnorm -> [gate|up] GEMM -> SwiGLU -> down GEMM (+residual)
+
+Parameters stay fp32 `nn.Parameter`s under their reference names (scripts/train.py:306 asserts fp32); each layer
+keeps a bf16 compute copy of its weights, fused as [q;k;v] and [gate;up], refreshed from the fp32 masters when they
+change.  Weight gradients are written by the wgrad GEMMs straight into fp32 gradient arenas that `param.grad`
+aliases (no autograd-side accumulation buffers).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+# What a layer keeps for backward.
+#   "layer": only its input; the whole layer is recomputed in backward (what the reference's FSDP activation
+#            checkpointing does, training/strategies/fsdp.py:217-223)
+#   "mlp"  : input, qkv, attention output, LSE, mid residual; only the gate/up GEMM (+SwiGLU) is recomputed
+#   "none" : additionally keeps gate/up; nothing but the cheap norm/SwiGLU kernels is recomputed
+SAVE_LEVELS = ("layer", "mlp", "none")
+
+
+class LlamaRMSNorm(nn.Module):
+    def __init__(self, hidden_size: int, eps: float = 1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.variance_epsilon = eps
+
+
+class _Proj(nn.Module):
+    """Parameter holder with nn.Linear's attribute layout (weight [out,in], no bias)."""
+
+    def __init__(self, in_features: int, out_features: int):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = nn.Parameter(torch.empty(out_features, in_features))
+
+
+class LlamaAttention(nn.Module):
+    def __init__(self, hidden: int, heads: int):
+        super().__init__()
+        self.q_proj = _Proj(hidden, hidden)
+        self.k_proj = _Proj(hidden, hidden)
+        self.v_proj = _Proj(hidden, hidden)
+        self.o_proj = _Proj(hidden, hidden)
+
+
+class LlamaMLP(nn.Module):
+    def __init__(self, hidden: int, inter: int):
+        super().__init__()
+        self.gate_proj = _Proj(hidden, inter)
+        self.up_proj = _Proj(hidden, inter)
+        self.down_proj = _Proj(inter, hidden)
+
+
+@dataclass
+class LayerShape:
+    B: int
+    S: int
+    H: int
+    D: int
+    mask: Optional[torch.Tensor]      # uint8 [B,S] or None
+    cos: torch.Tensor                 # bf16 [S, D/2]
+    sin: torch.Tensor
+
+
+class LlamaDecoderLayer(nn.Module):
+    def __init__(self, hidden: int, inter: int, heads: int, eps: float, layer_idx: int):
+        super().__init__()
+        self.hidden_size, self.inter, self.heads, self.eps, self.layer_idx = hidden, inter, heads, eps, layer_idx
+        self.self_attn = LlamaAttention(hidden, heads)
+        self.mlp = LlamaMLP(hidden, inter)
+        self.input_layernorm = LlamaRMSNorm(hidden, eps)
+        self.post_attention_layernorm = LlamaRMSNorm(hidden, eps)
+        self.save_level = "layer"
+        self._c = None          # bf16 compute copies
+        self._versions = None
+        self._g = None          # fp32 gradient arenas
+        self._grads_fresh = True
+
+    # ------------------------------------------------------------------ parameter plumbing
+    def _masters(self) -> List[nn.Parameter]:
+        a, m = self.self_attn, self.mlp
+        return [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight, a.o_proj.weight, m.gate_proj.weight,
+                m.up_proj.weight, m.down_proj.weight, self.input_layernorm.weight,
+                self.post_attention_layernorm.weight]
+
+    def compute_weights(self):
+        """bf16 [q;k;v], o, [gate;up], down, ln1, ln2 — refreshed when any fp32 master changed."""
+        ps = self._masters()
+        vers = tuple(p._version for p in ps) + tuple(p.data_ptr() for p in ps)
+        if self._c is None or vers != self._versions:
+            h, f = self.hidden_size, self.inter
+            dev = ps[0].device
+            if self._c is None or self._c[0].device != dev:
+                self._c = (torch.empty(3 * h, h, dtype=torch.bfloat16, device=dev),
+                           torch.empty(h, h, dtype=torch.bfloat16, device=dev),
+                           torch.empty(2 * f, h, dtype=torch.bfloat16, device=dev),
+                           torch.empty(h, f, dtype=torch.bfloat16, device=dev),
+                           torch.empty(h, dtype=torch.bfloat16, device=dev),
+                           torch.empty(h, dtype=torch.bfloat16, device=dev))
+            wqkv, wo, wgu, wd, l1, l2 = self._c
+            with torch.no_grad():
+                ops.cast_bf16(ps[0], wqkv[:h]); ops.cast_bf16(ps[1], wqkv[h:2 * h]); ops.cast_bf16(ps[2], wqkv[2 * h:])
+                ops.cast_bf16(ps[3], wo)
+                ops.cast_bf16(ps[4], wgu[:f]); ops.cast_bf16(ps[5], wgu[f:])
+                ops.cast_bf16(ps[6], wd); ops.cast_bf16(ps[7], l1); ops.cast_bf16(ps[8], l2)
+            self._versions = vers
+        return self._c
+
+    def grad_arenas(self):
+        """fp32 [3h,h], [h,h], [2f,h], [h,f], [h], [h]; param.grad aliases views of these."""
+        ps = self._masters()
+        dev = ps[0].device
+        if self._g is None or self._g[0].device != dev:
+            h, f = self.hidden_size, self.inter
+            self._g = (torch.zeros(3 * h, h, dtype=torch.float32, device=dev),
+                       torch.zeros(h, h, dtype=torch.float32, device=dev),
+                       torch.zeros(2 * f, h, dtype=torch.float32, device=dev),
+                       torch.zeros(h, f, dtype=torch.float32, device=dev),
+                       torch.zeros(h, dtype=torch.float32, device=dev),
+                       torch.zeros(h, dtype=torch.float32, device=dev))
+            self._views = None
+        if getattr(self, "_views", None) is None:
+            h, f = self.hidden_size, self.inter
+            gqkv, go, ggu, gd, g1, g2 = self._g
+            self._views = [gqkv[:h], gqkv[h:2 * h], gqkv[2 * h:], go, ggu[:f], ggu[f:], gd, g1, g2]
+        return self._g
+
+    def _attach_grads(self) -> bool:
+        """Point param.grad at the arenas.  Returns True when the arenas hold live gradients to accumulate into
+        (i.e. the caller has not dropped/zeroed them since the last backward)."""
+        self.grad_arenas()
+        ps = self._masters()
+        live = all(p.grad is v for p, v in zip(ps, self._views)) and not self._grads_fresh
+        if not live:
+            for p, v in zip(ps, self._views):
+                if p.requires_grad:
+                    p.grad = v
+        return live
+
+    def mark_grads_fresh(self):
+        """Next backward overwrites the arenas instead of accumulating (cheaper than zeroing 0.8 GB per layer)."""
+        self._grads_fresh = True
+
+    # ------------------------------------------------------------------ compute
+    def _attn_half(self, x: torch.Tensor, sh: LayerShape, keep: bool):
+        wqkv, wo, _, _, l1, _ = self.compute_weights()
+        n1 = ops.rmsnorm_fwd(x, l1, self.eps)
+        qkv = ops.gemm(n1, wqkv)
+        ops.rope_(qkv, 0, 2 * sh.H, sh.D, sh.S, sh.cos, sh.sin)          # q and k heads are contiguous
+        ctx, lse = ops.attn_fwd(qkv, sh.B, sh.S, sh.H, sh.D, sh.mask)
+        x_mid = ops.gemm(ctx, wo, residual=x)
+        return n1, qkv, ctx, lse, x_mid
+
+    def _mlp_half(self, x_mid: torch.Tensor):
+        _, _, wgu, wd, _, l2 = self.compute_weights()
+        n2 = ops.rmsnorm_fwd(x_mid, l2, self.eps)
+        gu = ops.gemm(n2, wgu)
+        act = ops.swiglu_fwd(gu)
+        y = ops.gemm(act, wd, residual=x_mid)
+        return n2, gu, act, y
+
+    def forward_impl(self, x: torch.Tensor, sh: LayerShape, save_level: str):
+        n1, qkv, ctx, lse, x_mid = self._attn_half(x, sh, True)
+        n2, gu, act, y = self._mlp_half(x_mid)
+        if save_level == "layer":
+            saved = (x,)
+        elif save_level == "mlp":
+            saved = (x, qkv, ctx, lse, x_mid)
+        else:
+            saved = (x, qkv, ctx, lse, x_mid, gu)
+        return y, saved
+
+    def backward_impl(self, dy: torch.Tensor, saved: Tuple[torch.Tensor, ...], sh: LayerShape, save_level: str):
+        wqkv, wo, wgu, wd, l1, l2 = self.compute_weights()
+        x = saved[0]
+        if save_level == "layer":
+            n1, qkv, ctx, lse, x_mid = self._attn_half(x, sh, True)
+            n2, gu, act, _ = self._mlp_half_no_down(x_mid)
+        else:
+            qkv, ctx, lse, x_mid = saved[1:5]
+            n1 = ops.rmsnorm_fwd(x, l1, self.eps)
+            n2 = ops.rmsnorm_fwd(x_mid, l2, self.eps)
+            gu = saved[5] if save_level == "none" else ops.gemm(n2, wgu)
+            act = ops.swiglu_fwd(gu)
+        acc = self._attach_grads()
+        gqkv, go, ggu, gd, g1, g2 = self._g
+        if not acc:
+            g1.zero_(); g2.zero_()   # the norm-weight kernels accumulate atomically
+        # ---- MLP half
+        ops.gemm(dy, act, a_mn=True, b_mn=True, out=gd, accumulate=acc)              # dWd  = dy^T act
+        dact = ops.gemm(dy, wd, b_mn=True)                                           # dact = dy Wd
+        del act
+        dgu = ops.swiglu_bwd(dact, gu)
+        del dact, gu
+        ops.gemm(dgu, n2, a_mn=True, b_mn=True, out=ggu, accumulate=acc)             # dWgu = dgu^T n2
+        dn2 = ops.gemm(dgu, wgu, b_mn=True)                                          # dn2  = dgu Wgu
+        del dgu, n2
+        dx_mid = ops.rmsnorm_bwd(dn2, x_mid, l2, self.eps, dres=dy, dw=g2)
+        del dn2
+        # ---- attention half
+        ops.gemm(dx_mid, ctx, a_mn=True, b_mn=True, out=go, accumulate=acc)          # dWo  = dx_mid^T ctx
+        dctx = ops.gemm(dx_mid, wo, b_mn=True)
+        dqkv = ops.attn_bwd(dctx, qkv, ctx, lse, sh.B, sh.S, sh.H, sh.D, sh.mask)
+        del dctx, ctx, qkv
+        ops.rope_(dqkv, 0, 2 * sh.H, sh.D, sh.S, sh.cos, sh.sin, transpose=True)
+        ops.gemm(dqkv, n1, a_mn=True, b_mn=True, out=gqkv, accumulate=acc)           # dWqkv = dqkv^T n1
+        dn1 = ops.gemm(dqkv, wqkv, b_mn=True)
+        del dqkv, n1
+        dx = ops.rmsnorm_bwd(dn1, x, l1, self.eps, dres=dx_mid, dw=g1)
+        self._grads_fresh = False
+        return dx
+
+    def _mlp_half_no_down(self, x_mid: torch.Tensor):
+        _, _, wgu, _, _, l2 = self.compute_weights()
+        n2 = ops.rmsnorm_fwd(x_mid, l2, self.eps)
+        gu = ops.gemm(n2, wgu)
+        act = ops.swiglu_fwd(gu)
+        return n2, gu, act, None
+
+
+class _LayerFn(torch.autograd.Function):
+    """One autograd node per decoder layer.  `anchor` is a dummy that keeps the node alive when the layer input
+    itself does not require grad (e.g. everything upstream frozen)."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, layer: LlamaDecoderLayer, sh: LayerShape):
+        level = layer.save_level if torch.is_grad_enabled() or True else "layer"
+        y, saved = layer.forward_impl(x, sh, level)
+        ctx.layer, ctx.sh, ctx.level = layer, sh, level
+        ctx.save_for_backward(*saved)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx = ctx.layer.backward_impl(dy.contiguous(), ctx.saved_tensors, ctx.sh, ctx.level)
+        return dx, None, None, None
+
+
+class LlamaModel(nn.Module):
+    """embed_tokens / layers / norm — modeling_llama.py:912-940."""
+
+    def __init__(self, vocab_size: int, hidden: int, inter: int, n_layers: int, heads: int, eps: float = 1e-5,
+                 rope_theta: float = 10000.0, padding_idx: Optional[int] = None):
+        super().__init__()
+        self.hidden_size, self.heads, self.eps, self.rope_theta = hidden, heads, eps, rope_theta
+        self.embed_tokens = nn.Embedding(vocab_size, hidden, padding_idx)
+        self.layers = nn.ModuleList(LlamaDecoderLayer(hidden, inter, heads, eps, i) for i in range(n_layers))
+        self.norm = LlamaRMSNorm(hidden, eps)
+        self._rope_cache = {}
+        self._anchor = None
+
+    def rope_tables(self, S: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+        """bf16 cos/sin [S, D/2], computed as modeling_llama.py:132-145 does (fp32 outer product, cast to the
+        activation dtype); constant per (S, D, theta) so it is built once on the host and cached."""
+        D = self.hidden_size // self.heads
+        key = (S, D, str(device))
+        if key not in self._rope_cache:
+            inv_freq = 1.0 / (self.rope_theta ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))
+            pos = torch.arange(S, dtype=torch.int64).float()
+            freqs = (inv_freq[None, :, None] @ pos[None, None, :]).transpose(1, 2)[0]
+            self._rope_cache[key] = (freqs.cos().to(torch.bfloat16).to(device).contiguous(),
+                                     freqs.sin().to(torch.bfloat16).to(device).contiguous())
+        return self._rope_cache[key]
+
+    def set_save_levels(self, levels) -> None:
+        if isinstance(levels, str):
+            levels = [levels] * len(self.layers)
+        for l, lv in zip(self.layers, levels):
+            assert lv in SAVE_LEVELS, lv
+            l.save_level = lv
+
+    def mark_grads_fresh(self):
+        for l in self.layers:
+            l.mark_grads_fresh()
+
+    def run_layers(self, x: torch.Tensor, B: int, S: int, mask: Optional[torch.Tensor]) -> List[torch.Tensor]:
+        """x: bf16 [B*S, h].  Returns the list of hidden states (layer inputs + final normed), each [B*S, h]."""
+        D = self.hidden_size // self.heads
+        cos, sin = self.rope_tables(S, x.device)
+        sh = LayerShape(B, S, self.heads, D, mask, cos, sin)
+        if self._anchor is None or self._anchor.device != x.device:
+            self._anchor = torch.zeros(1, device=x.device, requires_grad=True)
+        hs = []
+        for layer in self.layers:
+            hs.append(x)
+            x = _LayerFn.apply(x, self._anchor, layer, sh)
+        hs.append(ops.RMSNormFn.apply(x, self.norm.weight, self.eps))
+        return hs

@@ -81,3 +81,376 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     g.pre_act = _ptr(pre_act)
     check(_lib.lib().mla_gemm_bf16(C.byref(g), _stream()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------- row kernels
+def _p(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(None if t is None else t.data_ptr())
+
+
+def rmsnorm_fwd(x: torch.Tensor, w: torch.Tensor, eps: float, *, mode: int = 0,
+                rstd: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: [..., h] bf16 (last dim contiguous, rows uniformly strided) -> same shape."""
+    _req(x, torch.bfloat16, "x")
+    _req(w, torch.bfloat16, "w")
+    h = x.shape[-1]
+    x2 = x.reshape(-1, h)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    o2 = out.view(-1, h)
+    check(_lib.lib().mla_rmsnorm_fwd(_p(x2), _p(w), _p(o2), _p(rstd), C.c_int64(x2.shape[0]), C.c_int32(h),
+                                     C.c_int64(x2.stride(0)), C.c_int64(o2.stride(0)), C.c_float(eps),
+                                     C.c_int32(mode), _stream()))
+    return out
+
+
+def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, w: torch.Tensor, eps: float, *,
+                dres: Optional[torch.Tensor] = None, dw: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Returns dx (+ dres); accumulates the weight gradient into dw (f32 [h]) when given."""
+    for t, n in ((dy, "dy"), (x, "x"), (w, "w")):
+        _req(t, torch.bfloat16, n)
+    h = x.shape[-1]
+    dy2, x2 = dy.reshape(-1, h), x.reshape(-1, h)
+    if not (dy2.is_contiguous() and x2.is_contiguous()):
+        raise _lib.MlaError("rmsnorm_bwd: dy and x must be contiguous")
+    if dres is not None:
+        _req(dres, torch.bfloat16, "dres")
+        if not dres.is_contiguous():
+            raise _lib.MlaError("rmsnorm_bwd: dres must be contiguous")
+    if dw is not None:
+        _req(dw, torch.float32, "dw")
+    dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().mla_rmsnorm_bwd(_p(dy2), _p(x2), _p(w), _p(dres), _p(dx), _p(dw), C.c_int64(x2.shape[0]),
+                                     C.c_int32(h), C.c_float(eps), _stream()))
+    return dx
+
+
+def rope_(buf: torch.Tensor, col0: int, heads: int, head_dim: int, seq: int, cos_t: torch.Tensor,
+          sin_t: torch.Tensor, transpose: bool = False) -> None:
+    """Rotate, in place, `heads` heads starting at column col0 of the 2-D buffer buf [tokens, ld]."""
+    _req(buf, torch.bfloat16, "buf")
+    ld = _rowmajor_2d(buf, "buf")
+    base = buf.data_ptr() + 2 * col0
+    check(_lib.lib().mla_rope_inplace(C.c_void_p(base), _p(cos_t), _p(sin_t), C.c_int64(buf.shape[0]), C.c_int32(seq),
+                                      C.c_int32(heads), C.c_int32(head_dim), C.c_int64(ld), C.c_int32(int(transpose)),
+                                      _stream()))
+
+
+def swiglu_fwd(gu: torch.Tensor) -> torch.Tensor:
+    _req(gu, torch.bfloat16, "gu")
+    rows, f2 = gu.shape
+    if not gu.is_contiguous():
+        raise _lib.MlaError("swiglu_fwd: gu must be contiguous")
+    out = torch.empty((rows, f2 // 2), dtype=torch.bfloat16, device=gu.device)
+    check(_lib.lib().mla_swiglu_fwd(_p(gu), _p(out), C.c_int64(rows), C.c_int32(f2 // 2), _stream()))
+    return out
+
+
+def swiglu_bwd(dact: torch.Tensor, gu: torch.Tensor) -> torch.Tensor:
+    _req(dact, torch.bfloat16, "dact")
+    _req(gu, torch.bfloat16, "gu")
+    rows, f2 = gu.shape
+    if not (gu.is_contiguous() and dact.is_contiguous()):
+        raise _lib.MlaError("swiglu_bwd: inputs must be contiguous")
+    dgu = torch.empty_like(gu)
+    check(_lib.lib().mla_swiglu_bwd(_p(dact), _p(gu), _p(dgu), C.c_int64(rows), C.c_int32(f2 // 2), _stream()))
+    return dgu
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def _attn_args(qkv: torch.Tensor, B: int, S: int, H: int, D: int, mask: Optional[torch.Tensor]) -> "_lib.AttnArgs":
+    _req(qkv, torch.bfloat16, "qkv")
+    ld = _rowmajor_2d(qkv, "qkv")
+    if qkv.shape[0] != B * S or qkv.shape[1] != 3 * H * D:
+        raise _lib.MlaError(f"attention: qkv shape {tuple(qkv.shape)} != [{B * S}, {3 * H * D}]")
+    a = _lib.AttnArgs()
+    base = qkv.data_ptr()
+    a.q, a.k, a.v = base, base + 2 * H * D, base + 4 * H * D
+    a.ld_qkv = ld
+    a.batch, a.seq, a.heads, a.head_dim = B, S, H, D
+    a.scale = D ** -0.5
+    if mask is not None:
+        if mask.dtype not in (torch.uint8, torch.bool) or not mask.is_contiguous() or tuple(mask.shape) != (B, S):
+            raise _lib.MlaError("attention: mask must be a contiguous uint8/bool [B,S] tensor")
+        a.mask = mask.data_ptr()
+    return a
+
+
+def attn_fwd(qkv: torch.Tensor, B: int, S: int, H: int, D: int, mask: Optional[torch.Tensor] = None):
+    """qkv: fused projection [B*S, 3*H*D] (q | k | v, RoPE already applied). Returns (ctx [B*S, H*D], lse [B,H,S])."""
+    a = _attn_args(qkv, B, S, H, D, mask)
+    ctx = torch.empty((B * S, H * D), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((B, H, S), dtype=torch.float32, device=qkv.device)
+    a.o, a.ld_o, a.lse = ctx.data_ptr(), ctx.stride(0), lse.data_ptr()
+    check(_lib.lib().mla_attn_fwd(C.byref(a), _stream()))
+    return ctx, lse
+
+
+def attn_bwd(dctx: torch.Tensor, qkv: torch.Tensor, ctx: torch.Tensor, lse: torch.Tensor, B: int, S: int, H: int,
+             D: int, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Returns d_qkv [B*S, 3*H*D] (dq | dk | dv) — gradients w.r.t. the post-RoPE q,k and v."""
+    a = _attn_args(qkv, B, S, H, D, mask)
+    _req(dctx, torch.bfloat16, "dctx")
+    if not (dctx.is_contiguous() and ctx.is_contiguous()):
+        raise _lib.MlaError("attention bwd: ctx / dctx must be contiguous")
+    dqkv = torch.empty_like(qkv, memory_format=torch.contiguous_format)
+    delta = torch.empty_like(lse)
+    a.o, a.ld_o, a.lse = ctx.data_ptr(), ctx.stride(0), lse.data_ptr()
+    a.d_o, a.delta = dctx.data_ptr(), delta.data_ptr()
+    base = dqkv.data_ptr()
+    a.dq, a.dk, a.dv = base, base + 2 * H * D, base + 4 * H * D
+    a.ld_dqkv = dqkv.stride(0)
+    check(_lib.lib().mla_attn_bwd(C.byref(a), _stream()))
+    return dqkv
+
+
+# ---------------------------------------------------------------------------------------------- casts / caches
+def cast_bf16(src: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 -> bf16 copy (contiguous)."""
+    _req(src, torch.float32, "src")
+    s = src.detach()
+    if not s.is_contiguous():
+        raise _lib.MlaError("cast_bf16: src must be contiguous")
+    if dst is None:
+        dst = torch.empty(s.shape, dtype=torch.bfloat16, device=s.device)
+    elif not dst.is_contiguous() or dst.numel() != s.numel():
+        raise _lib.MlaError("cast_bf16: dst must be contiguous with the same number of elements")
+    check(_lib.lib().mla_cast_f32_bf16(_p(s), _p(dst), C.c_int64(s.numel()), _stream()))
+    return dst
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+_BF16_CACHE: dict = {}
+
+
+def bf16_of(param: torch.Tensor, pad2d: bool = False) -> torch.Tensor:
+    """bf16 compute copy of an fp32 parameter, cached on (storage, version).  With pad2d a [N,K] matrix is copied
+    into a zero-padded [pad8(N), pad8(K)] buffer so that it satisfies the TMA 16-byte pitch rule."""
+    if param.dtype == torch.bfloat16 and not pad2d:
+        return param.detach()
+    key = (id(param), pad2d)
+    tag = (param.data_ptr(), param._version, tuple(param.shape), str(param.device))
+    hit = _BF16_CACHE.get(key)
+    if hit is not None and hit[0] == tag:
+        return hit[1]
+    p = param.detach()
+    if p.dtype != torch.float32:
+        p = p.float()
+    if pad2d and p.dim() == 2 and (p.shape[0] % 8 or p.shape[1] % 8):
+        n8, k8 = _pad8(p.shape[0]), _pad8(p.shape[1])
+        out = hit[1] if hit is not None and tuple(hit[1].shape) == (n8, k8) else torch.empty(
+            (n8, k8), dtype=torch.bfloat16, device=p.device)
+        p = p.contiguous()
+        check(_lib.lib().mla_cast_pad_f32_bf16(_p(p), _p(out), C.c_int64(n8), C.c_int64(k8), C.c_int64(p.shape[0]),
+                                               C.c_int64(p.shape[1]), C.c_int64(p.stride(0)), _stream()))
+    else:
+        out = hit[1] if hit is not None and hit[1].shape == p.shape else None
+        out = cast_bf16(p.contiguous(), out)
+    _BF16_CACHE[key] = (tag, out)
+    return out
+
+
+def pad_cols_bf16(x: torch.Tensor, k8: int) -> torch.Tensor:
+    """[M,K] f32/bf16 activations -> bf16 [M,k8] zero padded (inputs with K not a multiple of 8: 7-dof actions)."""
+    M, K = x.shape
+    xf = x.detach().float().contiguous()
+    out = torch.empty((M, k8), dtype=torch.bfloat16, device=x.device)
+    check(_lib.lib().mla_cast_pad_f32_bf16(_p(xf), _p(out), C.c_int64(M), C.c_int64(k8), C.c_int64(M), C.c_int64(K),
+                                           C.c_int64(K), _stream()))
+    return out
+
+
+def act_bwd(dy: torch.Tensor, pre: torch.Tensor, act: int) -> torch.Tensor:
+    dy = dy.contiguous()
+    dx = torch.empty_like(dy)
+    check(_lib.lib().mla_act_bwd(_p(dy), _p(pre), _p(dx), C.c_int64(dy.numel()), C.c_int32(act), _stream()))
+    return dx
+
+
+def colsum(x: torch.Tensor, n_cols: int) -> torch.Tensor:
+    out = torch.zeros(n_cols, dtype=torch.float32, device=x.device)
+    check(_lib.lib().mla_colsum_bf16(_p(x), _p(out), C.c_int64(x.shape[0]), C.c_int32(n_cols), C.c_int64(x.stride(0)),
+                                     _stream()))
+    return out
+
+
+def add_bf16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    a, b = a.contiguous(), b.contiguous()
+    out = torch.empty_like(a)
+    check(_lib.lib().mla_add_bf16(_p(a), _p(b), _p(out), C.c_int64(a.numel()), _stream()))
+    return out
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) on the tcgen05 GEMM; x bf16 [M,K], W/b fp32 parameters (bf16 compute copies cached).
+    Gradients: dx bf16, dW/db fp32 returned to autograd (these are the small non-decoder modules)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        M, K = x.shape
+        N = weight.shape[0]
+        padded = bool(K % 8 or N % 8)
+        w = bf16_of(weight, pad2d=True)
+        N8, K8 = w.shape
+        xin = x
+        if K8 != K:
+            xin = torch.zeros((M, K8), dtype=torch.bfloat16, device=x.device)
+            xin[:, :K] = x
+        b = None
+        if bias is not None:
+            b = bf16_of(bias)
+            if N8 != N:
+                bp = torch.zeros(N8, dtype=torch.bfloat16, device=x.device)
+                bp[:N] = b
+                b = bp
+        pre = torch.empty((M, N8), dtype=torch.bfloat16, device=x.device) if act != ACT_NONE else None
+        y = gemm(xin, w, bias=b, act=act, pre_act=pre)
+        ctx.save_for_backward(xin, pre)
+        ctx.weight, ctx.act, ctx.has_bias, ctx.dims = weight, act, bias is not None, (M, N, K, N8, K8)
+        ctx.x_needs = x.requires_grad
+        return y[:, :N] if padded and N8 != N else y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xin, pre = ctx.saved_tensors
+        M, N, K, N8, K8 = ctx.dims
+        if N8 != N:
+            d = torch.zeros((M, N8), dtype=torch.bfloat16, device=dy.device)
+            d[:, :N] = dy
+            dy = d
+        else:
+            dy = dy.contiguous()
+        if ctx.act != ACT_NONE:
+            dy = act_bwd(dy, pre, ctx.act)
+        w = bf16_of(ctx.weight, pad2d=True)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dy, w, b_mn=True)
+            if K8 != K:
+                dx = dx[:, :K]
+        if ctx.needs_input_grad[1]:
+            dW = gemm(dy, xin, a_mn=True, b_mn=True, out_dtype=torch.float32)
+            if N8 != N or K8 != K:
+                dW = dW[:N, :K].contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy, N8)[:N]
+        return dx, dW, db, None
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE):
+    """nn.Linear (+activation) over the last dim; x any leading shape, bf16."""
+    lead = x.shape[:-1]
+    y = LinearFn.apply(x.reshape(-1, x.shape[-1]), weight, bias, act)
+    return y.reshape(*lead, weight.shape[0])
+
+
+class RMSNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, eps, mode=0):
+        w = bf16_of(weight)
+        ctx.save_for_backward(x)
+        ctx.weight, ctx.eps, ctx.mode = weight, eps, mode
+        return rmsnorm_fwd(x, w, eps, mode=mode)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        if ctx.mode != 0:
+            raise _lib.MlaError("RMSNorm backward is implemented for the mean-square mode only")
+        dw = torch.zeros(x.shape[-1], dtype=torch.float32, device=x.device)
+        dx = rmsnorm_bwd(dy.contiguous(), x.contiguous(), bf16_of(ctx.weight), ctx.eps, dw=dw)
+        return dx, dw, None, None
+
+
+# ---------------------------------------------------------------------------------------------- gather / scatter
+def gather_rows(src: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """src bf16 [R,h]; idx int32/int64 [n] (negative -> zero row) -> [n,h]."""
+    _req(src, torch.bfloat16, "src")
+    lds = _rowmajor_2d(src, "src")
+    n, h = idx.numel(), src.shape[1]
+    dst = torch.empty((n, h), dtype=torch.bfloat16, device=src.device)
+    check(_lib.lib().mla_gather_rows(_p(src), _p(idx), _p(dst), C.c_int64(n), C.c_int32(h), C.c_int64(lds),
+                                     C.c_int32(int(idx.dtype == torch.int64)), _stream()))
+    return dst
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """dst = src[idx] with an injective int32 idx (sequence splice); backward is the inverse permutation."""
+
+    @staticmethod
+    def forward(ctx, src, idx):
+        ctx.save_for_backward(idx)
+        ctx.rows = src.shape[0]
+        return gather_rows(src, idx)
+
+    @staticmethod
+    def backward(ctx, d):
+        (idx,) = ctx.saved_tensors
+        d = d.contiguous()
+        dsrc = torch.zeros((ctx.rows, d.shape[1]), dtype=torch.bfloat16, device=d.device)
+        check(_lib.lib().mla_scatter_rows(_p(dsrc), _p(idx), _p(d), C.c_int64(d.shape[0]), C.c_int32(d.shape[1]),
+                                          C.c_int64(dsrc.stride(0)), _stream()))
+        return dsrc, None
+
+
+class EmbeddingFn(torch.autograd.Function):
+    """nn.Embedding lookup from the bf16 compute copy; backward scatter-adds into an fp32 gradient."""
+
+    @staticmethod
+    def forward(ctx, ids, weight, padding_idx):
+        ctx.save_for_backward(ids)
+        ctx.weight, ctx.padding_idx = weight, padding_idx
+        return gather_rows(bf16_of(weight), ids.reshape(-1).contiguous())
+
+    @staticmethod
+    def backward(ctx, d):
+        (ids,) = ctx.saved_tensors
+        w = ctx.weight
+        d = d.contiguous()
+        g = torch.zeros(w.shape, dtype=torch.float32, device=d.device)
+        pad = -1 if ctx.padding_idx is None else int(ctx.padding_idx)
+        check(_lib.lib().mla_embedding_bwd(_p(g), _p(ids.reshape(-1).contiguous()), _p(d), C.c_int64(d.shape[0]),
+                                           C.c_int32(d.shape[1]), C.c_int64(pad), _stream()))
+        return None, g, None
+
+
+class MSEFn(torch.autograd.Function):
+    """mean((pred - target)^2) with bf16 pred and fp32 target -> fp32 scalar (models/mla/model_mla.py:215)."""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        pred = pred.contiguous()
+        target = target.contiguous()
+        ctx.save_for_backward(pred, target)
+        loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+        check(_lib.lib().mla_mse_fwd(_p(pred), _p(target), _p(loss), C.c_int64(pred.numel()), _stream()))
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        pred, target = ctx.saved_tensors
+        gs = g.reshape(1).float().contiguous()
+        dp = torch.empty_like(pred)
+        check(_lib.lib().mla_mse_bwd(_p(pred), _p(target), _p(gs), _p(dp), C.c_int64(pred.numel()), _stream()))
+        return dp, None
+
+
+def layernorm(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float) -> torch.Tensor:
+    """nn.LayerNorm over the last dim; x bf16 [rows,h] contiguous, w/b fp32. Forward only (frozen tokenizer)."""
+    _req(x, torch.bfloat16, "x")
+    y = torch.empty_like(x)
+    h = x.shape[-1]
+    check(_lib.lib().mla_layernorm_fwd(_p(x), _p(w.detach()), _p(b.detach()), _p(y), C.c_int64(x.numel() // h),
+                                       C.c_int32(h), C.c_float(eps), _stream()))
+    return y
+
+
+def q_sample(a: torch.Tensor, noise: torch.Tensor, t: torch.Tensor, sqrt_ac: torch.Tensor, sqrt_1mac: torch.Tensor):
+    a, noise = a.contiguous(), noise.contiguous()
+    out = torch.empty_like(a)
+    check(_lib.lib().mla_q_sample(_p(a), _p(noise), _p(t), _p(sqrt_ac), _p(sqrt_1mac), _p(out), C.c_int64(a.numel()),
+                                  C.c_int32(a.numel() // a.shape[0]), _stream()))
+    return out

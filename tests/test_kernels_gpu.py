@@ -1,0 +1,170 @@
+"""GPU parity of the individual kernels against the oracle (oracle/llama.py), called through the C ABI."""
+import math
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("rows,h", [(7, 128), (300, 4096), (33, 1024)])
+def test_rmsnorm_fwd_bwd(cuda_lib, rows, h):
+    from mla_b200 import ops
+    from oracle import llama as O
+    torch.manual_seed(1)
+    x = _bf(torch.randn(rows, h, device="cuda") * 2)
+    w = _bf(1 + 0.1 * torch.randn(h, device="cuda"))
+    y = ops.rmsnorm_fwd(x, w, 1e-5)
+    y_ref = O.rmsnorm(x, w, 1e-5)
+    assert torch.equal(y, y_ref) or rel_err(y, y_ref) < 2e-3, rel_err(y, y_ref)
+    # backward against fp32 autograd of the oracle
+    xf = x.float().requires_grad_(True)
+    wf = w.float().requires_grad_(True)
+    dy = _bf(torch.randn(rows, h, device="cuda"))
+    O.rmsnorm(xf, wf, 1e-5).backward(dy.float())
+    dres = _bf(torch.randn(rows, h, device="cuda"))
+    dw = torch.zeros(h, device="cuda")
+    dx = ops.rmsnorm_bwd(dy, x, w, 1e-5, dres=dres, dw=dw)
+    assert rel_err(dx, xf.grad + dres.float()) < 6e-3
+    assert rel_err(dw, wf.grad) < 6e-3
+
+
+@pytest.mark.parametrize("B,S,H,D", [(2, 44, 4, 32), (2, 70, 2, 128)])
+def test_rope_matches_reference_rounding(cuda_lib, B, S, H, D):
+    from mla_b200 import ops
+    from oracle import llama as O
+    torch.manual_seed(2)
+    h = H * D
+    qkv = _bf(torch.randn(B * S, 3 * h, device="cuda"))
+    cos, sin = O.rope_tables(S, D, 10000.0, torch.bfloat16)
+    cos, sin = cos.cuda(), sin.cuda()
+    q = qkv[:, :h].view(B, S, H, D).transpose(1, 2)
+    k = qkv[:, h:2 * h].view(B, S, H, D).transpose(1, 2)
+    q_ref, k_ref = O.apply_rope(q, k, cos, sin)
+    buf = qkv.clone()
+    ops.rope_(buf, 0, 2 * H, D, S, cos[:, :D // 2].contiguous(), sin[:, :D // 2].contiguous())
+    q_got = buf[:, :h].view(B, S, H, D).transpose(1, 2)
+    k_got = buf[:, h:2 * h].view(B, S, H, D).transpose(1, 2)
+    assert torch.equal(q_got, q_ref), rel_err(q_got, q_ref)   # bit-exact: same rounding points
+    assert torch.equal(k_got, k_ref)
+    assert torch.equal(buf[:, 2 * h:], qkv[:, 2 * h:])          # v untouched
+    # transpose(rotation) o rotation ~ identity
+    ops.rope_(buf, 0, 2 * H, D, S, cos[:, :D // 2].contiguous(), sin[:, :D // 2].contiguous(), transpose=True)
+    assert rel_err(buf[:, :2 * h], qkv[:, :2 * h]) < 1e-2
+
+
+def test_swiglu_fwd_bwd(cuda_lib):
+    from mla_b200 import ops
+    torch.manual_seed(3)
+    rows, f = 37, 352
+    gu = _bf(torch.randn(rows, 2 * f, device="cuda") * 2)
+    out = ops.swiglu_fwd(gu)
+    g, u = gu[:, :f], gu[:, f:]
+    ref = torch.nn.functional.silu(g) * u
+    assert torch.equal(out, ref), rel_err(out, ref)
+    gf = gu.float().requires_grad_(True)
+    (torch.nn.functional.silu(gf[:, :f]) * gf[:, f:]).backward(torch.ones(rows, f, device="cuda"))
+    d = ops.swiglu_bwd(_bf(torch.ones(rows, f, device="cuda")), gu)
+    assert rel_err(d, gf.grad) < 8e-3
+
+
+@pytest.mark.parametrize("B,S,H,D,masked", [(2, 44, 4, 32, False), (2, 150, 2, 128, False), (3, 131, 2, 64, True),
+                                             (2, 548, 2, 128, True)])
+def test_attention_fwd_bwd(cuda_lib, B, S, H, D, masked):
+    from mla_b200 import ops
+    from oracle import llama as O
+    torch.manual_seed(4)
+    h = H * D
+    qkv = _bf(torch.randn(B * S, 3 * h, device="cuda"))
+    mask = None
+    if masked:
+        mask = torch.ones(B, S, dtype=torch.bool, device="cuda")
+        mask[0, S - 7:] = False          # right padding
+        mask[1, S // 2: S // 2 + 3] = False  # a hole (general mask semantics)
+    ctx, lse = ops.attn_fwd(qkv, B, S, H, D, mask)
+
+    def split(t):
+        return [t[:, i * h:(i + 1) * h].reshape(B, S, H, D).transpose(1, 2) for i in range(3)]
+    qf = qkv.float().requires_grad_(True)
+    q, k, v = split(qf)
+    ref = O.attention(q, k, v, mask)              # fp32 truth
+    ref_bf = O.attention(*split(qkv), mask)       # bf16 path
+    got = ctx.view(B, S, h)
+    assert rel_err(got, ref) < 1e-2, rel_err(got, ref)
+    assert rel_err(got, ref_bf) < 6e-3, rel_err(got, ref_bf)
+    if masked:
+        assert got[0, S - 7:].abs().max() == 0
+    dctx = _bf(torch.randn(B * S, h, device="cuda"))
+    ref.backward(dctx.view(B, S, h).float())
+    dqkv = ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, mask)
+    for i, name in enumerate("qkv"):
+        e = rel_err(dqkv[:, i * h:(i + 1) * h], qf.grad[:, i * h:(i + 1) * h])
+        assert e < 1.5e-2, (name, e)
+
+
+def test_gather_scatter_embedding(cuda_lib):
+    from mla_b200 import ops
+    torch.manual_seed(5)
+    src = _bf(torch.randn(50, 64, device="cuda")).requires_grad_(True)
+    idx = torch.randperm(50, device="cuda")[:30].to(torch.int32)
+    idx[3] = -1
+    out = ops.GatherRowsFn.apply(src, idx)
+    ref = src.detach()[idx.clamp(min=0).long()]
+    ref[3] = 0
+    assert torch.equal(out, ref)
+    out.backward(torch.ones_like(out))
+    exp = torch.zeros(50, 64, device="cuda")
+    exp[idx[idx >= 0].long()] = 1
+    assert torch.equal(src.grad.float(), exp)
+    w = torch.randn(40, 64, device="cuda", requires_grad=True)
+    ids = torch.tensor([[1, 2, 2, 39]], device="cuda")
+    e = ops.EmbeddingFn.apply(ids, w, None)
+    assert torch.equal(e, _bf(w.detach())[ids.view(-1)])
+    e.backward(torch.ones_like(e))
+    assert w.grad[2].eq(2).all() and w.grad[1].eq(1).all() and w.grad[0].eq(0).all()
+
+
+@pytest.mark.parametrize("K,N,act", [(64, 128, 0), (7, 128, 3), (128, 7, 3), (256, 64, 4), (12, 64, 2)])
+def test_linear_fn(cuda_lib, K, N, act):
+    from mla_b200 import ops
+    torch.manual_seed(6)
+    M = 45
+    x = _bf(torch.randn(M, K, device="cuda")).requires_grad_(True)
+    w = (torch.randn(N, K, device="cuda") * 0.2).requires_grad_(True)
+    b = (torch.randn(N, device="cuda") * 0.2).requires_grad_(True)
+    y = ops.linear(x, w, b, act)
+    xf, wf, bf_ = x.detach().float().requires_grad_(True), _bf(w.detach()).float().requires_grad_(True), _bf(b.detach()).float().requires_grad_(True)
+    pre = torch.nn.functional.linear(xf, wf, bf_)
+    F = torch.nn.functional
+    ref = {0: lambda t: t, 1: F.relu, 2: F.gelu, 3: lambda t: F.gelu(t, approximate="tanh"), 4: F.silu}[act](pre)
+    assert rel_err(y, ref) < 6e-3
+    dy = _bf(torch.randn(M, N, device="cuda"))
+    y.backward(dy)
+    ref.backward(dy.float())
+    assert rel_err(x.grad, xf.grad) < 1.2e-2
+    assert rel_err(w.grad, wf.grad) < 1.2e-2
+    assert rel_err(b.grad, bf_.grad) < 1.2e-2
+
+
+def test_mse_and_qsample(cuda_lib):
+    from mla_b200 import ops
+    torch.manual_seed(7)
+    pred = _bf(torch.randn(32, 1, 7, device="cuda")).requires_grad_(True)
+    tgt = torch.randn(32, 1, 7, device="cuda")
+    loss = ops.MSEFn.apply(pred, tgt)
+    ref = ((pred.detach() - tgt) ** 2).mean()
+    assert abs(loss.item() - ref.item()) < 1e-6 * max(1, abs(ref.item()))
+    (loss * 3).backward()
+    gref = 3 * 2 * (pred.detach().float() - tgt) / tgt.numel()
+    assert rel_err(pred.grad, gref) < 5e-3
+    a, n = torch.randn(32, 1, 7, device="cuda"), torch.randn(32, 1, 7, device="cuda")
+    t = torch.randint(0, 100, (32,), device="cuda")
+    sa, sb = torch.rand(100, device="cuda"), torch.rand(100, device="cuda")
+    x = ops.q_sample(a, n, t, sa, sb)
+    assert torch.allclose(x, sa[t].view(-1, 1, 1) * a + sb[t].view(-1, 1, 1) * n, atol=1e-6)
