@@ -145,6 +145,53 @@ int mla_mse_fwd(const void* pred, const void* target, void* loss, int64_t n, voi
 int mla_mse_bwd(const void* pred, const void* target, const void* gscale, void* dpred, int64_t n, void* stream);
 int mla_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
 
+/* ---- image tokenizer (models/mla/image/vision_tokenizer.py) ----------------------------------------------------
+ * mla_patchify: im2col of nn.Conv2d(3,C,patch,patch) (:112,:124): pixels f32 [B,c_total,H,W] (first 3 channels) ->
+ *   bf16 [B*(H/patch)*(W/patch), k_pad], rows window-major ((b*G+g)*cs^2 + n), column = c*patch^2 + ky*patch + kx.
+ * mla_window_mean: F.avg_pool2d(features, cs, cs) (:28) on window-major rows: [groups*win, c] -> [groups, c].
+ * mla_local_attn: the 9-way attention of LocalAttention.forward (:40-45): q [groups,c], kv [groups*win, 2c]. */
+int mla_patchify(const void* pixels, void* out, int32_t batch, int32_t c_total, int32_t himg, int32_t wimg,
+                 int32_t patch, int32_t conv_stride, int32_t k_pad, void* stream);
+int mla_window_mean(const void* x, void* out, int64_t groups, int32_t c, int32_t win, void* stream);
+int mla_local_attn(const void* q, const void* kv, void* out, int64_t groups, int32_t c, int32_t heads, int32_t win,
+                   float scale, void* stream);
+
+/* ---- multimodal sequence splice (models/vlm/prismatic.py:949-1042,:1121-1124) -----------------------------------
+ * Builds, without host syncs, the row map of [BOS | fused(n_fused) | text.. | proprio,t,x.. | EOS..] per sample:
+ * src_idx int32 [B,S] into a row table (text at text_base+b*lt+j, fused at fused_base+b*n_fused+j, inserted rows at
+ * ins_base+b*n_ins+j), the fused attention mask uint8 [B,S], labels int64 [B,S] (optional), lti int32 [B] and the
+ * flat rows of the n_x noisy-action tokens (head_rows int32 [B,n_x]).  S = n_fused + lt + n_ins.  err_flag (int32)
+ * is set to 1 if a sample has no `eos_id` (the reference raises IndexError at :983). */
+int mla_splice_index(const void* input_ids, const void* attn_mask, const void* labels, int32_t batch, int32_t lt,
+                     int32_t n_fused, int32_t n_ins, int32_t n_x, int64_t eos_id, int32_t text_base,
+                     int32_t fused_base, int32_t ins_base, void* src_idx, void* mask_out, void* labels_out,
+                     void* lti_out, void* head_rows, void* err_flag, void* stream);
+
+/* ---- InfoNCE alignment losses (models/mla/fuser/contrastive.py) and patch correspondence ---------------------------
+ * l2norm: F.normalize(p=2, dim=-1) (:192-193), fp32 math, bf16 out, norms f32 [rows] saved for backward.
+ * infonce: CoordinateAwareContrastiveLoss.forward (:196-215) on a materialised bf16 similarity matrix sim [n,n]
+ *   (sim = a . b^T from mla_gemm_bf16); rows/cols with valid[i] == 0 are excluded (the reference compacts them away);
+ *   out[0] = (CE(rows) + CE(cols)) / 2, out[1] = M (#valid).  bwd overwrites sim with d(loss)/d(sim) (bf16).
+ * tac_nce: TactileContrastiveLoss (:241-258), one (query, 256 keys, positive index) problem per (batch, arm);
+ *   loss_rows f32 [batch*arms] (mean them), probs f32 [batch*arms, k]; bwd: dq f32 [batch*arms,d], dkeys f32 += .
+ * project_points: project_3d_to_2d_672_* (:5-131): xyz f32 [n,3]; cam f32 [21] = R(9) | t(3) | K(9);
+ *   patch_idx int64 [n,2] = (row, col) clamped, valid uint8 [n]. */
+int mla_l2norm_fwd(const void* x, void* y, void* norms, int64_t rows, int32_t d, int64_t ldx, float eps, void* stream);
+int mla_l2norm_bwd(const void* x, const void* norms, const void* dy, void* dx, int64_t rows, int32_t d, int64_t ldx,
+                   void* stream);
+size_t mla_infonce_workspace(int32_t n);
+int mla_infonce_fwd(const void* sim, const void* valid, void* workspace, void* out, int32_t n, float temperature,
+                    void* stream);
+int mla_infonce_bwd(void* sim_inout, const void* valid, const void* workspace, const void* out, const void* gscale,
+                    int32_t n, float temperature, void* stream);
+int mla_tac_nce_fwd(const void* q, const void* keys, const void* pos, void* probs, void* loss_rows, int32_t batch,
+                    int32_t arms, int32_t k, int32_t d, float temperature, void* stream);
+int mla_tac_nce_bwd(const void* q, const void* keys, const void* pos, const void* probs, const void* gscale, void* dq,
+                    void* dkeys, int32_t batch, int32_t arms, int32_t k, int32_t d, float temperature, void* stream);
+int mla_project_points(const void* xyz, const void* cam, int64_t n, float sx, float sy, float total_stride,
+                       int32_t patch_h, int32_t patch_w, float img_w, float img_h, void* patch_idx, void* valid,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

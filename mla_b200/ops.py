@@ -231,8 +231,10 @@ def bf16_of(param: torch.Tensor, pad2d: bool = False) -> torch.Tensor:
     into a zero-padded [pad8(N), pad8(K)] buffer so that it satisfies the TMA 16-byte pitch rule."""
     if param.dtype == torch.bfloat16 and not pad2d:
         return param.detach()
-    key = (id(param), pad2d)
-    tag = (param.data_ptr(), param._version, tuple(param.shape), str(param.device))
+    # keyed on the storage (kept alive by the entry, so its address cannot be recycled under us) + view geometry
+    st = param.untyped_storage()
+    key = (st._cdata, param.storage_offset(), tuple(param.shape), tuple(param.stride()), pad2d)
+    tag = (param._version, str(param.device), param.dtype)
     hit = _BF16_CACHE.get(key)
     if hit is not None and hit[0] == tag:
         return hit[1]
@@ -249,8 +251,12 @@ def bf16_of(param: torch.Tensor, pad2d: bool = False) -> torch.Tensor:
     else:
         out = hit[1] if hit is not None and hit[1].shape == p.shape else None
         out = cast_bf16(p.contiguous(), out)
-    _BF16_CACHE[key] = (tag, out)
+    _BF16_CACHE[key] = (tag, out, st)
     return out
+
+
+def clear_bf16_cache() -> None:
+    _BF16_CACHE.clear()
 
 
 def pad_cols_bf16(x: torch.Tensor, k8: int) -> torch.Tensor:

@@ -1,0 +1,323 @@
+"""PrismaticVLM: multimodal fusion + LLM + diffusion head — drop-in for models/vlm/prismatic.py:148-1144.
+
+Same constructor flags, attribute names, module keys (`all_module_keys`, `trainable_module_keys`), `freeze_backbones`
+stages and `forward` returns as the reference; the compute is libmla_b200 kernels:
+
+    tokenizers/projectors -> splice [BOS | pc | img (| views) | tac | text | proprio,t,x | EOS] (one index kernel +
+    one row gather, no per-sample python loop or .item() sync, prismatic.py:981-1038) -> decoder stack ->
+    FinalLayer on the T+1 noisy-action rows only (the reference runs it on all S rows and slices, :1117-1126 —
+    row-wise ops, identical values).
+
+Post-training generation heads (models/mla/generation, config 5) are not built yet: `use_generation=True` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from functools import partial
+from typing import Callable, Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from ._lib import check
+from .backbone import CausalLMOutputWithPast, LLMBackbone
+from .contrastive import get_camera_params, project_points
+from .modules import (ActionEmbedder, FinalLayer, LabelEmbedder, MLP_GELU, MLPProjector, TimestepEmbedder)
+from .vision import VisionTokenizer
+
+IGNORE_INDEX = -100
+
+
+class PrismaticVLM(nn.Module):
+    def __init__(self, model_id: str, llm_backbone: LLMBackbone, enable_mixed_precision_training: bool = True,
+                 action_dim: int = 7, token_size: int = 4096, future_action_window_size: int = 0,
+                 past_action_window_size: int = 0, class_dropout_prob: float = 0.0, norm_stats=None,
+                 use_diff: bool = False, use_pointcloud: bool = False, use_tactile: bool = False,
+                 use_contrastive: bool = False, llm_vision_layers: int = 1, use_generation: bool = True,
+                 gen_image: bool = False, gen_pointcloud: bool = True, gen_tactile: bool = True,
+                 use_roi: bool = False, image_hidden_dim: int = 1024, **kwargs) -> None:
+        super().__init__()
+        self.model_family, self.model_id = "prismatic", model_id
+        self.llm_backbone = llm_backbone
+        self.enable_mixed_precision_training = enable_mixed_precision_training
+        self.token_size = token_size
+        self.use_diff, self.use_pointcloud, self.use_tactile = use_diff, use_pointcloud, use_tactile
+        self.use_contrastive, self.llm_vision_layers = use_contrastive, llm_vision_layers
+        self.use_generation = use_generation
+        self.gen_image = gen_image and use_generation
+        self.use_roi = use_roi
+        self.gen_pointcloud = gen_pointcloud and use_generation
+        self.gen_tactile = gen_tactile and use_generation
+        if use_generation and (self.gen_image or self.gen_pointcloud or self.gen_tactile):
+            raise NotImplementedError("post-training generation heads (config 5) are not built yet; pass "
+                                      "use_generation=False (pretrain / SFT stages)")
+
+        # prismatic.py:208-212 — likelihood helper tokens
+        self.string2idx = {}
+        for s in ["True", "False", "Yes", "No"] + [chr(ord("A") + i) for i in range(26)]:
+            ids = self.llm_backbone.tokenizer.encode(s, add_special_tokens=False)
+            assert len(ids) == 1, f'String "{s}" is tokenized as more than one token!'
+            self.string2idx[s] = ids[0]
+
+        self.norm_stats = norm_stats
+        self.class_dropout_prob = class_dropout_prob
+        self.future_action_window_size = future_action_window_size
+        self.action_dim = action_dim
+
+        self.image_hidden_dim = image_hidden_dim
+        self.vision_tower_2d = VisionTokenizer(input_size=self.image_hidden_dim)
+        self.projector_2d = MLP_GELU(self.image_hidden_dim, token_size, 2)
+        if self.use_pointcloud:
+            from .pointcloud import PointTokenizer
+            self.vision_tower_3d = PointTokenizer(in_channels=3, embed_dim=768, depth=12, num_heads=12)
+            self.projector_3d = MLPProjector(self.vision_tower_3d.embed_dim, token_size)
+        if self.use_tactile:
+            self.tactile_dim = 12
+            self.tactile_embedder = ActionEmbedder(action_size=self.tactile_dim, hidden_size=token_size)
+        self.proprio_embedder = ActionEmbedder(action_size=action_dim, hidden_size=token_size)
+        if self.use_diff:
+            self.x_embedder = ActionEmbedder(action_size=action_dim, hidden_size=token_size)
+            self.t_embedder = TimestepEmbedder(token_size)
+            self.z_embedder = LabelEmbedder(in_size=token_size, hidden_size=token_size, dropout_prob=class_dropout_prob)
+            self.final_layer = FinalLayer(token_size, action_dim)
+
+        self.all_module_keys = ["vision_tower_2d", "projector_2d", "llm_backbone", "proprio_embedder"]
+        if self.use_diff:
+            self.all_module_keys.extend(["x_embedder", "t_embedder", "final_layer"])
+        if self.use_pointcloud:
+            self.all_module_keys.extend(["vision_tower_3d", "projector_3d"])
+        if self.use_tactile:
+            self.all_module_keys.extend(["tactile_embedder"])
+        self.trainable_module_keys: List[str] = []
+        self.vision_backbone_requires_grad = False
+        self.initialize_weights()
+        if self.use_pointcloud:
+            self.vision_tower_3d.initialize_weights()
+        self._err_flag = None
+
+    # ------------------------------------------------------------------ reference API surface
+    def get_vision_tower_2d(self):
+        return self.vision_tower_2d
+
+    def encode_images(self, images):
+        return self.vision_tower_2d(images, self.projector_2d)
+
+    def initialize_weights(self):
+        """prismatic.py:299-321 — xavier-uniform for every nn.Linear (the LLM included, as `self.apply` does),
+        unit LayerNorm, N(0, 0.02) embedders, zero-initialised final projection."""
+        def _basic_init(m):
+            if isinstance(m, nn.Linear):
+                torch.nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.weight, 1.0)
+                nn.init.constant_(m.bias, 0)
+        self.apply(_basic_init)
+        if self.use_diff:
+            nn.init.normal_(self.x_embedder.mlp.fc1.weight, std=0.02)
+            nn.init.normal_(self.x_embedder.mlp.fc2.weight, std=0.02)
+            nn.init.normal_(self.proprio_embedder.mlp.fc1.weight, std=0.02)
+            nn.init.normal_(self.proprio_embedder.mlp.fc2.weight, std=0.02)
+            nn.init.normal_(self.t_embedder.mlp[0].weight, std=0.02)
+            nn.init.normal_(self.t_embedder.mlp[2].weight, std=0.02)
+            nn.init.constant_(self.final_layer.mlp.fc2.weight, 0)
+            nn.init.constant_(self.final_layer.mlp.fc2.bias, 0)
+
+    def freeze_backbones(self, stage: str) -> None:
+        """prismatic.py:415-536."""
+        if stage not in {"pretrain", "finetune", "post-training"}:
+            raise ValueError(f"Stage `{stage}` is not supported! Try < pretrain | finetune | post-training >")
+        train_towers = stage == "pretrain"
+        self.vision_tower_2d.requires_grad_(train_towers)
+        self.llm_backbone.requires_grad_(True)
+        self.projector_2d.requires_grad_(True)
+        if self.use_pointcloud:
+            self.vision_tower_3d.requires_grad_(train_towers)
+            self.projector_3d.requires_grad_(True)
+        if self.use_tactile:
+            self.tactile_embedder.requires_grad_(True)
+        if stage == "finetune":
+            keys = ["llm_backbone", "projector_2d", "proprio_embedder"]
+            if self.use_diff:
+                keys += ["x_embedder", "t_embedder", "final_layer"]
+            if self.use_pointcloud:
+                keys += ["projector_3d"]
+            if self.use_tactile:
+                keys += ["tactile_embedder"]
+        else:
+            keys = ["vision_tower_2d", "projector_2d", "llm_backbone", "proprio_embedder"]
+            if self.use_diff:
+                keys += ["x_embedder", "t_embedder", "final_layer"]
+            if self.use_pointcloud:
+                keys += ["vision_tower_3d", "projector_3d"]
+            if self.use_tactile:
+                keys += ["tactile_embedder"]
+        self.trainable_module_keys = keys
+        self.vision_backbone_requires_grad = train_towers
+
+    def get_fsdp_wrapping_policy(self) -> Callable:
+        from torch.distributed.fsdp.wrap import _module_wrap_policy, _or_policy
+        from .pointcloud import PointTokenizer
+        return partial(_or_policy, policies=[
+            partial(_module_wrap_policy, module_classes={PointTokenizer, VisionTokenizer}),
+            self.llm_backbone.get_fsdp_wrapping_policy(),
+            partial(_module_wrap_policy, module_classes={MLP_GELU}),
+        ])
+
+    # ------------------------------------------------------------------ fusion
+    def _image_tokens(self, px: torch.Tensor, repeat: int) -> torch.Tensor:
+        """[B,4,H,W] -> bf16 [B*repeat, n_tok, token]; the frozen tokenizer runs once per distinct image."""
+        pooled, h, w = self.vision_tower_2d.pooled_features(px)
+        tok = self.projector_2d(pooled).view(px.shape[0], h * w, -1)
+        if repeat > 1:
+            tok = tok.repeat(repeat, 1, 1)
+        return tok
+
+    def get_fused_tokens(self, images, pointcloud, tactile, gripper_xyz, camera_name, image_repeat: int = 1):
+        """prismatic.py:598-769.  Returns (fused [B, F, token], patch_indices [B,N,2] i64, valid_mask [B,N] bool,
+        positive_pc_indices_for_tac, linear_positive_img_indices_for_tac, pointcloud_centers)."""
+        views = images if isinstance(images, dict) else {"front_image": images}
+        assert "front_image" in views, "front_image must be present in multi-view images"
+        dev = self.llm_backbone.llm.lm_head.weight.device
+        front = self._image_tokens(views["front_image"].to(dev, non_blocking=True), image_repeat)
+        B, n_img, _ = front.shape
+        centers = None
+        if self.use_pointcloud and pointcloud is not None:
+            pc_emb, centers = self.vision_tower_3d(pointcloud.to(dev, non_blocking=True))
+            pc_tok = self.projector_3d(pc_emb.reshape(-1, pc_emb.shape[-1])).view(B, -1, self.token_size)
+            patch_indices, valid_mask = project_points(centers, camera_name)
+        else:
+            pc_tok = torch.zeros((B, n_img, self.token_size), dtype=front.dtype, device=dev)
+            patch_indices = torch.zeros((B, n_img, 2), dtype=torch.long, device=dev)
+            valid_mask = torch.zeros((B, n_img), dtype=torch.bool, device=dev)
+        assert pc_tok.shape[1] == front.shape[1], f"Token count mismatch: PC={pc_tok.shape[1]}, Front Img={front.shape[1]}"
+        parts = [pc_tok, front]
+        for key in views:
+            if key != "front_image":
+                parts.append(self._image_tokens(views[key].to(dev, non_blocking=True), image_repeat))
+        pos_pc = lin_img = None
+        if self.use_tactile and tactile is not None:
+            last_dim = gripper_xyz.shape[-1]
+            if last_dim % 3 != 0:
+                raise ValueError(f"gripper_xyz last dimension ({last_dim}) is not divisible by 3")
+            n_arms = last_dim // 3
+            t_flat = tactile.to(dev).view(tactile.shape[0], -1)
+            if t_flat.shape[-1] != self.tactile_dim * n_arms:
+                raise ValueError(f"Unexpected tactile shape {tuple(tactile.shape)}.")
+            tac = self.tactile_embedder(t_flat.reshape(B * n_arms, self.tactile_dim)).view(B, n_arms, -1)
+            parts.append(tac)
+            # nearest point-cloud centre to each gripper (:742-749); tiny [B, n_arms, 256] problem
+            g = gripper_xyz.to(dev).view(B, n_arms, 3).float()
+            d = torch.cdist(g, centers)
+            pos_pc = torch.topk(d, k=1, dim=2, largest=False)[1]
+            patch_w = int(front.shape[1] ** 0.5)
+            sel = torch.gather(patch_indices.unsqueeze(1).expand(-1, n_arms, -1, -1), 2,
+                               pos_pc.unsqueeze(-1).expand(-1, -1, -1, 2))
+            lin_img = sel[..., 0] * patch_w + sel[..., 1]
+        else:
+            parts.append(torch.zeros((B, 1, self.token_size), dtype=front.dtype, device=dev))
+        fused = torch.cat(parts, dim=1)
+        return fused, patch_indices, valid_mask, pos_pc, lin_img, centers
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x=None, t=None, z=None, proprio=None, gripper_xyz=None, input_ids=None, attention_mask=None,
+                images=None, camera_name=None, point_cloud=None, tactile=None, labels=None, inputs_embeds=None,
+                past_key_values=None, use_cache=None, output_attentions=None, output_hidden_states=True,
+                return_dict=None, multimodal_indices=None, gen_discret_action=None, use_diff=None, next_images=None,
+                next_point_cloud=None, next_tactile=None, image_repeat: int = 1, **kwargs):
+        if use_diff is not None:
+            self.use_diff = use_diff
+        if past_key_values is not None or (input_ids is not None and input_ids.shape[1] == 1):
+            raise NotImplementedError("cached single-token decoding is inference-only (out of the hot-path scope)")
+        if images is None:
+            raise RuntimeError("Invalid `forward()` call!")
+        if multimodal_indices is not None and len(multimodal_indices) != len(input_ids):
+            raise NotImplementedError("unimodal/mixed batches (multimodal_indices) are not part of the VLA training path")
+        llm = self.llm_backbone.llm
+        dev = llm.lm_head.weight.device
+        h = self.token_size
+        eos_tag = 2 if self.training else 29871            # tag_0 (:882-887)
+
+        fused, patch_indices, valid_mask, pos_pc, lin_img, _ = self.get_fused_tokens(
+            images, point_cloud, tactile, gripper_xyz, camera_name, image_repeat)
+        B, F, _ = fused.shape
+        N_pc = N_img = patch_indices.shape[1]     # 256 in the reference (prismatic.py:932-933)
+        input_ids = input_ids.to(dev, non_blocking=True)
+        Lt = input_ids.shape[1]
+        text = self.llm_backbone.embed_input_ids(input_ids)                                   # [B, Lt, h]
+
+        n_ins = n_x = 0
+        ins_parts = []
+        if self.use_diff:
+            pr = self.proprio_embedder(proprio.to(dev).to(torch.bfloat16))                     # [B, 1, h]
+            if self.training and self.z_embedder.dropout_prob > 0:
+                # LabelEmbedder.token_drop (models/diffusion/models.py:82-92) zeroes the whole condition sequence
+                # z = [BOS | fused | text] of a dropped sample: apply one draw to both row groups
+                drop = (torch.rand(B, device=dev) < self.z_embedder.dropout_prob).view(B, 1, 1)
+                fused = torch.where(drop, torch.zeros_like(fused), fused)
+                text = torch.where(drop, torch.zeros_like(text), text)
+            xe = self.x_embedder(x.to(dev).to(torch.bfloat16))                                # [B, T+1, h]
+            if t is not None:
+                te = self.t_embedder(t.to(dev)).unsqueeze(1)
+            else:
+                te = torch.zeros_like(pr)
+            ins_parts = [pr, te, xe]
+            n_x = xe.shape[1]
+            n_ins = pr.shape[1] + 1 + n_x
+        # row table: text | fused | inserted
+        table = torch.cat([text.reshape(B * Lt, h), fused.reshape(B * F, h)] +
+                          ([torch.cat(ins_parts, dim=1).reshape(B * n_ins, h)] if n_ins else []), dim=0)
+        S = F + Lt + n_ins
+        src_idx = torch.empty((B, S), dtype=torch.int32, device=dev)
+        mask = torch.empty((B, S), dtype=torch.uint8, device=dev)
+        lti = torch.empty(B, dtype=torch.int32, device=dev)
+        head_rows = torch.empty((B, max(n_x, 1)), dtype=torch.int32, device=dev)
+        fused_labels = torch.empty((B, S), dtype=torch.int64, device=dev) if labels is not None else None
+        if self._err_flag is None or self._err_flag.device != dev:
+            self._err_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        am = None
+        if attention_mask is not None:
+            am = attention_mask.to(dev, non_blocking=True)
+            am = (am if am.dtype in (torch.bool, torch.uint8) else am != 0).contiguous()
+        lab = labels.to(dev, non_blocking=True).contiguous() if labels is not None else None
+        check(_lib.lib().mla_splice_index(
+            ops._p(input_ids.contiguous()), ops._p(am), ops._p(lab), C.c_int32(B), C.c_int32(Lt), C.c_int32(F),
+            C.c_int32(n_ins), C.c_int32(n_x), C.c_int64(eos_tag), C.c_int32(0), C.c_int32(B * Lt),
+            C.c_int32(B * Lt + B * F), ops._p(src_idx), ops._p(mask), ops._p(fused_labels), ops._p(lti),
+            ops._p(head_rows), ops._p(self._err_flag), ops._stream()))
+        embeds = ops.GatherRowsFn.apply(table, src_idx.view(-1))                              # [B*S, h]
+
+        pc_idx = (1, 1 + N_pc)
+        img_idx = (1 + N_pc, 1 + N_pc + N_img)
+        tac_idx = (img_idx[1], img_idx[1] + self.action_dim // 7) if self.use_tactile else None
+        output: CausalLMOutputWithPast = self.llm_backbone(
+            input_ids=None, attention_mask=mask if attention_mask is not None else None, position_ids=None,
+            past_key_values=None, inputs_embeds=embeds.view(B, S, h), labels=fused_labels, use_cache=use_cache,
+            output_attentions=output_attentions, output_hidden_states=True, return_dict=True,
+            pc_token_indices=pc_idx, img_token_indices=img_idx, tac_token_indices=tac_idx,
+            patch_correspondence_indices=patch_indices, correspondence_valid_mask=valid_mask,
+            positive_pc_indices_for_tac=pos_pc, linear_positive_img_indices_for_tac=lin_img,
+            compute_token_contrastive_loss=self.use_contrastive,
+            compute_tactile_contrastive_loss=(self.use_contrastive and self.use_tactile))
+        output.last_true_indices = lti
+        generation_outputs: Dict[str, torch.Tensor] = {}
+        generation_losses: Dict[str, torch.Tensor] = {}
+        if self.use_diff:
+            last = output.hidden_states[-1].reshape(B * S, h)
+            rows = ops.GatherRowsFn.apply(last, head_rows.view(-1))                           # [B*(T+1), h]
+            noise_pred = self.final_layer(rows).reshape(B, n_x, self.action_dim)
+            if self.training:
+                return output, noise_pred, generation_outputs, generation_losses
+            return output, noise_pred
+        if self.training:
+            return output, generation_outputs, generation_losses
+        return output
+
+    def check_errors(self) -> None:
+        """Deferred device-side error check (one sync): raises what the reference would have raised eagerly."""
+        if self._err_flag is not None and int(self._err_flag.item()) != 0:
+            self._err_flag.zero_()
+            raise IndexError("a sample has no EOS/tag token to splice the action tokens before "
+                             "(models/vlm/prismatic.py:983 would raise IndexError)")
