@@ -192,6 +192,42 @@ int mla_project_points(const void* xyz, const void* cam, int64_t n, float sx, fl
                        int32_t patch_h, int32_t patch_w, float img_w, float img_h, void* patch_idx, void* valid,
                        void* stream);
 
+/* ---- point-cloud tokenizer (models/mla/pointcloud/backbone/Point_PN.py) -----------------------------------------
+ * fps: furthest_point_sample (:6-21): xyz f32 [B,n,3], start int64 [B] (the reference's torch.randint draw) ->
+ *   idx int32 [B,npoint], centers f32 [B,npoint,3]; lowest-index tie-break.
+ * knn: knn_point (:62-73): k nearest of each query f32 [B,groups,3] among xyz; bf16_dist=1 reproduces the autocast
+ *   distance arithmetic (bf16 matmul + in-place bf16 accumulation); ties by lowest index; idx int32 [B,groups,k].
+ * group_pose: LGA 'scan' normalisation + concat(knn feat, centre feat) + PosE_Geo (:125-150,:228-249):
+ *   feat [B,n,c] (bf16 or f32) -> rows (b,g,k) x 2c channels, written as f32 and as a bf16 copy.
+ * bn_*: train-mode BatchNorm over rows of a bf16 [rows,c] matrix: sums f32 [2c] (zero it first), coef f32 [2c] =
+ *   mean | invstd, running stats updated with `momentum`; bn_relu: out = bf16(relu(bn(y)));
+ *   bn_res_relu: v = relu(bf16(bn(y)) + x) (Linear2Layer :219) written as f32 + bf16, or max-pooled over the k rows
+ *   of each group when `pooled` is non-NULL (Pooling :161-170). */
+int mla_fps(const void* xyz, const void* start, void* idx_out, void* centers, int32_t batch, int32_t n,
+            int32_t npoint, void* stream);
+int mla_knn(const void* xyz, const void* query, void* knn_idx, int32_t batch, int32_t n, int32_t groups, int32_t k,
+            int32_t bf16_dist, void* stream);
+int mla_group_pose(const void* xyz, const void* feat, int32_t feat_is_bf16, const void* fps_idx, const void* knn_idx,
+                   const void* dim_embed, void* x_f32, void* x_bf16, int32_t batch, int32_t n, int32_t groups,
+                   int32_t k, int32_t c, float beta, void* stream);
+int mla_bn_stats(const void* y, void* sums, int64_t rows, int32_t c, void* stream);
+int mla_bn_finalize(const void* sums, void* coef, void* running_mean, void* running_var, int64_t rows, int32_t c,
+                    float eps, float momentum, void* stream);
+int mla_bn_relu(const void* y, const void* coef, const void* w, const void* bias, void* out, int64_t rows, int32_t c,
+                void* stream);
+int mla_bn_res_relu(const void* y, const void* coef, const void* w, const void* bias, const void* x, void* x_f32_out,
+                    void* x_bf16_out, void* pooled, int64_t groups, int32_t k, int32_t c, void* stream);
+
+/* ---- optimizer step of the data-parallel trainer (training/strategies/fsdp.py:242-257,:310) ------------------
+ * sumsq: out[0] += sum(x^2) (f32).  clip_coef: scale[0] = min(1, max_norm/(||g||*inv_world + 1e-6)) * inv_world,
+ * scale[1] = the mean-gradient norm — clip_grad_norm_ without the host round trip (g holds rank-summed gradients).
+ * adamw: torch.optim.AdamW update of an f32 tensor with the gradient pre-scaled by grad_scale[0] (device scalar, may be
+ * NULL); optionally refreshes the bf16 compute copy in the same pass. */
+int mla_sumsq_f32(const void* x, int64_t n, void* out, void* stream);
+int mla_clip_coef(const void* sumsq, float max_norm, float inv_world, void* scale, void* stream);
+int mla_adamw_f32(void* p, const void* g, void* m, void* v, void* p_bf16, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int64_t step, const void* grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

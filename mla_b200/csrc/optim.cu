@@ -1,0 +1,94 @@
+// Optimizer-side kernels of the data-parallel training step: global gradient norm, clip coefficient, fused AdamW
+// (fp32 master update + bf16 compute-copy refresh in one pass).  Mirrors torch.optim.AdamW + clip_grad_norm_ as the
+// reference's strategy uses them (training/strategies/fsdp.py:242-257,:310), minus the host round trips.
+#include "mla_internal.cuh"
+#include "ptx.cuh"
+
+namespace mla {
+
+__global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  const int64_t n4 = n >> 2;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) { const float v = x[n4 * 4 + threadIdx.x]; acc += v * v; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) atomicAdd(out, acc);
+  }
+}
+
+// scale[0] = min(1, max_norm / (||g_mean|| + 1e-6)) * inv_world ; scale[1] = ||g_mean||   (g_mean = g_sum * inv_world)
+__global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float inv_world,
+                                 float* __restrict__ scale) {
+  const float norm = sqrtf(sumsq[0]) * inv_world;
+  float c = max_norm > 0.f ? max_norm / (norm + 1e-6f) : 1.f;
+  c = c < 1.f ? c : 1.f;
+  scale[0] = c * inv_world;
+  scale[1] = norm;
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, __nv_bfloat16* __restrict__ p_bf16, int64_t n, float lr, float beta1,
+                             float beta2, float eps, float wd, float bc1, float bc2_sqrt,
+                             const float* __restrict__ gscale) {
+  const float gs = gscale ? gscale[0] : 1.f;
+  const float step = lr / bc1;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * gs;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= step * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (p_bf16) p_bf16[i] = __float2bfloat16_rn(pi);
+  }
+}
+
+}  // namespace mla
+
+using namespace mla;
+
+extern "C" int mla_sumsq_f32(const void* x, int64_t n, void* out, void* stream) {
+  if (int rc = device_check()) return rc;
+  if (n <= 0) return MLA_OK;
+  int64_t blocks = (n / 4 + 255) / 256;
+  int64_t cap = int64_t(num_sms()) * 8;
+  sumsq_kernel<<<int(blocks < 1 ? 1 : (blocks < cap ? blocks : cap)), 256, 0, (cudaStream_t)stream>>>((const float*)x, n, (float*)out);
+  MLA_CHECK_LAUNCH("sumsq");
+  return MLA_OK;
+}
+
+extern "C" int mla_clip_coef(const void* sumsq, float max_norm, float inv_world, void* scale, void* stream) {
+  if (int rc = device_check()) return rc;
+  clip_coef_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const float*)sumsq, max_norm, inv_world, (float*)scale);
+  MLA_CHECK_LAUNCH("clip_coef");
+  return MLA_OK;
+}
+
+extern "C" int mla_adamw_f32(void* p, const void* g, void* m, void* v, void* p_bf16, int64_t n, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int64_t step, const void* grad_scale,
+                             void* stream) {
+  if (int rc = device_check()) return rc;
+  if (n <= 0) return MLA_OK;
+  if (step < 1) return set_error(MLA_ERR_ARG, "adamw: step must be >= 1");
+  const float bc1 = 1.f - powf(beta1, float(step));
+  const float bc2 = 1.f - powf(beta2, float(step));
+  int64_t blocks = (n + 255) / 256;
+  int64_t cap = int64_t(num_sms()) * 16;
+  adamw_kernel<<<int(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+      (float*)p, (const float*)g, (float*)m, (float*)v, (__nv_bfloat16*)p_bf16, n, lr, beta1, beta2, eps, weight_decay,
+      bc1, sqrtf(bc2), (const float*)grad_scale);
+  MLA_CHECK_LAUNCH("adamw");
+  return MLA_OK;
+}

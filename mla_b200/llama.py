@@ -88,6 +88,7 @@ class LlamaDecoderLayer(nn.Module):
         self._versions = None
         self._g = None          # fp32 gradient arenas
         self._grads_fresh = True
+        self._grad_ready_cb = None   # set by the data-parallel trainer: called when this layer's arenas are final
 
     # ------------------------------------------------------------------ parameter plumbing
     def _masters(self) -> List[nn.Parameter]:
@@ -221,6 +222,8 @@ class LlamaDecoderLayer(nn.Module):
         del dqkv, n1
         dx = ops.rmsnorm_bwd(dn1, x, l1, self.eps, dres=dx_mid, dw=g1)
         self._grads_fresh = False
+        if self._grad_ready_cb is not None:
+            self._grad_ready_cb(self)
         return dx
 
     def _mlp_half_no_down(self, x_mid: torch.Tensor):
@@ -237,7 +240,7 @@ class _LayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, anchor, layer: LlamaDecoderLayer, sh: LayerShape):
-        level = layer.save_level if torch.is_grad_enabled() or True else "layer"
+        level = layer.save_level
         y, saved = layer.forward_impl(x, sh, level)
         ctx.layer, ctx.sh, ctx.level = layer, sh, level
         ctx.save_for_backward(*saved)

@@ -1,0 +1,165 @@
+"""Data-parallel training strategy for the drop-in MLA module: DDP replicas + NCCL gradient all-reduce + fused AdamW.
+
+The reference trains with FSDP only (training/strategies/fsdp.py); north_star asks for plain data-parallel replicas
+with gradient all-reduce over NVLink and no parameter all-gather on the hot path.  This strategy keeps the
+reference's optimizer semantics — AdamW(lr, weight decay on >=2-D non-bias params only, fsdp.py:242-257),
+clip_grad_norm_(max_grad_norm) before the step (:310, base_strategy_mla.py:372), constant or warmup+cosine LR — and
+its step order (forward, backward, clip, step, zero_grad), with:
+  * one NCCL all-reduce per decoder layer's fp32 gradient arenas, issued from that layer's backward so it overlaps
+    the rest of backward; a handful more for the small modules' autograd gradients;
+  * the global norm, clip coefficient, 1/world averaging and the AdamW update computed on the device (no host sync),
+    the update refreshing the bf16 compute copies in the same pass.
+Samples are independent (per-replica InfoNCE negatives and BatchNorm statistics, as in the reference), so there is no
+other exchange.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+from ._lib import check
+from .llama import LlamaDecoderLayer
+
+
+class DataParallelTrainer:
+    def __init__(self, model: torch.nn.Module, lr: float = 2e-5, weight_decay: float = 0.0,
+                 max_grad_norm: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8,
+                 lr_scheduler_type: str = "constant", warmup_steps: int = 0, total_steps: Optional[int] = None,
+                 process_group=None):
+        self.model = model
+        self.lr, self.weight_decay, self.max_grad_norm = lr, weight_decay, max_grad_norm
+        self.betas, self.eps = betas, eps
+        self.lr_scheduler_type, self.warmup_steps, self.total_steps = lr_scheduler_type, warmup_steps, total_steps
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.step_count = 0
+        self._handles: List = []
+        self.layers: List[LlamaDecoderLayer] = [m for m in model.modules() if isinstance(m, LlamaDecoderLayer)]
+        layer_params = set()
+        for l in self.layers:
+            for p in l._masters():
+                layer_params.add(id(p))
+            if self.world > 1:
+                l._grad_ready_cb = self._layer_grads_ready
+        # (name, param, decay?) for everything trainable outside the decoder layers
+        self.other = [(n, p, not (p.ndim <= 1 or n.endswith(".bias"))) for n, p in model.named_parameters()
+                      if p.requires_grad and id(p) not in layer_params]
+        self.state: Dict[int, tuple] = {}
+        dev = next(model.parameters()).device
+        self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._scale = torch.zeros(2, dtype=torch.float32, device=dev)
+
+    # ------------------------------------------------------------------ gradient exchange
+    def _layer_grads_ready(self, layer: LlamaDecoderLayer) -> None:
+        """Called at the end of a decoder layer's backward: its arenas are final, reduce them while earlier layers
+        are still running backward."""
+        for g in layer._g:
+            self._handles.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def _reduce_others(self) -> None:
+        for _, p, _ in self.other:
+            if p.grad is not None:
+                self._handles.append(dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
+    def current_lr(self) -> float:
+        if self.lr_scheduler_type == "constant":
+            return self.lr
+        s = self.step_count
+        if s < self.warmup_steps:
+            return self.lr * s / max(1, self.warmup_steps)
+        prog = (s - self.warmup_steps) / max(1, (self.total_steps or s + 1) - self.warmup_steps)
+        return self.lr * max(0.0, 0.5 * (1.0 + math.cos(math.pi * min(1.0, prog))))
+
+    # ------------------------------------------------------------------ optimizer step
+    def _adam(self, param: torch.nn.Parameter, g: torch.Tensor, decay: bool, bf16_dst: Optional[torch.Tensor],
+              lr: float):
+        p = param.data
+        st = self.state.get(id(param))
+        if st is None:
+            st = (torch.zeros_like(p, memory_format=torch.contiguous_format),
+                  torch.zeros_like(p, memory_format=torch.contiguous_format))
+            self.state[id(param)] = st
+        check(_lib.lib().mla_adamw_f32(
+            ops._p(p), ops._p(g), ops._p(st[0]), ops._p(st[1]), ops._p(bf16_dst), C.c_int64(p.numel()), C.c_float(lr),
+            C.c_float(self.betas[0]), C.c_float(self.betas[1]), C.c_float(self.eps),
+            C.c_float(self.weight_decay if decay else 0.0), C.c_int64(self.step_count), ops._p(self._scale),
+            ops._stream()))
+
+    def step(self) -> None:
+        """clip_grad_norm_ + AdamW.step + zero_grad, after loss.backward()."""
+        lib, s = _lib.lib(), ops._stream()
+        if self.world > 1:
+            self._reduce_others()
+            for h in self._handles:
+                h.wait()
+            self._handles.clear()
+        self.step_count += 1
+        lr = self.current_lr()
+        # global norm over every gradient that exists (params without grad are skipped, as torch does)
+        self._sumsq.zero_()
+        for l in self.layers:
+            if l._grads_fresh:
+                continue          # no backward reached this layer since the last step
+            for g in l._g:
+                check(lib.mla_sumsq_f32(ops._p(g), C.c_int64(g.numel()), ops._p(self._sumsq), s))
+        for _, p, _ in self.other:
+            if p.grad is not None:
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                check(lib.mla_sumsq_f32(ops._p(g), C.c_int64(g.numel()), ops._p(self._sumsq), s))
+        check(lib.mla_clip_coef(ops._p(self._sumsq), C.c_float(self.max_grad_norm or 0.0), C.c_float(1.0 / self.world),
+                                ops._p(self._scale), s))
+        for l in self.layers:
+            if l._grads_fresh:
+                continue
+            h, f = l.hidden_size, l.inter
+            wqkv, wo, wgu, wd, l1, l2 = l.compute_weights()
+            dsts = [wqkv[:h], wqkv[h:2 * h], wqkv[2 * h:], wo, wgu[:f], wgu[f:], wd, l1, l2]
+            for p, g, dst in zip(l._masters(), l._views, dsts):
+                if p.requires_grad:
+                    self._adam(p, g, p.ndim > 1, dst, lr)
+            l.mark_grads_fresh()
+        for _, p, decay in self.other:
+            if p.grad is None:
+                continue
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            self._adam(p, g, decay, None, lr)
+            torch.autograd.graph.increment_version(p)      # invalidates the cached bf16 compute copy
+            p.grad = None
+
+    def grad_norm(self) -> torch.Tensor:
+        """Mean-gradient global norm of the last step (device scalar)."""
+        return self._scale[1]
+
+
+def plan_save_levels(model: torch.nn.Module, tokens: int, reserve_gb: float = 10.0) -> List[str]:
+    """Pick, per decoder layer, how much to keep for backward so that activations fit next to the parameters,
+    gradients and the (not yet allocated) Adam state: "none" (no GEMM recompute) where memory allows, then "mlp",
+    falling back to full-layer recompute ("layer", what the reference's activation checkpointing does)."""
+    layers = [m for m in model.modules() if isinstance(m, LlamaDecoderLayer)]
+    if not layers or not torch.cuda.is_available():
+        return ["layer"] * len(layers)
+    free, _total = torch.cuda.mem_get_info()
+    n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    n_layer_params = sum(p.numel() for l in layers for p in l._masters())
+    pending = 8 * n_train                       # Adam m, v (fp32)
+    pending += (4 + 2) * n_layer_params         # gradient arenas + bf16 compute copies, allocated lazily
+    pending += 4 * (n_train - n_layer_params)   # autograd gradients of the small modules
+    h, f = layers[0].hidden_size, layers[0].inter
+    work = 2 * tokens * (8 * f + 12 * h)        # transient buffers of one layer's backward
+    budget = free - pending - work - int(reserve_gb * 2 ** 30)
+    cost = {"layer": 2 * tokens * h, "mlp": 2 * tokens * 6 * h, "none": 2 * tokens * (6 * h + 2 * f)}
+    levels = ["layer"] * len(layers)
+    budget -= cost["layer"] * len(layers)
+    for target in ("mlp", "none"):
+        prev = "layer" if target == "mlp" else "mlp"
+        for i in range(len(layers)):
+            extra = cost[target] - cost[prev]
+            if levels[i] == prev and budget >= extra:
+                levels[i] = target
+                budget -= extra
+    return levels
