@@ -90,14 +90,21 @@ class DataParallelTrainer:
             C.c_float(self.weight_decay if decay else 0.0), C.c_int64(self.step_count), ops._p(self._scale),
             ops._stream()))
 
-    def step(self) -> None:
-        """clip_grad_norm_ + AdamW.step + zero_grad, after loss.backward()."""
-        lib, s = _lib.lib(), ops._stream()
+    def exchange(self) -> None:
+        """Finish the gradient exchange of this step: reduce the small modules' gradients and wait for every
+        outstanding all-reduce (decoder layers were issued from their backward).  Gradients hold rank SUMS afterwards;
+        the 1/world averaging is folded into the optimizer's gradient scale.  Parameters without a gradient (lm_head
+        in diffusion mode, unused tokenizer parameters) are skipped consistently on every rank."""
         if self.world > 1:
             self._reduce_others()
             for h in self._handles:
                 h.wait()
             self._handles.clear()
+
+    def step(self) -> None:
+        """clip_grad_norm_ + AdamW.step + zero_grad, after loss.backward()."""
+        lib, s = _lib.lib(), ops._stream()
+        self.exchange()
         self.step_count += 1
         lr = self.current_lr()
         # global norm over every gradient that exists (params without grad are skipped, as torch does)

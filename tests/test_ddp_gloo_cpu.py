@@ -1,0 +1,73 @@
+"""world_size-2 gloo test (CPU) of the data-parallel host logic: the per-layer gradient arenas and the small modules'
+gradients are all-reduced (sum) across ranks, parameters without gradients are skipped consistently, and per-rank
+synthetic batches differ (seed = 1234 + rank) while the model weights are identical."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mla_b200.llama import LlamaModel
+        from mla_b200.synthetic import make_batch
+        from mla_b200.trainer import DataParallelTrainer
+        torch.manual_seed(0)                                   # identical replicas
+        model = LlamaModel(64, 32, 64, 2, 4)
+        for p_ in model.parameters():
+            torch.nn.init.normal_(p_, std=0.02)
+        extra = torch.nn.Linear(4, 4)
+        unused = torch.nn.Linear(4, 4)                         # never gets a gradient (like lm_head in diffusion mode)
+        root = torch.nn.ModuleDict(dict(llm=model, extra=extra, unused=unused))
+        tr = DataParallelTrainer(root, lr=1e-3)
+        assert tr.world == world and all(l._grad_ready_cb is not None for l in tr.layers)
+        # fake a backward: every layer fills its arenas with a rank-dependent value and signals readiness
+        for li, layer in enumerate(tr.layers):
+            layer.grad_arenas()
+            layer._attach_grads()
+            for g in layer._g:
+                g.fill_(float(rank + 1) * (li + 1))
+            layer._grads_fresh = False
+            layer._grad_ready_cb(layer)
+        extra.weight.grad = torch.full_like(extra.weight, float(rank + 1))
+        extra.bias.grad = torch.full_like(extra.bias, 10.0 * (rank + 1))
+        tr.exchange()
+        tot = sum(r + 1 for r in range(world))
+        for li, layer in enumerate(tr.layers):
+            for g in layer._g:
+                assert torch.all(g == tot * (li + 1)), (rank, li)
+            assert layer.self_attn.q_proj.weight.grad is layer._views[0]      # param.grad aliases the arena
+        assert torch.all(extra.weight.grad == tot) and torch.all(extra.bias.grad == 10.0 * tot)
+        assert unused.weight.grad is None and model.embed_tokens.weight.grad is None
+        assert not tr._handles
+        # replicas see different data, same weights
+        b = make_batch(2, 8, seed=1234 + rank, image_hw=42)
+        gathered = [torch.zeros_like(b["actions"]) for _ in range(world)]
+        dist.all_gather(gathered, b["actions"])
+        assert not torch.equal(gathered[0], gathered[1])
+        w = model.layers[0].mlp.down_proj.weight.detach().clone()
+        ws = [torch.zeros_like(w) for _ in range(world)]
+        dist.all_gather(ws, w)
+        assert torch.equal(ws[0], ws[1])
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_exchange_world2(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
