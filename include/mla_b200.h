@@ -228,6 +228,23 @@ int mla_clip_coef(const void* sumsq, float max_norm, float inv_world, void* scal
 int mla_adamw_f32(void* p, const void* g, void* m, void* v, void* p_bf16, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int64_t step, const void* grad_scale, void* stream);
 
+/* ---- vocabulary cross-entropy (modeling_llama.py:1254-1269) ------------------------------------------------------
+ * logits bf16 [rows = B*seq, vocab] (pitch ld) from the lm_head GEMM; labels int64 [B, seq] UNshifted: row (b,s) is
+ * scored against labels[b,s+1]; -100 and the last position are ignored; loss[0] = mean over scored rows.
+ * lse f32 [rows], acc2 f32 [2] (sum, count) are kept for backward, which overwrites logits with d(loss)/d(logits). */
+int mla_ce_fwd(const void* logits, int64_t ld, const void* labels, int64_t rows, int32_t seq, int32_t vocab, void* lse,
+               void* acc2, void* loss, void* stream);
+int mla_ce_bwd(void* logits_inout, int64_t ld, const void* labels, int64_t rows, int32_t seq, int32_t vocab,
+               const void* lse, const void* acc2, const void* gscale, void* stream);
+
+/* ---- ActionTokenizer (vla/action_tokenizer.py:43-71) — integer results bit-exact ------------------------------------
+ * digitize: ids[i] = vocab_size - np.digitize(np.clip(x[i], lo, hi), edges)  (edges: float64 [bins] = np.linspace);
+ * decode: out[i] = centers[clip(vocab_size - ids[i] - 1, 0, n_centers-1)] (float64). */
+int mla_action_digitize(const void* x, int32_t x_is_f64, int64_t n, const void* edges, int32_t bins, double lo,
+                        double hi, int64_t vocab_size, void* ids_out, void* stream);
+int mla_action_decode(const void* ids, int64_t n, const void* centers, int32_t n_centers, int64_t vocab_size,
+                      void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,10 +138,10 @@ class LlamaForCausalLM(nn.Module):
 
         loss = logits = None
         if self.compute_lm_loss:
-            logits = ops.linear(hs2d[-1], self.lm_head.weight).view(B, S, -1).float()
+            logits_bf16 = ops.linear(hs2d[-1], self.lm_head.weight)                   # [B*S, V] bf16 (nn.Linear output)
             if labels is not None:
-                loss = torch.nn.functional.cross_entropy(
-                    logits[..., :-1, :].reshape(-1, self.config.vocab_size), labels[..., 1:].reshape(-1))
+                loss = ops.CrossEntropyFn.apply(logits_bf16, labels.to(logits_bf16.device))
+            logits = logits_bf16.view(B, S, -1).float()                               # `logits.float()` (:1256)
 
         img_pc_loss = None
         if self.training and compute_token_contrastive_loss:

@@ -460,3 +460,31 @@ def q_sample(a: torch.Tensor, noise: torch.Tensor, t: torch.Tensor, sqrt_ac: tor
     check(_lib.lib().mla_q_sample(_p(a), _p(noise), _p(t), _p(sqrt_ac), _p(sqrt_1mac), _p(out), C.c_int64(a.numel()),
                                   C.c_int32(a.numel() // a.shape[0]), _stream()))
     return out
+
+
+class CrossEntropyFn(torch.autograd.Function):
+    """Shifted CE of bf16 logits [B*S, V] against labels [B, S] (modeling_llama.py:1258-1269): fp32 math, mean over
+    the rows whose next-token label is not -100.  Backward reuses the logits buffer for d(logits)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        B, S = labels.shape
+        V = logits.shape[1]
+        labels = labels.contiguous()
+        lse = torch.empty(B * S, dtype=torch.float32, device=logits.device)
+        acc = torch.empty(2, dtype=torch.float32, device=logits.device)
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        check(_lib.lib().mla_ce_fwd(_p(logits), C.c_int64(logits.stride(0)), _p(labels), C.c_int64(B * S), C.c_int32(S),
+                                    C.c_int32(V), _p(lse), _p(acc), _p(loss), _stream()))
+        ctx.save_for_backward(logits, labels, lse, acc)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, labels, lse, acc = ctx.saved_tensors
+        B, S = labels.shape
+        gs = g.reshape(1).float().contiguous()
+        d = logits.detach().clone()
+        check(_lib.lib().mla_ce_bwd(_p(d), C.c_int64(d.stride(0)), _p(labels), C.c_int64(B * S), C.c_int32(S),
+                                    C.c_int32(logits.shape[1]), _p(lse), _p(acc), _p(gs), _stream()))
+        return d, None

@@ -120,3 +120,19 @@ def lm_loss(hidden: torch.Tensor, lm_head: torch.Tensor, labels: torch.Tensor) -
     V = logits.shape[-1]
     loss = F.cross_entropy(logits[..., :-1, :].reshape(-1, V), labels[..., 1:].reshape(-1))
     return loss, logits
+
+
+def action_tokenize(action, vocab_size: int, bins: int = 256, lo: float = -1.0, hi: float = 1.0):
+    """ActionTokenizer.__call__ up to the token ids — vla/action_tokenizer.py:43-46 (numpy, float64 edges)."""
+    import numpy as np
+    a = np.clip(action, a_min=float(lo), a_max=float(hi))
+    return vocab_size - np.digitize(a, np.linspace(lo, hi, bins))
+
+
+def action_detokenize(ids, vocab_size: int, bins: int = 256, lo: float = -1.0, hi: float = 1.0):
+    """ActionTokenizer.decode_token_ids_to_actions — vla/action_tokenizer.py:54-71."""
+    import numpy as np
+    edges = np.linspace(lo, hi, bins)
+    centers = (edges[:-1] + edges[1:]) / 2.0
+    d = np.clip(vocab_size - ids - 1, a_min=0, a_max=centers.shape[0] - 1)
+    return centers[d]

@@ -168,3 +168,66 @@ def test_mse_and_qsample(cuda_lib):
     sa, sb = torch.rand(100, device="cuda"), torch.rand(100, device="cuda")
     x = ops.q_sample(a, n, t, sa, sb)
     assert torch.allclose(x, sa[t].view(-1, 1, 1) * a + sb[t].view(-1, 1, 1) * n, atol=1e-6)
+
+
+def test_action_tokenizer_bit_exact(cuda_lib):
+    """ActionTokenizer bins (integer) must match numpy's digitize exactly, including edge values and out-of-range."""
+    import numpy as np
+    from mla_b200.action_tokenizer import ActionTokenizer
+    from oracle import llama as O
+
+    class Tok:
+        vocab_size = 32000
+    at = ActionTokenizer(Tok())
+    rng = np.random.default_rng(0)
+    edges = np.linspace(-1, 1, 256)
+    x = np.concatenate([rng.uniform(-1.3, 1.3, 20000), edges, np.nextafter(edges, 2), np.nextafter(edges, -2),
+                        [-1.0, 1.0, 0.0, -0.0, 5.0, -5.0]]).astype(np.float32)
+    ids = at.encode_ids(x).cpu().numpy()
+    assert np.array_equal(ids, O.action_tokenize(x, 32000))
+    x64 = x.astype(np.float64) + 1e-12
+    assert np.array_equal(at.encode_ids(x64).cpu().numpy(), O.action_tokenize(x64, 32000))
+    back = at.decode_token_ids_to_actions(ids)
+    assert np.array_equal(back, O.action_detokenize(ids, 32000))
+    # round trip lands within half a bin
+    inside = np.abs(x) <= 1
+    assert np.max(np.abs(back[inside] - x[inside])) <= (2 / 255) + 1e-6
+
+
+def test_cross_entropy_fwd_bwd(cuda_lib):
+    from mla_b200 import ops
+    torch.manual_seed(8)
+    B, S, V = 3, 17, 1000
+    logits = (torch.randn(B * S, V, device="cuda") * 3).to(torch.bfloat16).requires_grad_(True)
+    labels = torch.randint(0, V, (B, S), device="cuda")
+    labels[0, 3:6] = -100
+    labels[2, :] = -100
+    loss = ops.CrossEntropyFn.apply(logits, labels)
+    lf = logits.detach().float().view(B, S, V).requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lf[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1))
+    assert abs(loss.item() - ref.item()) < 1e-4 * abs(ref.item())
+    (loss * 2).backward()
+    (ref * 2).backward()
+    assert rel_err(logits.grad.view(B, S, V), lf.grad) < 6e-3
+
+
+def test_lm_loss_path(cuda_lib):
+    """LlamaForCausalLM with compute_lm_loss: loss/logits as modeling_llama.py:1254-1269, lm_head receives a gradient."""
+    from mla_b200.backbone import LlamaConfig, LlamaForCausalLM
+    from oracle import llama as O
+    torch.manual_seed(9)
+    cfg = LlamaConfig(vocab_size=512, hidden_size=128, intermediate_size=352, num_hidden_layers=1, num_attention_heads=4,
+                      pad_token_id=None)
+    m = LlamaForCausalLM(cfg).cuda()
+    m.compute_lm_loss = True
+    ids = torch.randint(0, 512, (2, 12), device="cuda")
+    labels = ids.clone()
+    labels[0, :4] = -100
+    out = m(input_ids=ids, labels=labels)
+    hs_last = out.hidden_states[-1]
+    w = m.lm_head.weight.detach().to(torch.bfloat16)
+    ref_loss, ref_logits = O.lm_loss(hs_last.detach(), w, labels)
+    assert abs(out.loss.item() - ref_loss.item()) < 2e-3 * abs(ref_loss.item())
+    assert rel_err(out.logits, ref_logits) < 1e-2 and out.logits.dtype == torch.float32
+    out.loss.backward()
+    assert m.lm_head.weight.grad is not None and float(m.lm_head.weight.grad.abs().sum()) > 0
