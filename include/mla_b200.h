@@ -115,6 +115,10 @@ typedef struct mla_attn_args {
 } mla_attn_args;
 int mla_attn_fwd(const mla_attn_args* args, void* stream);
 int mla_attn_bwd(const mla_attn_args* args, void* stream);
+/* tcgen05/TMEM/TMA forward for head_dim 128: qkv is the fused [batch*seq, 3*heads*128] projection (q | k | v column
+ * blocks, pitch ld_qkv); same outputs and semantics as mla_attn_fwd. */
+int mla_attn_fwd_sm100(const void* qkv, int64_t ld_qkv, void* o, int64_t ld_o, void* lse, const void* mask,
+                       int32_t batch, int32_t seq, int32_t heads, float scale, void* stream);
 
 /* ---- small row/elementwise kernels around the GEMMs ---------------------------------------------------------
  * (ATen glue in the reference: dtype casts under autocast, activation backward, bias gradients, torch.cat / index

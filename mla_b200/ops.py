@@ -158,6 +158,10 @@ def swiglu_bwd(dact: torch.Tensor, gu: torch.Tensor) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------------------------- attention
+# Which kernel serves head_dim 128: "sm100" = tcgen05/TMEM/TMA (attention_sm100.cu), "mma" = mma.sync (attention.cu).
+ATTN_IMPL = {"fwd": "sm100"}
+
+
 def _attn_args(qkv: torch.Tensor, B: int, S: int, H: int, D: int, mask: Optional[torch.Tensor]) -> "_lib.AttnArgs":
     _req(qkv, torch.bfloat16, "qkv")
     ld = _rowmajor_2d(qkv, "qkv")
@@ -182,7 +186,13 @@ def attn_fwd(qkv: torch.Tensor, B: int, S: int, H: int, D: int, mask: Optional[t
     ctx = torch.empty((B * S, H * D), dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty((B, H, S), dtype=torch.float32, device=qkv.device)
     a.o, a.ld_o, a.lse = ctx.data_ptr(), ctx.stride(0), lse.data_ptr()
-    check(_lib.lib().mla_attn_fwd(C.byref(a), _stream()))
+    if D == 128 and ATTN_IMPL["fwd"] == "sm100":
+        # tcgen05 / TMEM / TMA kernel (head_dim 128); the mma.sync kernel serves head_dim 32 / 64
+        check(_lib.lib().mla_attn_fwd_sm100(C.c_void_p(qkv.data_ptr()), C.c_int64(a.ld_qkv), C.c_void_p(a.o),
+                                            C.c_int64(a.ld_o), C.c_void_p(a.lse), C.c_void_p(a.mask), C.c_int32(B),
+                                            C.c_int32(S), C.c_int32(H), C.c_float(a.scale), _stream()))
+    else:
+        check(_lib.lib().mla_attn_fwd(C.byref(a), _stream()))
     return ctx, lse
 
 

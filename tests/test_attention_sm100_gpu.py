@@ -1,0 +1,63 @@
+"""tcgen05 attention forward (head_dim 128) vs the oracle and vs the mma.sync kernel it replaces."""
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,S,H,masked", [(1, 128, 1, False), (2, 150, 2, False), (2, 548, 3, False),
+                                          (3, 548, 2, True), (1, 700, 2, True), (2, 64, 1, False), (1, 257, 1, True)])
+def test_attn_fwd_sm100(cuda_lib, B, S, H, masked):
+    from mla_b200 import ops
+    from oracle import llama as O
+    torch.manual_seed(11)
+    D = 128
+    h = H * D
+    qkv = torch.randn(B * S, 3 * h, device="cuda").to(torch.bfloat16)
+    mask = None
+    if masked:
+        mask = torch.ones(B, S, dtype=torch.bool, device="cuda")
+        mask[0, S - 9:] = False
+        if B > 1:
+            mask[1, S // 3: S // 3 + 5] = False
+    ops.ATTN_IMPL["fwd"] = "mma"
+    ctx_ref, lse_ref = ops.attn_fwd(qkv, B, S, H, D, mask)
+    ops.ATTN_IMPL["fwd"] = "sm100"
+    ctx, lse = ops.attn_fwd(qkv, B, S, H, D, mask)
+    torch.cuda.synchronize()
+    q, k, v = [qkv[:, i * h:(i + 1) * h].float().reshape(B, S, H, D).transpose(1, 2) for i in range(3)]
+    truth = O.attention(q, k, v, mask).reshape(B * S, h)
+    e_new, e_old = rel_err(ctx, truth), rel_err(ctx_ref, truth)
+    assert e_new < 1.3 * e_old + 1e-3, (e_new, e_old)
+    assert rel_err(ctx, ctx_ref) < 6e-3
+    fin = torch.isfinite(lse_ref)
+    assert torch.equal(torch.isfinite(lse), fin)
+    assert (lse[fin] - lse_ref[fin]).abs().max() < 2e-3
+    if masked:
+        assert ctx.view(B, S, h)[0, S - 9:].abs().max() == 0
+
+
+def test_attn_fwd_sm100_speed(cuda_lib):
+    """Not a pass/fail on speed: prints both kernels' time at the benchmark shape for the log."""
+    from mla_b200 import ops
+    B, S, H, D = 32, 548, 32, 128
+    qkv = torch.randn(B * S, 3 * H * D, device="cuda").to(torch.bfloat16)
+    res = {}
+    for impl in ("mma", "sm100"):
+        ops.ATTN_IMPL["fwd"] = impl
+        for _ in range(3):
+            ops.attn_fwd(qkv, B, S, H, D, None)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.attn_fwd(qkv, B, S, H, D, None)
+        e1.record()
+        torch.cuda.synchronize()
+        res[impl] = e0.elapsed_time(e1) / 10
+    ops.ATTN_IMPL["fwd"] = "sm100"
+    flops = 4.0 * S * S * D * H * B / 2
+    print(f"\nattn fwd [32,548,32,128]: mma.sync {res['mma']:.3f} ms ({flops / res['mma'] / 1e9:.0f} TFLOP/s causal), "
+          f"tcgen05 {res['sm100']:.3f} ms ({flops / res['sm100'] / 1e9:.0f} TFLOP/s)")
