@@ -119,6 +119,12 @@ int mla_attn_bwd(const mla_attn_args* args, void* stream);
  * blocks, pitch ld_qkv); same outputs and semantics as mla_attn_fwd. */
 int mla_attn_fwd_sm100(const void* qkv, int64_t ld_qkv, void* o, int64_t ld_o, void* lse, const void* mask,
                        int32_t batch, int32_t seq, int32_t heads, float scale, void* stream);
+/* tcgen05/TMEM/TMA backward for head_dim 128 (dK/dV kernel + dQ kernel): dqkv has the layout of qkv (dq | dk | dv);
+ * lse is the forward's [batch, heads, seq] output; workspace: mla_attn_bwd_sm100_workspace() bytes, 16-byte aligned. */
+size_t mla_attn_bwd_sm100_workspace(int32_t batch, int32_t seq, int32_t heads);
+int mla_attn_bwd_sm100(const void* qkv, int64_t ld_qkv, const void* o, const void* d_o, int64_t ld_o, const void* lse,
+                       const void* mask, void* dqkv, int64_t ld_dqkv, void* workspace, int32_t batch, int32_t seq,
+                       int32_t heads, float scale, void* stream);
 
 /* ---- small row/elementwise kernels around the GEMMs ---------------------------------------------------------
  * (ATen glue in the reference: dtype casts under autocast, activation backward, bias gradients, torch.cat / index

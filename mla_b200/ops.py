@@ -159,7 +159,7 @@ def swiglu_bwd(dact: torch.Tensor, gu: torch.Tensor) -> torch.Tensor:
 
 # ---------------------------------------------------------------------------------------------- attention
 # Which kernel serves head_dim 128: "sm100" = tcgen05/TMEM/TMA (attention_sm100.cu), "mma" = mma.sync (attention.cu).
-ATTN_IMPL = {"fwd": "sm100"}
+ATTN_IMPL = {"fwd": "sm100", "bwd": "sm100"}
 
 
 def _attn_args(qkv: torch.Tensor, B: int, S: int, H: int, D: int, mask: Optional[torch.Tensor]) -> "_lib.AttnArgs":
@@ -204,6 +204,16 @@ def attn_bwd(dctx: torch.Tensor, qkv: torch.Tensor, ctx: torch.Tensor, lse: torc
     if not (dctx.is_contiguous() and ctx.is_contiguous()):
         raise _lib.MlaError("attention bwd: ctx / dctx must be contiguous")
     dqkv = torch.empty_like(qkv, memory_format=torch.contiguous_format)
+    if D == 128 and ATTN_IMPL["bwd"] == "sm100":
+        lib = _lib.lib()
+        lib.mla_attn_bwd_sm100_workspace.restype = C.c_size_t
+        ws = torch.empty(lib.mla_attn_bwd_sm100_workspace(C.c_int32(B), C.c_int32(S), C.c_int32(H)) // 4,
+                         dtype=torch.float32, device=qkv.device)
+        check(lib.mla_attn_bwd_sm100(C.c_void_p(qkv.data_ptr()), C.c_int64(a.ld_qkv), _p(ctx), _p(dctx),
+                                     C.c_int64(ctx.stride(0)), _p(lse), C.c_void_p(a.mask), _p(dqkv),
+                                     C.c_int64(dqkv.stride(0)), _p(ws), C.c_int32(B), C.c_int32(S), C.c_int32(H),
+                                     C.c_float(a.scale), _stream()))
+        return dqkv
     delta = torch.empty_like(lse)
     a.o, a.ld_o, a.lse = ctx.data_ptr(), ctx.stride(0), lse.data_ptr()
     a.d_o, a.delta = dctx.data_ptr(), delta.data_ptr()

@@ -61,3 +61,58 @@ def test_attn_fwd_sm100_speed(cuda_lib):
     flops = 4.0 * S * S * D * H * B / 2
     print(f"\nattn fwd [32,548,32,128]: mma.sync {res['mma']:.3f} ms ({flops / res['mma'] / 1e9:.0f} TFLOP/s causal), "
           f"tcgen05 {res['sm100']:.3f} ms ({flops / res['sm100'] / 1e9:.0f} TFLOP/s)")
+
+
+@pytest.mark.parametrize("B,S,H,masked", [(1, 128, 1, False), (2, 150, 2, False), (2, 548, 2, False),
+                                          (2, 548, 2, True), (1, 700, 1, True), (1, 64, 1, False), (1, 257, 2, True)])
+def test_attn_bwd_sm100(cuda_lib, B, S, H, masked):
+    from mla_b200 import ops
+    from oracle import llama as O
+    torch.manual_seed(12)
+    D = 128
+    h = H * D
+    qkv = torch.randn(B * S, 3 * h, device="cuda").to(torch.bfloat16)
+    mask = None
+    if masked:
+        mask = torch.ones(B, S, dtype=torch.bool, device="cuda")
+        mask[0, S - 9:] = False
+        if B > 1:
+            mask[1, S // 3: S // 3 + 5] = False
+    ctx, lse = ops.attn_fwd(qkv, B, S, H, D, mask)
+    dctx = torch.randn(B * S, h, device="cuda").to(torch.bfloat16)
+    ops.ATTN_IMPL["bwd"] = "mma"
+    d_ref = ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, mask)
+    ops.ATTN_IMPL["bwd"] = "sm100"
+    d_new = ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, mask)
+    torch.cuda.synchronize()
+    qf = qkv.float().requires_grad_(True)
+    q, k, v = [qf[:, i * h:(i + 1) * h].reshape(B, S, H, D).transpose(1, 2) for i in range(3)]
+    O.attention(q, k, v, mask).backward(dctx.view(B, S, h).float())
+    for i, name in enumerate("qkv"):
+        sl = slice(i * h, (i + 1) * h)
+        e_new, e_old = rel_err(d_new[:, sl], qf.grad[:, sl]), rel_err(d_ref[:, sl], qf.grad[:, sl])
+        assert e_new < 1.3 * e_old + 2e-3, (name, e_new, e_old)
+    assert torch.isfinite(d_new.float()).all()
+
+
+def test_attn_bwd_sm100_speed(cuda_lib):
+    from mla_b200 import ops
+    B, S, H, D = 32, 548, 32, 128
+    qkv = torch.randn(B * S, 3 * H * D, device="cuda").to(torch.bfloat16)
+    ctx, lse = ops.attn_fwd(qkv, B, S, H, D, None)
+    dctx = torch.randn_like(ctx)
+    res = {}
+    for impl in ("mma", "sm100"):
+        ops.ATTN_IMPL["bwd"] = impl
+        for _ in range(3):
+            ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, None)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, None)
+        e1.record()
+        torch.cuda.synchronize()
+        res[impl] = e0.elapsed_time(e1) / 10
+    ops.ATTN_IMPL["bwd"] = "sm100"
+    print(f"\nattn bwd [32,548,32,128]: mma.sync {res['mma']:.3f} ms, tcgen05 {res['sm100']:.3f} ms")
