@@ -159,7 +159,10 @@ def swiglu_bwd(dact: torch.Tensor, gu: torch.Tensor) -> torch.Tensor:
 
 # ---------------------------------------------------------------------------------------------- attention
 # Which kernel serves head_dim 128: "sm100" = tcgen05/TMEM/TMA (attention_sm100.cu), "mma" = mma.sync (attention.cu).
-ATTN_IMPL = {"fwd": "sm100", "bwd": "sm100"}
+import os as _os
+
+_attn_default = _os.environ.get("MLA_ATTN_IMPL", "sm100")      # A/B switch for benchmarking: "sm100" | "mma"
+ATTN_IMPL = {"fwd": _attn_default, "bwd": _attn_default}
 
 
 def _attn_args(qkv: torch.Tensor, B: int, S: int, H: int, D: int, mask: Optional[torch.Tensor]) -> "_lib.AttnArgs":
