@@ -65,6 +65,10 @@ typedef struct mla_gemm_args {
   int64_t ldr;
   void* pre_act;               /* bf16 [M,N] or NULL: value before the activation (saved for backward) */
   int64_t ldp;
+  void* sched_ws;              /* NULL: static tile schedule.  Else 8 bytes of device memory, zero before the first use and
+                                  private to one stream: tiles are then claimed dynamically (CTAs that start late because a
+                                  concurrent kernel, e.g. an NCCL all-reduce, holds their SM take fewer tiles); the kernel
+                                  leaves it zeroed again. */
 } mla_gemm_args;
 int mla_gemm_bf16(const mla_gemm_args* args, void* stream);
 

@@ -24,7 +24,7 @@ class GemmArgs(C.Structure):
         ("c_dtype", C.c_int32), ("accumulate", C.c_int32), ("activation", C.c_int32),
         ("alpha", C.c_float),
         ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int64),
-        ("pre_act", C.c_void_p), ("ldp", C.c_int64),
+        ("pre_act", C.c_void_p), ("ldp", C.c_int64), ("sched_ws", C.c_void_p),
     ]
 
 

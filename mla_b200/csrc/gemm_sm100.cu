@@ -29,6 +29,7 @@ constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int GEMM_THREADS = 192;
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
+constexpr int SCHED_STAGES = 4;
 constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct GemmEpilogue {
@@ -61,12 +62,13 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 // Tile rasterisation: groups of GROUP_M row-tiles sweep all column-tiles, so the CTAs that run concurrently share
 // a small set of A row-panels while B streams through L2.
-constexpr int GROUP_M = 16;
-__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int& tm, int& tn) {
-  int group_size = GROUP_M * tiles_n;
+// The group height is chosen on the host so that one group's A row-panel (group_m x 128 x K bf16) stays L2 resident
+// (~48 MB of the 126 MB): B is then re-read from HBM only tiles_m / group_m times.
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int group_m, int& tm, int& tn) {
+  int group_size = group_m * tiles_n;
   int g = tile / group_size;
-  int first_m = g * GROUP_M;
-  int gm = min(GROUP_M, tiles_m - first_m);
+  int first_m = g * group_m;
+  int gm = min(group_m, tiles_m - first_m);
   int r = tile - g * group_size;
   tm = first_m + r % gm;
   tn = r / gm;
@@ -75,7 +77,7 @@ __device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, 
 template <int A_MN, int B_MN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 int M, int N, int K, GemmEpilogue ep) {
+                 int M, int N, int K, int group_m, int* sched, GemmEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -83,7 +85,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + ACC_STAGES;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC_STAGES);
+  uint64_t* sched_full = tmem_empty_bar + ACC_STAGES;      // tile-id ring (dynamic scheduling only)
+  uint64_t* sched_empty = sched_full + SCHED_STAGES;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(sched_empty + SCHED_STAGES);
+  int* sched_ids = reinterpret_cast<int*>(tmem_base_slot + 1);
+  const bool dynamic = sched != nullptr;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -103,6 +109,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 4);
     }
+    for (int s = 0; s < SCHED_STAGES; ++s) {
+      mbar_init(&sched_full[s], 1);
+      mbar_init(&sched_empty[s], 5);   // MMA thread + 4 epilogue warps
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -119,9 +129,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // Tile sequence: static (blockIdx.x, +gridDim.x, ...) or, with a scheduler counter, claimed dynamically so that
+      // CTAs which start late (SMs busy with a concurrent NCCL kernel) simply take fewer tiles.  The producer publishes
+      // every claimed tile id to the other warps through a small smem ring.
+      int tile = blockIdx.x;
+      for (int seq = 0;; ++seq) {
+        if (dynamic) {
+          const int sl = seq & (SCHED_STAGES - 1);
+          mbar_wait(&sched_empty[sl], ((seq / SCHED_STAGES) & 1) ^ 1);
+          sched_ids[sl] = tile < num_tiles ? tile : -1;
+          mbar_arrive(&sched_full[sl]);
+        }
+        if (tile >= num_tiles) break;
         int tm, tn;
-        tile_coords(tile, tiles_m, tiles_n, tm, tn);
+        tile_coords(tile, tiles_m, tiles_n, group_m, tm, tn);
         const int m0 = tm * BM, n0 = tn * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -145,6 +166,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        tile = dynamic ? int(gridDim.x) + atomicAdd(sched, 1) : tile + int(gridDim.x);
       }
     }
   } else if (warp == 1) {
@@ -155,7 +177,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int tile = blockIdx.x;
+      for (int seq = 0;; ++seq) {
+        if (dynamic) {
+          const int sl = seq & (SCHED_STAGES - 1);
+          mbar_wait(&sched_full[sl], (seq / SCHED_STAGES) & 1);
+          tile = sched_ids[sl];
+          mbar_arrive(&sched_empty[sl]);
+          if (tile < 0) break;
+        } else {
+          if (seq > 0) tile += gridDim.x;
+          if (tile >= num_tiles) break;
+        }
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -187,9 +220,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int tile = blockIdx.x;
+    for (int seq = 0;; ++seq) {
+      if (dynamic) {
+        const int sl = seq & (SCHED_STAGES - 1);
+        mbar_wait(&sched_full[sl], (seq / SCHED_STAGES) & 1);
+        tile = sched_ids[sl];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sched_empty[sl]);
+        if (tile < 0) break;
+      } else {
+        if (seq > 0) tile += gridDim.x;
+        if (tile >= num_tiles) break;
+      }
       int tm, tn;
-      tile_coords(tile, tiles_m, tiles_n, tm, tn);
+      tile_coords(tile, tiles_m, tiles_n, group_m, tm, tn);
       const int64_t row = int64_t(tm) * BM + quarter * 32 + lane;
       const int n0 = tn * BN;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -298,6 +343,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (dynamic && threadIdx.x == 0) {
+    // the last CTA to finish re-arms the counters for the next launch on this stream
+    __threadfence();
+    if (atomicAdd(sched + 1, 1) == int(gridDim.x) - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -320,7 +374,7 @@ static int encode_operand_map(CUtensorMap* map, const void* ptr, int mn_major, i
 
 template <int A_MN, int B_MN>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const GemmEpilogue& ep,
-                       cudaStream_t stream) {
+                       int* sched, cudaStream_t stream) {
   static bool attr_set = false;
   auto kern = gemm_bf16_kernel<A_MN, B_MN>;
   if (!attr_set) {
@@ -330,7 +384,9 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, int M, int 
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ma, mb, M, N, K, ep);
+  int group_m = int((48ll << 20) / (int64_t(BM) * K * 2));
+  group_m = group_m < 4 ? 4 : (group_m > 64 ? 64 : group_m);
+  kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ma, mb, M, N, K, group_m, tiles > grid ? sched : nullptr, ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
   count_launch();
@@ -366,8 +422,9 @@ extern "C" int mla_gemm_bf16(const mla_gemm_args* g, void* stream_) {
   ep.pre_act = static_cast<__nv_bfloat16*>(g->pre_act); ep.ldp = g->ldp;
   ep.alpha = g->alpha; ep.c_dtype = g->c_dtype; ep.accumulate = g->accumulate; ep.activation = g->activation;
   const int M = int(g->m), N = int(g->n), K = int(g->k);
-  if (!g->a_mn_major && !g->b_mn_major) return launch_gemm<0, 0>(ma, mb, M, N, K, ep, stream);
-  if (!g->a_mn_major && g->b_mn_major) return launch_gemm<0, 1>(ma, mb, M, N, K, ep, stream);
-  if (g->a_mn_major && !g->b_mn_major) return launch_gemm<1, 0>(ma, mb, M, N, K, ep, stream);
-  return launch_gemm<1, 1>(ma, mb, M, N, K, ep, stream);
+  int* sched = static_cast<int*>(g->sched_ws);
+  if (!g->a_mn_major && !g->b_mn_major) return launch_gemm<0, 0>(ma, mb, M, N, K, ep, sched, stream);
+  if (!g->a_mn_major && g->b_mn_major) return launch_gemm<0, 1>(ma, mb, M, N, K, ep, sched, stream);
+  if (g->a_mn_major && !g->b_mn_major) return launch_gemm<1, 0>(ma, mb, M, N, K, ep, sched, stream);
+  return launch_gemm<1, 1>(ma, mb, M, N, K, ep, sched, stream);
 }

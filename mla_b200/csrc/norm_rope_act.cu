@@ -79,61 +79,76 @@ __global__ void rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __
 // dn = dy*w ; dx = rstd*(dn - n*mean(dn*n)) (+ dres) ; dw += sum_rows dy*n.   Each CTA walks rows blockIdx.x,
 // +gridDim.x, ... keeping its dw partial in registers, then does one fp32 atomicAdd per column.
 template <int VPT>  // uint4 vectors per thread (h <= blockDim*8*VPT)
-__global__ void rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
-                                   const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ dres,
-                                   __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, int64_t rows, int h,
-                                   float eps) {
-  __shared__ float red[32];
+__global__ void __launch_bounds__(256, 2)
+rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                   const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ dres,
+                   __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, int64_t rows, int h, float eps) {
+  // One CTA walks rows blockIdx.x, +gridDim.x, ...; a thread owns the same columns of every row, so the weight
+  // gradient accumulates in registers.  Both row statistics (sum x^2 and sum dn*x) come out of ONE block reduction,
+  // and the next row's x / dy are prefetched (kept packed as bf16) before the reduction's barriers.
+  __shared__ float red[2][32];
   const int nvec = h >> 3;
-  float wv[VPT][8];
-  float dwacc[VPT][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  float wv[VPT][8], dwacc[VPT][8];
 #pragma unroll
   for (int v = 0; v < VPT; ++v) {
-    int i = threadIdx.x + v * blockDim.x;
+    const int i = threadIdx.x + v * blockDim.x;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dwacc[v][j] = 0.f; wv[v][j] = 0.f; }
     if (i < nvec) unpack8(*reinterpret_cast<const uint4*>(w + i * 8), wv[v]);
   }
-  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
-    const __nv_bfloat16* xr = x + row * h;
-    const __nv_bfloat16* dyr = dy + row * h;
-    float xf[VPT][8], dn[VPT][8];
-    float ss = 0.f;
+  uint4 nx[VPT], ndy[VPT];
+  int64_t row = blockIdx.x;
+  auto prefetch = [&](int64_t r) {
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
-      int i = threadIdx.x + v * blockDim.x;
-      if (i < nvec) {
-        unpack8(*reinterpret_cast<const uint4*>(xr + i * 8), xf[v]);
-        unpack8(*reinterpret_cast<const uint4*>(dyr + i * 8), dn[v]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { xf[v][j] = 0.f; dn[v][j] = 0.f; }
+      const int i = threadIdx.x + v * blockDim.x;
+      nx[v] = make_uint4(0, 0, 0, 0);
+      ndy[v] = make_uint4(0, 0, 0, 0);
+      if (r < rows && i < nvec) {
+        nx[v] = *reinterpret_cast<const uint4*>(x + r * h + i * 8);
+        ndy[v] = *reinterpret_cast<const uint4*>(dy + r * h + i * 8);
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) ss += xf[v][j] * xf[v][j];
     }
-    ss = block_sum(ss, red);
-    const float rstd = rsqrtf(ss / float(h) + eps);
-    float dot = 0.f;
+  };
+  prefetch(row);
+  for (; row < rows; row += gridDim.x) {
+    float xf[VPT][8], dn[VPT][8], dyf[VPT][8];
+    float ss = 0.f, dp = 0.f;
 #pragma unroll
-    for (int v = 0; v < VPT; ++v)
+    for (int v = 0; v < VPT; ++v) {
+      unpack8(nx[v], xf[v]);
+      unpack8(ndy[v], dyf[v]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float n = xf[v][j] * rstd;
-        dwacc[v][j] += dn[v][j] * bf16_round(n);  // dy * n (n is what forward multiplied by w)
-        dn[v][j] *= wv[v][j];                     // dn = dy * w
-        dot += dn[v][j] * n;
-        xf[v][j] = n;
+        dn[v][j] = dyf[v][j] * wv[v][j];
+        ss += xf[v][j] * xf[v][j];
+        dp += dn[v][j] * xf[v][j];
       }
-    dot = block_sum(dot, red) / float(h);
+    }
+    prefetch(row + gridDim.x);
+    // one reduction for both sums
+    ss = warp_sum(ss);
+    dp = warp_sum(dp);
+    __syncthreads();
+    if (lane == 0) { red[0][warp] = ss; red[1][warp] = dp; }
+    __syncthreads();
+    ss = warp_sum(lane < nw ? red[0][lane] : 0.f);
+    dp = warp_sum(lane < nw ? red[1][lane] : 0.f);
+    const float rstd = rsqrtf(ss / float(h) + eps);
+    const float dot = rstd * dp / float(h);      // mean(dn * n), n = x * rstd
     __nv_bfloat16* dxr = dx + row * h;
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
-      int i = threadIdx.x + v * blockDim.x;
+      const int i = threadIdx.x + v * blockDim.x;
       if (i < nvec) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = bf16_round(rstd * (dn[v][j] - xf[v][j] * dot));
+        for (int j = 0; j < 8; ++j) {
+          const float n = xf[v][j] * rstd;
+          dwacc[v][j] += dyf[v][j] * bf16_round(n);   // dy * n (n is what forward multiplied by w)
+          o[j] = bf16_round(rstd * (dn[v][j] - n * dot));
+        }
         if (dres) {
           float r[8];
           unpack8(*reinterpret_cast<const uint4*>(dres + row * h + i * 8), r);
@@ -147,7 +162,7 @@ __global__ void rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const _
   if (dw) {
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
-      int i = threadIdx.x + v * blockDim.x;
+      const int i = threadIdx.x + v * blockDim.x;
       if (i < nvec)
 #pragma unroll
         for (int j = 0; j < 8; ++j) atomicAdd(dw + i * 8 + j, dwacc[v][j]);

@@ -79,8 +79,25 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         _req(pre_act, torch.bfloat16, "pre_act")
         g.ldp = _rowmajor_2d(pre_act, "pre_act")
     g.pre_act = _ptr(pre_act)
+    if DYNAMIC_TILES["on"]:
+        g.sched_ws = _sched_ws(a.device).data_ptr()
     check(_lib.lib().mla_gemm_bf16(C.byref(g), _stream()))
     return out
+
+
+# Dynamic tile scheduling of the persistent GEMM (see include/mla_b200.h: sched_ws).  One 8-byte counter per
+# (device, stream); switched on by the data-parallel trainer, whose NCCL all-reduces share the SMs with the GEMMs.
+DYNAMIC_TILES = {"on": __import__("os").environ.get("MLA_DYNAMIC_TILES", "0") == "1"}
+_SCHED_WS: dict = {}
+
+
+def _sched_ws(device) -> torch.Tensor:
+    key = (str(device), torch.cuda.current_stream().cuda_stream)
+    t = _SCHED_WS.get(key)
+    if t is None:
+        t = torch.zeros(2, dtype=torch.int32, device=device)
+        _SCHED_WS[key] = t
+    return t
 
 
 # ---------------------------------------------------------------------------------------------- row kernels

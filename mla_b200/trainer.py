@@ -46,6 +46,11 @@ class DataParallelTrainer:
                 layer_params.add(id(p))
             if self.world > 1:
                 l._grad_ready_cb = self._layer_grads_ready
+        import os
+        if self.world > 1 and torch.cuda.is_available() and os.environ.get("MLA_FORCE_DYN", "1") != "0":
+            # the all-reduces share the SMs with backward: let the persistent GEMMs claim tiles dynamically so that
+            # CTAs whose SM is held by an NCCL kernel do not stall the whole GEMM
+            ops.DYNAMIC_TILES["on"] = True
         # (name, param, decay?) for everything trainable outside the decoder layers
         self.other = [(n, p, not (p.ndim <= 1 or n.endswith(".bias"))) for n, p in model.named_parameters()
                       if p.requires_grad and id(p) not in layer_params]

@@ -119,7 +119,7 @@ def test_forward_backward_parity(cuda_lib, name):
         t = sd32[k].grad
         e = rel_err(g.cpu(), t)
         gn_ref = float(z["gradnorm." + k])
-        assert e < (1.5e-1 if "contrastive" in k else 6e-2), (k, "grad vs fp32 truth", e)   # heads see only B_eff rows
+        assert e < (1.5e-1 if ("contrastive" in k or "tactile" in k) else 6e-2), (k, "grad vs fp32 truth", e)  # B_eff rows only
         assert abs(float(g.norm()) - gn_ref) <= 1.2e-1 * gn_ref, (k, float(g.norm()), gn_ref)
     # parameters the reference leaves without gradient stay without gradient (lm_head, unused tokenizer params)
     no_grad_ref = set(z["params_without_grad"].tolist())
