@@ -13,6 +13,7 @@
 //   warps 2-5 epilogue          (tcgen05.ld 32x32b -> registers -> fused bias/activation/residual -> global)
 // Two 128x256 fp32 accumulators (2 x 256 TMEM columns) are double-buffered so the epilogue of tile i overlaps
 // the main loop of tile i+1.
+#include <cstdlib>
 #include "mla_internal.cuh"
 #include "ptx.cuh"
 
@@ -384,8 +385,10 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, int M, int 
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  static const int group_override = [] { const char* e = getenv("MLA_GEMM_GROUP_M"); return e ? atoi(e) : 0; }();
   int group_m = int((48ll << 20) / (int64_t(BM) * K * 2));
   group_m = group_m < 4 ? 4 : (group_m > 64 ? 64 : group_m);
+  if (group_override > 0) group_m = group_override;   // tuning switch (tools/ab_overlap.sh)
   kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ma, mb, M, N, K, group_m, tiles > grid ? sched : nullptr, ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));

@@ -89,15 +89,17 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
   __shared__ float red[2][32];
   const int nvec = h >> 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  float wv[VPT][8], dwacc[VPT][8];
+  uint4 wp[VPT];           // weights stay packed (bf16x8) to keep two CTAs per SM
+  float dwacc[VPT][8];
 #pragma unroll
   for (int v = 0; v < VPT; ++v) {
     const int i = threadIdx.x + v * blockDim.x;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { dwacc[v][j] = 0.f; wv[v][j] = 0.f; }
-    if (i < nvec) unpack8(*reinterpret_cast<const uint4*>(w + i * 8), wv[v]);
+    for (int j = 0; j < 8; ++j) dwacc[v][j] = 0.f;
+    wp[v] = make_uint4(0, 0, 0, 0);
+    if (i < nvec) wp[v] = *reinterpret_cast<const uint4*>(w + i * 8);
   }
-  uint4 nx[VPT], ndy[VPT];
+  uint4 nx[VPT], ndy[VPT], nres[VPT];
   int64_t row = blockIdx.x;
   auto prefetch = [&](int64_t r) {
 #pragma unroll
@@ -105,28 +107,33 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
       const int i = threadIdx.x + v * blockDim.x;
       nx[v] = make_uint4(0, 0, 0, 0);
       ndy[v] = make_uint4(0, 0, 0, 0);
+      nres[v] = make_uint4(0, 0, 0, 0);
       if (r < rows && i < nvec) {
         nx[v] = *reinterpret_cast<const uint4*>(x + r * h + i * 8);
         ndy[v] = *reinterpret_cast<const uint4*>(dy + r * h + i * 8);
+        if (dres) nres[v] = *reinterpret_cast<const uint4*>(dres + r * h + i * 8);
       }
     }
   };
   prefetch(row);
   for (; row < rows; row += gridDim.x) {
-    float xf[VPT][8], dn[VPT][8], dyf[VPT][8];
+    float xf[VPT][8], dyf[VPT][8];
+    uint4 res[VPT];
     float ss = 0.f, dp = 0.f;
 #pragma unroll
     for (int v = 0; v < VPT; ++v) {
+      float wv[8];
       unpack8(nx[v], xf[v]);
       unpack8(ndy[v], dyf[v]);
+      unpack8(wp[v], wv);
+      res[v] = nres[v];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        dn[v][j] = dyf[v][j] * wv[v][j];
         ss += xf[v][j] * xf[v][j];
-        dp += dn[v][j] * xf[v][j];
+        dp += (dyf[v][j] * wv[j]) * xf[v][j];
       }
     }
-    prefetch(row + gridDim.x);
+    prefetch(row + gridDim.x);   // next row's x / dy / dres stay in flight across the reduction and the stores
     // one reduction for both sums
     ss = warp_sum(ss);
     dp = warp_sum(dp);
@@ -142,16 +149,17 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
     for (int v = 0; v < VPT; ++v) {
       const int i = threadIdx.x + v * blockDim.x;
       if (i < nvec) {
-        float o[8];
+        float o[8], wv[8];
+        unpack8(wp[v], wv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float n = xf[v][j] * rstd;
           dwacc[v][j] += dyf[v][j] * bf16_round(n);   // dy * n (n is what forward multiplied by w)
-          o[j] = bf16_round(rstd * (dn[v][j] - n * dot));
+          o[j] = bf16_round(rstd * (dyf[v][j] * wv[j] - n * dot));
         }
         if (dres) {
           float r[8];
-          unpack8(*reinterpret_cast<const uint4*>(dres + row * h + i * 8), r);
+          unpack8(res[v], r);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += r[j];
         }

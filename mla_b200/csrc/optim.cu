@@ -55,6 +55,38 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// 16-byte vector form (all pointers 16-byte aligned, n4 = n/4 groups): 4 loads + 3.5 stores of 16 B per group keep
+// more bytes in flight per thread than the scalar loop (30 B of HBM traffic per parameter either way).
+__device__ __forceinline__ float adamw_one(float& p, float g, float& m, float& v, float gs, float lr, float wd,
+                                           float beta1, float beta2, float eps, float step, float bc2_sqrt) {
+  const float gi = g * gs;
+  float pi = p * (1.f - lr * wd);
+  const float mi = beta1 * m + (1.f - beta1) * gi;
+  const float vi = beta2 * v + (1.f - beta2) * gi * gi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  pi -= step * (mi / denom);
+  p = pi; m = mi; v = vi;
+  return pi;
+}
+
+__global__ void __launch_bounds__(256)
+adamw_vec4_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                  uint2* __restrict__ p_bf16, int64_t n4, float lr, float beta1, float beta2, float eps, float wd,
+                  float bc1, float bc2_sqrt, const float* __restrict__ gscale) {
+  const float gs = gscale ? gscale[0] : 1.f;
+  const float step = lr / bc1;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
+    float4 pv = p[i], mv = m[i], vv = v[i];
+    const float4 gv = g[i];
+    const float a = adamw_one(pv.x, gv.x, mv.x, vv.x, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    const float b = adamw_one(pv.y, gv.y, mv.y, vv.y, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    const float c = adamw_one(pv.z, gv.z, mv.z, vv.z, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    const float d = adamw_one(pv.w, gv.w, mv.w, vv.w, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    p[i] = pv; m[i] = mv; v[i] = vv;
+    if (p_bf16) p_bf16[i] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+  }
+}
+
 }  // namespace mla
 
 using namespace mla;
@@ -84,6 +116,18 @@ extern "C" int mla_adamw_f32(void* p, const void* g, void* m, void* v, void* p_b
   if (step < 1) return set_error(MLA_ERR_ARG, "adamw: step must be >= 1");
   const float bc1 = 1.f - powf(beta1, float(step));
   const float bc2 = 1.f - powf(beta2, float(step));
+  const uintptr_t al = reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                       reinterpret_cast<uintptr_t>(v);
+  if ((n & 3) == 0 && (al & 15) == 0 && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0) {
+    const int64_t n4 = n >> 2;
+    int64_t blocks4 = (n4 + 255) / 256;
+    int64_t cap4 = int64_t(num_sms()) * 8;
+    adamw_vec4_kernel<<<int(blocks4 < cap4 ? blocks4 : cap4), 256, 0, (cudaStream_t)stream>>>(
+        (float4*)p, (const float4*)g, (float4*)m, (float4*)v, (uint2*)p_bf16, n4, lr, beta1, beta2, eps, weight_decay,
+        bc1, sqrtf(bc2), (const float*)grad_scale);
+    MLA_CHECK_LAUNCH("adamw");
+    return MLA_OK;
+  }
   int64_t blocks = (n + 255) / 256;
   int64_t cap = int64_t(num_sms()) * 16;
   adamw_kernel<<<int(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(

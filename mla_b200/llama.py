@@ -15,6 +15,7 @@ aliases (no autograd-side accumulation buffers).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Tuple
 
@@ -22,6 +23,25 @@ import torch
 import torch.nn as nn
 
 from . import ops
+
+# Optional stream overlap of the backward pass (MLA_WGRAD_STREAM=1, default OFF).  The four weight-gradient GEMMs of
+# a layer do not feed the activation-gradient chain, so they can be issued on a second ("side") stream and the
+# HBM-bound kernels of the chain (SwiGLU/RMSNorm backward, RoPE) then run next to a wgrad GEMM on the SMs' spare
+# registers.  MEASURED on B200 (profiles/r01_overlap_ab.txt): the step gets SLOWER (726 -> 790 ms) — the whole step is
+# power-capped (sw_power_cap, ~1380 of 1965 MHz), so concurrent HBM traffic lowers the clocks the GEMMs run at.  Kept
+# as a tested switch (tests/test_trainer_gpu.py proves the two orders are bit-identical), not as the default.
+OVERLAP = {"wgrad": os.environ.get("MLA_WGRAD_STREAM", "0") == "1"}
+_SIDE_STREAMS: dict = {}
+
+
+def side_stream(device) -> "torch.cuda.Stream":
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=key)
+        _SIDE_STREAMS[key] = st
+    return st
+
 
 # What a layer keeps for backward.
 #   "layer": only its input; the whole layer is recomputed in backward (what the reference's FSDP activation
@@ -89,6 +109,7 @@ class LlamaDecoderLayer(nn.Module):
         self._g = None          # fp32 gradient arenas
         self._grads_fresh = True
         self._grad_ready_cb = None   # set by the data-parallel trainer: called when this layer's arenas are final
+        self._weights_ready = None   # CUDA event: the optimizer's side-stream update of this layer has landed
 
     # ------------------------------------------------------------------ parameter plumbing
     def _masters(self) -> List[nn.Parameter]:
@@ -100,6 +121,9 @@ class LlamaDecoderLayer(nn.Module):
     def compute_weights(self):
         """bf16 [q;k;v], o, [gate;up], down, ln1, ln2 — refreshed when any fp32 master changed."""
         ps = self._masters()
+        if self._weights_ready is not None:
+            torch.cuda.current_stream().wait_event(self._weights_ready)
+            self._weights_ready = None
         vers = tuple(p._version for p in ps) + tuple(p.data_ptr() for p in ps)
         if self._c is None or vers != self._versions:
             h, f = self.hidden_size, self.inter
@@ -200,30 +224,51 @@ class LlamaDecoderLayer(nn.Module):
         gqkv, go, ggu, gd, g1, g2 = self._g
         if not acc:
             g1.zero_(); g2.zero_()   # the norm-weight kernels accumulate atomically
+        overlap = OVERLAP["wgrad"] and dy.is_cuda
+        main = torch.cuda.current_stream() if overlap else None
+        side = side_stream(dy.device) if overlap else None
+
+        def wgrad(d, a, out):
+            """out (+)= d^T a.  With overlap: on the side stream, ordered after everything issued so far."""
+            if not overlap:
+                ops.gemm(d, a, a_mn=True, b_mn=True, out=out, accumulate=acc)
+                return
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ops.gemm(d, a, a_mn=True, b_mn=True, out=out, accumulate=acc)
+            d.record_stream(side)    # the caching allocator must not recycle these before the side GEMM has read them
+            a.record_stream(side)
+
         # ---- MLP half
-        ops.gemm(dy, act, a_mn=True, b_mn=True, out=gd, accumulate=acc)              # dWd  = dy^T act
+        wgrad(dy, act, gd)                                                           # dWd  = dy^T act
         dact = ops.gemm(dy, wd, b_mn=True)                                           # dact = dy Wd
         del act
         dgu = ops.swiglu_bwd(dact, gu)
         del dact, gu
-        ops.gemm(dgu, n2, a_mn=True, b_mn=True, out=ggu, accumulate=acc)             # dWgu = dgu^T n2
+        wgrad(dgu, n2, ggu)                                                          # dWgu = dgu^T n2
         dn2 = ops.gemm(dgu, wgu, b_mn=True)                                          # dn2  = dgu Wgu
         del dgu, n2
         dx_mid = ops.rmsnorm_bwd(dn2, x_mid, l2, self.eps, dres=dy, dw=g2)
         del dn2
         # ---- attention half
-        ops.gemm(dx_mid, ctx, a_mn=True, b_mn=True, out=go, accumulate=acc)          # dWo  = dx_mid^T ctx
+        wgrad(dx_mid, ctx, go)                                                       # dWo  = dx_mid^T ctx
         dctx = ops.gemm(dx_mid, wo, b_mn=True)
         dqkv = ops.attn_bwd(dctx, qkv, ctx, lse, sh.B, sh.S, sh.H, sh.D, sh.mask)
         del dctx, ctx, qkv
         ops.rope_(dqkv, 0, 2 * sh.H, sh.D, sh.S, sh.cos, sh.sin, transpose=True)
-        ops.gemm(dqkv, n1, a_mn=True, b_mn=True, out=gqkv, accumulate=acc)           # dWqkv = dqkv^T n1
+        wgrad(dqkv, n1, gqkv)                                                        # dWqkv = dqkv^T n1
         dn1 = ops.gemm(dqkv, wqkv, b_mn=True)
         del dqkv, n1
         dx = ops.rmsnorm_bwd(dn1, x, l1, self.eps, dres=dx_mid, dw=g1)
         self._grads_fresh = False
         if self._grad_ready_cb is not None:
-            self._grad_ready_cb(self)
+            if overlap:
+                # the arenas are final once BOTH streams are done: issue the exchange behind the side stream
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    self._grad_ready_cb(self)
+            else:
+                self._grad_ready_cb(self)
         return dx
 
     def _mlp_half_no_down(self, x_mid: torch.Tensor):

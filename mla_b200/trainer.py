@@ -23,7 +23,13 @@ import torch.distributed as dist
 
 from . import _lib, ops
 from ._lib import check
-from .llama import LlamaDecoderLayer
+from .llama import LlamaDecoderLayer, side_stream
+
+# Optional: AdamW of the decoder layers on the side stream (MLA_ADAM_STREAM=1, default OFF).  The update is HBM-bound
+# and layer k's new weights are first needed by layer k's forward, so it can run next to the NEXT step's forward
+# GEMMs, each layer's forward waiting on that layer's event only.  Measured slower on the power-capped B200 (see
+# llama.OVERLAP), so it stays a tested switch.
+ADAM_OVERLAP = {"on": __import__("os").environ.get("MLA_ADAM_STREAM", "0") == "1"}
 
 
 class DataParallelTrainer:
@@ -109,7 +115,12 @@ class DataParallelTrainer:
     def step(self) -> None:
         """clip_grad_norm_ + AdamW.step + zero_grad, after loss.backward()."""
         lib, s = _lib.lib(), ops._stream()
+        cuda = self._sumsq.is_cuda
+        main = torch.cuda.current_stream() if cuda else None
+        side = side_stream(self._sumsq.device) if cuda else None
         self.exchange()
+        if cuda:
+            main.wait_stream(side)      # weight-gradient GEMMs issued on the side stream (llama.OVERLAP)
         self.step_count += 1
         lr = self.current_lr()
         # global norm over every gradient that exists (params without grad are skipped, as torch does)
@@ -125,16 +136,28 @@ class DataParallelTrainer:
                 check(lib.mla_sumsq_f32(ops._p(g), C.c_int64(g.numel()), ops._p(self._sumsq), s))
         check(lib.mla_clip_coef(ops._p(self._sumsq), C.c_float(self.max_grad_norm or 0.0), C.c_float(1.0 / self.world),
                                 ops._p(self._scale), s))
-        for l in self.layers:
-            if l._grads_fresh:
-                continue
-            h, f = l.hidden_size, l.inter
-            wqkv, wo, wgu, wd, l1, l2 = l.compute_weights()
-            dsts = [wqkv[:h], wqkv[h:2 * h], wqkv[2 * h:], wo, wgu[:f], wgu[f:], wd, l1, l2]
-            for p, g, dst in zip(l._masters(), l._views, dsts):
-                if p.requires_grad:
-                    self._adam(p, g, p.ndim > 1, dst, lr)
-            l.mark_grads_fresh()
+        overlap = cuda and ADAM_OVERLAP["on"]
+        for l in self.layers:           # Adam state is allocated (first step) on the main stream
+            if not l._grads_fresh:
+                for p in l._masters():
+                    if p.requires_grad and id(p) not in self.state:
+                        self.state[id(p)] = (torch.zeros_like(p.data, memory_format=torch.contiguous_format),
+                                             torch.zeros_like(p.data, memory_format=torch.contiguous_format))
+        if overlap:
+            side.wait_stream(main)
+        with torch.cuda.stream(side) if overlap else _nullctx():
+            for l in self.layers:
+                if l._grads_fresh:
+                    continue
+                h, f = l.hidden_size, l.inter
+                wqkv, wo, wgu, wd, l1, l2 = l.compute_weights()
+                dsts = [wqkv[:h], wqkv[h:2 * h], wqkv[2 * h:], wo, wgu[:f], wgu[f:], wd, l1, l2]
+                for p, g, dst in zip(l._masters(), l._views, dsts):
+                    if p.requires_grad:
+                        self._adam(p, g, p.ndim > 1, dst, lr)
+                l.mark_grads_fresh()
+                if overlap:
+                    l._weights_ready = side.record_event()
         for _, p, decay in self.other:
             if p.grad is None:
                 continue
@@ -146,6 +169,14 @@ class DataParallelTrainer:
     def grad_norm(self) -> torch.Tensor:
         """Mean-gradient global norm of the last step (device scalar)."""
         return self._scale[1]
+
+
+class _nullctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 def plan_save_levels(model: torch.nn.Module, tokens: int, reserve_gb: float = 10.0) -> List[str]:
