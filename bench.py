@@ -105,6 +105,21 @@ def build_model(workload: str, T: int = 0):
     return mla
 
 
+def GEMM_SHAPES(T):
+    """(M, N, K) of the 12 launches timed by gemm_roofline: forward, dgrad (bf16 out), wgrad (fp32 out)."""
+    return [(T, 3 * H, H), (T, H, H), (T, 2 * F, H), (T, H, F), (T, H, 3 * H), (T, H, H), (T, H, 2 * F), (T, F, H),
+            (3 * H, H, T), (H, H, T), (2 * F, H, T), (H, F, T)]
+
+
+def ncu_gemm_traffic():
+    """Mean DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (None if absent)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")))["gemm"]
+        return round(sum((r["dram_read_MB"] + r["dram_write_MB"]) * 1e6 for r in d) / len(d))
+    except Exception:
+        return None
+
+
 def gemm_roofline(tokens: int, peak_tf: float, iters: int = 5):
     """The dominant kernel is the tcgen05 GEMM (~97 % of the step's FLOPs): time every GEMM shape of a decoder layer
     (forward, dgrad, wgrad) back to back with CUDA events on the launching stream and report algorithmic FLOP/s."""
@@ -142,7 +157,11 @@ def gemm_roofline(tokens: int, peak_tf: float, iters: int = 5):
     flops = sum(f for _, f in calls)
     ach = flops / ms / 1e9
     return {"bound": "tensor", "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
-            "traffic": None, "kernel": "gemm_bf16_kernel (tcgen05, 12 GEMM shapes of one decoder layer fwd+bwd)",
+            "traffic": ncu_gemm_traffic(), "traffic_unit": "bytes per launch (dram read+write, ncu --set full, mean of "
+            "the same 12 launches: profiles/r01_ncu_full_summary.json)",
+            "algorithmic_bytes_per_launch": round(sum(2.0 * (m * k + n * k) + (2.0 if i < 8 else 4.0) * m * n
+                                                      for i, (m, n, k) in enumerate(GEMM_SHAPES(T))) / 12),
+            "kernel": "gemm_bf16_kernel (tcgen05, 12 GEMM shapes of one decoder layer fwd+bwd)",
             "launch_ms_avg": round(ms / len(calls), 4)}
 
 

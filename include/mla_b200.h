@@ -259,6 +259,104 @@ int mla_action_digitize(const void* x, int32_t x_is_f64, int64_t n, const void* 
 int mla_action_decode(const void* ids, int64_t n, const void* centers, int32_t n_centers, int64_t vocab_size,
                       void* out, void* stream);
 
+/* ---- post-training generation heads (models/mla/generation/models.py, gen_loss.py, utils.py; prismatic.py:771-838,
+ *      :1075-1113) — SURVEY.md §8 A14 ----------------------------------------------------------------------------
+ * mha_fwd / mha_bwd: the attention core of nn.MultiheadAttention / nn.TransformerDecoderLayer (generation/models.py
+ * :44,:103-122,:405-413): non-causal softmax(scale * Q K^T) V for any even head_dim <= 1024 (multiple of 4), Lq != Lk;
+ * bf16 in/out, fp32 math.  q row (b,i) = q + (b*len_q + i)*ldq + head*head_dim (likewise k, v with len_k), so packed
+ * in_proj outputs are consumed in place.  keep_mask (u8 [batch, heads, len_q, len_k], may be NULL) + keep_scale
+ * = 1/(1-p) is the attention-probability dropout of the reference's train mode.  lse f32 [batch, heads, len_q].
+ * Backward (delta f32 [batch, heads, len_q] is scratch) writes dq, dk, dv with their own row strides. */
+typedef struct mla_mha_args {
+  const void *q, *k, *v;
+  int64_t ldq, ldk, ldv;
+  void* o;
+  int64_t ldo;
+  void* lse;
+  const void* keep_mask;
+  float keep_scale;
+  int32_t batch, heads, len_q, len_k, head_dim;
+  float scale;
+  const void* d_o;
+  int64_t ld_do;
+  void* delta;
+  void *dq, *dk, *dv;
+  int64_t ld_dq, ld_dk, ld_dv;
+} mla_mha_args;
+int mla_mha_fwd(const mla_mha_args* a, void* stream);
+int mla_mha_bwd(const mla_mha_args* a, void* stream);
+
+/* nn.LayerNorm in fp32 (CUDA autocast runs layer_norm in fp32): x, y f32 [rows, h]; w, b f32 [h]; y_bf16 optional bf16
+ * copy of y; mean, rstd f32 [rows] saved for backward.  Backward: dx f32; dw, db f32 [h] are ACCUMULATED (atomics). */
+int mla_ln_f32_fwd(const void* x, const void* w, const void* b, void* y, void* y_bf16, void* mean, void* rstd,
+                   int64_t rows, int32_t h, float eps, void* stream);
+int mla_ln_f32_bwd(const void* dy, const void* x, const void* w, const void* mean, const void* rstd, void* dx, void* dw,
+                   void* db, int64_t rows, int32_t h, void* stream);
+/* helpers of the heads' fp32 residual stream: bf16 -> f32 cast; out = a(f32) + b(bf16) (optionally rounded to bf16, the
+ * value a bf16 + bf16 add of the reference produces); y = keep[i / per_mask] ? x * scale : 0 (dropout / DropPath masks
+ * drawn by the host-side generator); mean over the sequence [B, S, C] -> [B, C] (generation/models.py:352) and its
+ * backward. */
+int mla_cast_bf16_f32(const void* x, void* y, int64_t n, void* stream);
+int mla_add_f32_bf16(const void* a, const void* b, void* out, int64_t n, int32_t round_bf16, void* stream);
+int mla_mask_scale_bf16(const void* x, const void* keep, void* y, int64_t n, int64_t per_mask, float scale, void* stream);
+int mla_seq_mean_fwd(const void* x, void* y, int32_t B, int32_t S, int32_t C, void* stream);
+int mla_seq_mean_bwd(const void* dy, void* dx, int32_t B, int32_t S, int32_t C, void* stream);
+/* nn.BatchNorm1d in train mode (+ReLU) over rows: x, y, dx bf16 [R, C] (the reference's [B, C, L] transposed,
+ * generation/models.py:332-337); w, b f32; batch statistics over the R rows, running stats updated (momentum, unbiased
+ * variance).  Backward writes dw, db f32 [C]. */
+int mla_bn_rows_fwd(const void* x, const void* w, const void* b, void* y, void* mean, void* rstd, void* running_mean,
+                    void* running_var, int32_t R, int32_t C, float eps, float momentum, int32_t relu, void* stream);
+int mla_bn_rows_bwd(const void* dy, const void* x, const void* y, const void* w, const void* mean, const void* rstd,
+                    void* dx, void* dw, void* db, int32_t R, int32_t C, int32_t relu, void* stream);
+/* tile_rows: learned table f32 [P*h] (queries / positional embedding; bf16 in the reference) repeated for B samples ->
+ * f32 [B*P*h] holding the bf16-rounded values; backward sums over samples.  mask_tokens: MAE decoder input
+ * (generation/models.py:183-187) = (roi ? mask_token : image feature) + pos, bf16 arithmetic, written as f32 [B*P, h];
+ * backward writes d_feat bf16, d_pos f32 [P, h] and ACCUMULATES d_mask_token f32 [h] (caller zeroes it). */
+int mla_tile_rows_fwd(const void* table, void* out, int64_t table_elems, int32_t B, void* stream);
+int mla_tile_rows_bwd(const void* d_out, void* d_table, int64_t table_elems, int32_t B, void* stream);
+int mla_mask_tokens_fwd(const void* feat, const void* roi, const void* mask_token, const void* pos, void* out, int32_t B,
+                        int32_t P, int32_t h, void* stream);
+int mla_mask_tokens_bwd(const void* d_out, const void* roi, void* d_feat, void* d_mask_token, void* d_pos, int32_t B,
+                        int32_t P, int32_t h, void* stream);
+/* create_roi_mask_from_indices + dilate_mask (generation/utils.py:41-70): patch_idx i64 [B, n_pts, 2] (row, col) ->
+ * mask u8 [B, G, G] dilated by a ksize x ksize max-pool. */
+int mla_roi_mask(const void* patch_idx, void* mask, int32_t B, int32_t n_pts, int32_t G, int32_t ksize, void* stream);
+
+/* Image head tail + image losses in one pass per patch (ImageGenerationModule.forward tail and
+ * _generate_generated_patches, generation/models.py:193-286; compute_generation_losses prismatic.py:779-816).
+ * cur / nxt: f32 images, element strides per image / channel (row stride = width); sample b uses image b % n_images
+ * (MLA.forward tiles the batch, model_mla.py:160-167); patch n = (b, gy, gx), n_patches = B_eff * grid * grid.
+ * delta_raw bf16 [n_patches, ld_delta >= 3*patch^2], ao_raw bf16 [n_patches, ld_ao >= 3] = raw (alpha, offset_x,
+ * offset_y) head outputs; roi u8 [n_patches].  Forward writes blended f32 [n_patches, 3*patch^2] (image_generation),
+ * delta_all / alpha_all / offset_all (bf16), sums f32 [5] (scratch), losses f32 [4] = {image_gen_loss, roi, bg,
+ * delta reward} and coef f32 [4] for backward.  Backward (grad_scale f32 [1] = upstream gradient of image_gen_loss)
+ * writes d_delta_raw / d_ao_raw with the raw tensors' strides. */
+typedef struct mla_gen_image_args {
+  const void *cur, *nxt;
+  int64_t cur_stride_b, cur_stride_c, nxt_stride_b, nxt_stride_c;
+  int32_t n_images, width, patch, grid, n_patches;
+  const void* delta_raw;
+  int64_t ld_delta;
+  const void* ao_raw;
+  int64_t ld_ao;
+  const void* roi;
+  float delta_clip, max_shift, gen_weight;
+  void *blended, *delta_all, *alpha_all, *offset_all, *sums, *losses, *coef;
+  const void* grad_scale;
+  void *d_delta_raw, *d_ao_raw;
+} mla_gen_image_args;
+int mla_gen_image_fwd(const mla_gen_image_args* a, void* stream);
+int mla_gen_image_bwd(const mla_gen_image_args* a, void* stream);
+
+/* chamfer_distance_l2 (generation/gen_loss.py:12-18): pred bf16 [B, N1, 3], gt f32 [n_gt, N2, 3] (sample b uses
+ * gt[b % n_gt]); idx / dist keep the arg-min pairs for backward; loss f32 [1].  Backward accumulates into dpred_f32
+ * [B, N1, 3] (caller zeroes it), scaled by grad_scale f32 [1]. */
+int mla_chamfer_fwd(const void* pred, const void* gt, int32_t B, int32_t N1, int32_t N2, int32_t n_gt, void* idx1,
+                    void* dist1, void* idx2, void* dist2, void* loss, void* stream);
+int mla_chamfer_bwd(const void* pred, const void* gt, int32_t B, int32_t N1, int32_t N2, int32_t n_gt, const void* idx1,
+                    const void* dist1, const void* idx2, const void* dist2, const void* grad_scale, void* dpred_f32,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif

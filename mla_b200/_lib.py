@@ -61,3 +61,31 @@ class AttnArgs(C.Structure):
         ("d_o", C.c_void_p), ("delta", C.c_void_p),
         ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("ld_dqkv", C.c_int64),
     ]
+
+
+class MhaArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+        ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64),
+        ("o", C.c_void_p), ("ldo", C.c_int64), ("lse", C.c_void_p),
+        ("keep_mask", C.c_void_p), ("keep_scale", C.c_float),
+        ("batch", C.c_int32), ("heads", C.c_int32), ("len_q", C.c_int32), ("len_k", C.c_int32), ("head_dim", C.c_int32),
+        ("scale", C.c_float),
+        ("d_o", C.c_void_p), ("ld_do", C.c_int64), ("delta", C.c_void_p),
+        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p),
+        ("ld_dq", C.c_int64), ("ld_dk", C.c_int64), ("ld_dv", C.c_int64),
+    ]
+
+
+class GenImageArgs(C.Structure):
+    _fields_ = [
+        ("cur", C.c_void_p), ("nxt", C.c_void_p),
+        ("cur_stride_b", C.c_int64), ("cur_stride_c", C.c_int64), ("nxt_stride_b", C.c_int64), ("nxt_stride_c", C.c_int64),
+        ("n_images", C.c_int32), ("width", C.c_int32), ("patch", C.c_int32), ("grid", C.c_int32), ("n_patches", C.c_int32),
+        ("delta_raw", C.c_void_p), ("ld_delta", C.c_int64), ("ao_raw", C.c_void_p), ("ld_ao", C.c_int64),
+        ("roi", C.c_void_p),
+        ("delta_clip", C.c_float), ("max_shift", C.c_float), ("gen_weight", C.c_float),
+        ("blended", C.c_void_p), ("delta_all", C.c_void_p), ("alpha_all", C.c_void_p), ("offset_all", C.c_void_p),
+        ("sums", C.c_void_p), ("losses", C.c_void_p), ("coef", C.c_void_p),
+        ("grad_scale", C.c_void_p), ("d_delta_raw", C.c_void_p), ("d_ao_raw", C.c_void_p),
+    ]

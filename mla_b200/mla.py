@@ -38,8 +38,6 @@ class MLA(nn.Module):
         self.use_diff, self.use_pointcloud, self.use_tactile = use_diff, use_pointcloud, use_tactile
         self.use_contrastive, self.use_generation = use_contrastive, use_generation
         self.gen_image, self.use_roi, self.gen_pointcloud, self.gen_tactile = gen_image, use_roi, gen_pointcloud, gen_tactile
-        if use_generation and (gen_image or gen_pointcloud or gen_tactile):
-            raise NotImplementedError("post-training generation heads (config 5) are not built yet")
         self.vlm = vlm
         self.future_action_window_size = future_action_window_size
         self.vlm.future_action_window_size = future_action_window_size
@@ -119,6 +117,16 @@ class MLA(nn.Module):
                                        "diff_loss", "image_gen_loss", "point_cloud_gen_loss", "tactile_gen_loss")}
         diff_loss = ops.MSEFn.apply(noise_pred, noise)
         total = diff_loss
+        # model_mla.py:218-226 — generation losses are added before the contrastive ones
+        if self.use_generation and self.gen_image:
+            loss_dict["image_gen_loss"] = generation_losses["image_gen_loss"]
+            total = total + generation_losses["image_gen_loss"]
+        if self.use_generation and self.gen_pointcloud:
+            loss_dict["point_cloud_gen_loss"] = generation_losses["point_cloud_gen_loss"]
+            total = total + generation_losses["point_cloud_gen_loss"]
+        if self.use_generation and self.gen_tactile:
+            loss_dict["tactile_gen_loss"] = generation_losses["tactile_gen_loss"]
+            total = total + generation_losses["tactile_gen_loss"]
         if self.use_contrastive:
             loss_dict["img_pc_contrastive_loss"] = output.img_pc_contrastive_loss
             total = total + output.img_pc_contrastive_loss

@@ -8,7 +8,8 @@ stages and `forward` returns as the reference; the compute is libmla_b200 kernel
     FinalLayer on the T+1 noisy-action rows only (the reference runs it on all S rows and slices, :1117-1126 —
     row-wise ops, identical values).
 
-Post-training generation heads (models/mla/generation, config 5) are not built yet: `use_generation=True` raises.
+Post-training generation heads (models/mla/generation, config 5): `generation_manager` (mla_b200/generation.py) runs
+on the last hidden state in train mode exactly where the reference calls it (prismatic.py:1075-1113).
 """
 from __future__ import annotations
 
@@ -23,6 +24,7 @@ from . import _lib, ops
 from ._lib import check
 from .backbone import CausalLMOutputWithPast, LLMBackbone
 from .contrastive import get_camera_params, project_points
+from .generation import MultimodalGenerationManager, compute_generation_losses, roi_mask
 from .modules import (ActionEmbedder, FinalLayer, LabelEmbedder, MLP_GELU, MLPProjector, TimestepEmbedder)
 from .vision import VisionTokenizer
 
@@ -36,7 +38,12 @@ class PrismaticVLM(nn.Module):
                  use_diff: bool = False, use_pointcloud: bool = False, use_tactile: bool = False,
                  use_contrastive: bool = False, llm_vision_layers: int = 1, use_generation: bool = True,
                  gen_image: bool = False, gen_pointcloud: bool = True, gen_tactile: bool = True,
-                 use_roi: bool = False, image_hidden_dim: int = 1024, **kwargs) -> None:
+                 use_roi: bool = False, image_hidden_dim: int = 1024, num_image_gen_queries: int = 128,
+                 image_decoder_layers: int = 3, image_decoder_heads: int = 8, image_patch_size: int = 42,
+                 roi_dilation_kernel_size: int = 3, pointcloud_trans_dim: int = 1024,
+                 pointcloud_decoder_layers: int = 4, pointcloud_decoder_heads: int = 8, pointcloud_group_size: int = 8,
+                 pointcloud_num_groups: int = 128, tactile_decoder_layers: int = 2, tactile_decoder_heads: int = 4,
+                 **kwargs) -> None:
         super().__init__()
         self.model_family, self.model_id = "prismatic", model_id
         self.llm_backbone = llm_backbone
@@ -49,9 +56,7 @@ class PrismaticVLM(nn.Module):
         self.use_roi = use_roi
         self.gen_pointcloud = gen_pointcloud and use_generation
         self.gen_tactile = gen_tactile and use_generation
-        if use_generation and (self.gen_image or self.gen_pointcloud or self.gen_tactile):
-            raise NotImplementedError("post-training generation heads (config 5) are not built yet; pass "
-                                      "use_generation=False (pretrain / SFT stages)")
+        self.roi_dilation_kernel_size = roi_dilation_kernel_size
 
         # prismatic.py:208-212 — likelihood helper tokens
         self.string2idx = {}
@@ -72,8 +77,8 @@ class PrismaticVLM(nn.Module):
             from .pointcloud import PointTokenizer
             self.vision_tower_3d = PointTokenizer(in_channels=3, embed_dim=768, depth=12, num_heads=12)
             self.projector_3d = MLPProjector(self.vision_tower_3d.embed_dim, token_size)
+        self.tactile_dim = 12      # the reference sets it under use_tactile only and then crashes at :267 without it
         if self.use_tactile:
-            self.tactile_dim = 12
             self.tactile_embedder = ActionEmbedder(action_size=self.tactile_dim, hidden_size=token_size)
         self.proprio_embedder = ActionEmbedder(action_size=action_dim, hidden_size=token_size)
         if self.use_diff:
@@ -81,6 +86,16 @@ class PrismaticVLM(nn.Module):
             self.t_embedder = TimestepEmbedder(token_size)
             self.z_embedder = LabelEmbedder(in_size=token_size, hidden_size=token_size, dropout_prob=class_dropout_prob)
             self.final_layer = FinalLayer(token_size, action_dim)
+        if self.use_generation:         # prismatic.py:247-270
+            self.generation_manager = MultimodalGenerationManager(
+                token_size=token_size, use_image_generation=self.gen_image, num_image_gen_queries=num_image_gen_queries,
+                image_decoder_layers=image_decoder_layers, image_decoder_heads=image_decoder_heads,
+                image_patch_size=image_patch_size, use_roi=use_roi, roi_dilation_kernel_size=roi_dilation_kernel_size,
+                use_pointcloud_generation=self.gen_pointcloud, pointcloud_trans_dim=pointcloud_trans_dim,
+                pointcloud_decoder_layers=pointcloud_decoder_layers, pointcloud_decoder_heads=pointcloud_decoder_heads,
+                pointcloud_group_size=pointcloud_group_size, pointcloud_num_groups=pointcloud_num_groups,
+                use_tactile_generation=self.gen_tactile, tactile_dim=self.tactile_dim,
+                tactile_decoder_layers=tactile_decoder_layers, tactile_decoder_heads=tactile_decoder_heads)
 
         self.all_module_keys = ["vision_tower_2d", "projector_2d", "llm_backbone", "proprio_embedder"]
         if self.use_diff:
@@ -89,6 +104,8 @@ class PrismaticVLM(nn.Module):
             self.all_module_keys.extend(["vision_tower_3d", "projector_3d"])
         if self.use_tactile:
             self.all_module_keys.extend(["tactile_embedder"])
+        if self.use_generation:
+            self.all_module_keys.append("generation_manager")
         self.trainable_module_keys: List[str] = []
         self.vision_backbone_requires_grad = False
         self.initialize_weights()
@@ -138,6 +155,8 @@ class PrismaticVLM(nn.Module):
             self.projector_3d.requires_grad_(True)
         if self.use_tactile:
             self.tactile_embedder.requires_grad_(True)
+        if stage == "post-training":
+            self.generation_manager.requires_grad_(True)       # prismatic.py:501 (requires use_generation, as there)
         if stage == "finetune":
             keys = ["llm_backbone", "projector_2d", "proprio_embedder"]
             if self.use_diff:
@@ -154,6 +173,8 @@ class PrismaticVLM(nn.Module):
                 keys += ["vision_tower_3d", "projector_3d"]
             if self.use_tactile:
                 keys += ["tactile_embedder"]
+            if stage == "post-training":
+                keys += ["generation_manager"]
         self.trainable_module_keys = keys
         self.vision_backbone_requires_grad = train_towers
 
@@ -163,7 +184,7 @@ class PrismaticVLM(nn.Module):
         return partial(_or_policy, policies=[
             partial(_module_wrap_policy, module_classes={PointTokenizer, VisionTokenizer}),
             self.llm_backbone.get_fsdp_wrapping_policy(),
-            partial(_module_wrap_policy, module_classes={MLP_GELU}),
+            partial(_module_wrap_policy, module_classes={MLP_GELU, MultimodalGenerationManager}),
         ])
 
     # ------------------------------------------------------------------ fusion
@@ -181,7 +202,8 @@ class PrismaticVLM(nn.Module):
         views = images if isinstance(images, dict) else {"front_image": images}
         assert "front_image" in views, "front_image must be present in multi-view images"
         dev = self.llm_backbone.llm.lm_head.weight.device
-        front = self._image_tokens(views["front_image"].to(dev, non_blocking=True), image_repeat)
+        self._front_px = views["front_image"].to(dev, non_blocking=True)     # kept for the image generation head
+        front = self._image_tokens(self._front_px, image_repeat)
         B, n_img, _ = front.shape
         centers = None
         if self.use_pointcloud and pointcloud is not None:
@@ -304,6 +326,28 @@ class PrismaticVLM(nn.Module):
         output.last_true_indices = lti
         generation_outputs: Dict[str, torch.Tensor] = {}
         generation_losses: Dict[str, torch.Tensor] = {}
+        if (self.use_generation and (self.gen_image or self.gen_pointcloud or self.gen_tactile) and self.training):
+            # prismatic.py:1075-1113.  next_* arrive un-repeated (sample b of the B_eff = B*R rows uses entry b % B,
+            # which is what MLA.forward's .repeat(R, ...) of the reference produces)
+            hidden16 = output.hidden_states[-1].reshape(B * S, h)
+            img_feat = cur_px = nxt_px = roi = None
+            if self.gen_image:
+                assert next_images is not None
+                img_feat = fused[:, N_pc:N_pc + N_img, :].reshape(B * N_img, h)
+                cur_px = self._front_px.float()
+                nxt_px = next_images.to(dev, non_blocking=True).float()
+                if self.use_roi:
+                    roi = roi_mask(patch_indices, 16, self.roi_dilation_kernel_size)
+            if self.gen_pointcloud:
+                assert next_point_cloud is not None
+            if self.gen_tactile:
+                assert next_tactile is not None
+            generation_outputs = self.generation_manager.run(hidden16, B, S, img_feat, cur_px, nxt_px, roi)
+            generation_losses = compute_generation_losses(
+                generation_outputs, self.gen_image, self.gen_pointcloud, self.gen_tactile,
+                next_point_cloud.to(dev, non_blocking=True) if next_point_cloud is not None else None,
+                next_tactile.to(dev, non_blocking=True) if next_tactile is not None else None)
+        self._front_px = None
         if self.use_diff:
             last = output.hidden_states[-1].reshape(B * S, h)
             rows = ops.GatherRowsFn.apply(last, head_rows.view(-1))                           # [B*(T+1), h]

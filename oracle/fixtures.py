@@ -32,7 +32,7 @@ def fill_state_dict(sd: Dict[str, torch.Tensor], seed: int = 0) -> Dict[str, tor
 
 def synthetic_batch(B: int, Lt: int, T: int = 0, image_hw: int = 672, n_points: int = 1024, seed: int = 1234,
                     use_pointcloud: bool = False, use_tactile: bool = False, pad_last: int = 0,
-                    extra_views: int = 0) -> Dict:
+                    extra_views: int = 0, generation: bool = False) -> Dict:
     """CPU fp32 batch in the collator's contract (util/data_utils.py:100-195): images f32 [B,4,H,W] with an all-ones
     mask channel, point clouds inside the RLBench workspace box, ids with BOS first and EOS (id 2) last."""
     g = torch.Generator().manual_seed(seed)
@@ -60,4 +60,10 @@ def synthetic_batch(B: int, Lt: int, T: int = 0, image_hw: int = 672, n_points: 
     if use_tactile:
         batch["tactile"] = torch.rand(B, 12, generator=g)
         batch["gripper_xyz"] = torch.rand(B, 3, generator=g) * torch.tensor([0.8, 1.0, 0.8]) + torch.tensor([-0.1, -0.5, 0.75])
+    if generation:      # post-training targets: next frame, next point cloud, next tactile reading
+        g2 = torch.Generator().manual_seed(seed + 77)
+        batch["next_images"] = torch.randn(B, 3, image_hw, image_hw, generator=g2)
+        batch["next_point_cloud"] = (torch.rand(B, n_points, 3, generator=g2) * torch.tensor([0.8, 1.0, 0.8])
+                                     + torch.tensor([-0.1, -0.5, 0.75]))
+        batch["next_tactile"] = torch.rand(B, 12, generator=g2)
     return batch

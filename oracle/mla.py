@@ -306,7 +306,8 @@ def forward(sd: Dict[str, Tensor], batch: Dict, cfg: Dict, draws: Dict, compute_
     """MLA.forward (model_mla.py:118-234) with use_diff=True.
 
     cfg: n_heads, rms_eps, future_action_window_size, repeated_diffusion_steps, use_pointcloud, use_tactile,
-         use_contrastive, camera_name, rmsnorm_variance_mode.
+         use_contrastive, camera_name, rmsnorm_variance_mode; post-training: use_generation, gen_image, use_roi,
+         gen_pointcloud, gen_tactile (+ the heads' head counts).
     draws: noise [B_eff,T+1,A], timestep [B_eff] (and fps_starts: list of [B_eff] per stage when use_pointcloud).
     Returns losses, noise_pred and the boundary tensors the parity tests compare."""
     c = Ctx(sd, compute_dtype, flavor)
@@ -399,6 +400,34 @@ def forward(sd: Dict[str, Tensor], batch: Dict, cfg: Dict, draws: Dict, compute_
                 c, lm + "tactile_contrastive_loss_module", h8[:, 1 + 2 * n_img:2 + 2 * n_img], h8[:, 1:1 + n_img],
                 h8[:, 1 + n_img:1 + 2 * n_img], pos_pc, lin_img)
             total_extra = total_extra + out["tactile_contrastive_loss"]
+    # ---- post-training generation heads (prismatic.py:1075-1113, :771-838; model_mla.py:218-226)
+    if cfg.get("use_generation") and (cfg.get("gen_image") or cfg.get("gen_pointcloud") or cfg.get("gen_tactile")):
+        from . import generation as G
+        GM = V + "generation_manager."
+        gen_total = 0.0
+        if cfg.get("gen_image"):
+            cur_p = G.images_to_patches(images["front_image"][:, :3], 42)
+            nxt_p = G.images_to_patches(rep(batch["next_images"]), 42)
+            roi = (G.roi_mask(patch_idx, cfg.get("roi_dilation_kernel_size", 3)) if cfg.get("use_roi")
+                   else torch.ones(B, n_img, dtype=torch.bool))
+            io = G.image_head(c, GM + "image_gen_module", hs[-1], fused[:, n_img:2 * n_img], cur_p, roi,
+                              heads=cfg.get("image_decoder_heads", 8))
+            il = G.image_losses(io, nxt_p)
+            out.update(image_generation=io["image_generation"], generation_roi_mask=roi, delta_all=io["delta_all"],
+                       alpha_all=io["alpha_all"], offset_all=io["offset_all"], image_gen_loss=il["image_gen_loss"],
+                       image_loss_terms=il)
+            gen_total = gen_total + il["image_gen_loss"]
+        if cfg.get("gen_pointcloud"):
+            pc_pred = G.pointcloud_head(c, GM + "pointcloud_gen_module", hs[-1], heads=cfg.get("pointcloud_decoder_heads", 8))
+            out["pointcloud_coord_generation"] = pc_pred
+            out["point_cloud_gen_loss"] = G.chamfer_l2(pc_pred, rep(batch["next_point_cloud"]))
+            gen_total = gen_total + out["point_cloud_gen_loss"]
+        if cfg.get("gen_tactile"):
+            tp = G.tactile_head(c, GM + "tactile_gen_module", hs[-1], heads=cfg.get("tactile_decoder_heads", 4))
+            out["tactile_generation"] = tp
+            out["tactile_gen_loss"] = F.mse_loss(tp.float(), rep(batch["next_tactile"]).float())
+            gen_total = gen_total + out["tactile_gen_loss"]
+        total_extra = total_extra + gen_total
     # ---- final layer + loss (prismatic.py:1115-1126, model_mla.py:205-232)
     last = hs[-1]
     y = timm_rmsnorm(last, sd[V + "final_layer.norm_final.weight"], 1e-6, cfg.get("rmsnorm_variance_mode", False))

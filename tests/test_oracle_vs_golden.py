@@ -21,7 +21,8 @@ def load_case(name):
         if k.startswith("batch.images."):
             batch["images"][k[len("batch.images."):]] = torch.from_numpy(z[k].astype(np.float32))
         elif k.startswith("batch."):
-            batch[k[len("batch."):]] = torch.from_numpy(z[k])
+            v = torch.from_numpy(z[k])
+            batch[k[len("batch."):]] = v.float() if v.dtype == torch.float16 else v
     return z, batch
 
 
@@ -41,7 +42,9 @@ def build_state_dict(c, dtype=torch.bfloat16):
                       num_attention_heads=c["heads"], rms_norm_eps=1e-5)
     flags = dict(use_diff=True, use_pointcloud=c["use_pointcloud"], use_tactile=c["use_tactile"],
                  use_contrastive=c["use_contrastive"], use_generation=False)
-    vlm = PrismaticVLM("tiny", LLMBackbone(config=cfg), token_size=c["h"], action_dim=7, **flags)
+    flags.update(c.get("gen", {}))
+    vlm = PrismaticVLM("tiny", LLMBackbone(config=cfg), token_size=c["h"], action_dim=7, **flags,
+                       **c.get("gen_kwargs", {}))
     if c["use_pointcloud"] and c.get("n_points", 1024) != 1024:
         vlm.vision_tower_3d.patch_embed = pointcloud.Point_PN_scan(input_points=c["n_points"], k_neighbors=c["k"])
     mla = MLA(vlm, None, token_size=c["h"], action_dim=7, future_action_window_size=c["T"], **flags)
@@ -52,7 +55,7 @@ def build_state_dict(c, dtype=torch.bfloat16):
 def oracle_cfg(c):
     return dict(n_heads=c["heads"], rms_eps=1e-5, future_action_window_size=c["T"], repeated_diffusion_steps=c["R"],
                 use_pointcloud=c["use_pointcloud"], use_tactile=c["use_tactile"], use_contrastive=c["use_contrastive"],
-                camera_name="rlbench_front", k_neighbors=c.get("k", 81))
+                camera_name="rlbench_front", k_neighbors=c.get("k", 81), **c.get("gen", {}))
 
 
 def draws_of(z):
@@ -104,3 +107,30 @@ def test_oracle_fp32_is_close_to_bf16_reference():
     valid = torch.from_numpy(z["fused_attention_mask"]).bool()
     assert rel_err(out["hidden_states"][-1][valid], torch.from_numpy(z["hidden_last"])[valid]) < 2e-2
     assert abs(float(out["total_loss"]) - float(z["total_loss"])) < 2e-2 * abs(float(z["total_loss"]))
+
+
+def test_oracle_reproduces_reference_generation_heads():
+    """Post-training heads: the oracle replays the reference's CPU run of the image / point-cloud /
+    tactile generation modules and their losses (dropout off on both sides)."""
+    from golden.make_golden import GEN_PATCH_ROWS
+    from oracle import mla as O
+    z, batch = load_case("gen")
+    c = case_cfg("gen")
+    mla, sd = build_state_dict(c)
+    # key-for-key parity of the generation manager with the reference module tree (names recorded with the gradients)
+    ours = set(mla.state_dict())
+    for k in z.files:
+        if k.startswith("grad.vlm.generation_manager."):
+            assert k[len("grad."):] in ours, k
+    with torch.no_grad():
+        out = O.forward(sd, batch, oracle_cfg(c), draws_of(z), compute_dtype=torch.bfloat16, flavor="cpu")
+    assert np.array_equal(out["generation_roi_mask"].numpy(), z["generation_roi_mask"])
+    for k, tol in (("image_gen_loss", 3e-3), ("point_cloud_gen_loss", 3e-3), ("tactile_gen_loss", 5e-3), ("total_loss", 3e-3)):
+        assert abs(float(out[k]) - float(z[k])) <= tol * abs(float(z[k])), (k, float(out[k]), float(z[k]))
+    it = out["image_loss_terms"]
+    for k in ("image_roi_generation_loss", "bg_consistency_loss", "delta_magnitude_reward"):
+        assert abs(float(it[k]) - float(z[k])) <= 1e-2 * abs(float(z[k])), (k, float(it[k]), float(z[k]))
+    assert rel_err(out["image_generation"][:, GEN_PATCH_ROWS], torch.from_numpy(z["image_generation_rows"])) < 2e-2
+    assert rel_err(out["alpha_all"], torch.from_numpy(z["alpha_all"])) < 2e-2
+    assert rel_err(out["pointcloud_coord_generation"], torch.from_numpy(z["pointcloud_coord_generation"])) < 3e-2
+    assert rel_err(out["tactile_generation"], torch.from_numpy(z["tactile_generation"])) < 3e-2

@@ -20,7 +20,12 @@ dev = "cuda"
 bf = torch.bfloat16
 
 
+ONCE = os.environ.get("ONCE") == "1"      # one launch per kernel (for an ncu --set full capture)
+
+
 def timeit(fn, n=20, warm=3):
+    if ONCE:
+        n, warm = 1, 0
     for _ in range(warm):
         fn(0)
     torch.cuda.synchronize()
@@ -96,6 +101,8 @@ def main():
     print(f"attn_bwd_sm100         {ms:8.4f} ms  {2.5 * fl_f / ms / 1e9:8.1f} TFLOP/s (causal algorithmic)", flush=True)
     del qkv, ctx, dctx
     torch.cuda.empty_cache()
+    if ONCE:
+        return
     roof = bench.gemm_roofline(T, tf_sust)
     out["gemm"] = roof
     print("gemm 12 shapes:", json.dumps(roof), flush=True)
