@@ -30,7 +30,12 @@ WORKLOADS = {
     # name: (use_pointcloud, use_tactile, use_contrastive, description)
     "cfg2": (False, False, False, "MLA Llama2-7B, image-only (672x672 patchified -> 256 tokens) + 32 text toks, bs=8 x 4 repeats"),
     "cfg3": (True, True, True, "MLA Llama2-7B, image+pointcloud+tactile alignment + contrastive loss, bs=8 x 4 repeats"),
+    # BASELINE configs[4]: post-training (gen_img + gen_pc + use_roi), 14 camera views -> 3876 fused tokens per sequence
+    "cfg5": (True, True, True, "MLA post-training (gen_image+gen_pointcloud+use_roi), 14 views -> seq 3876, bs=1 x 4 repeats"),
 }
+GENERATION = {"cfg5": dict(use_generation=True, gen_image=True, gen_pointcloud=True, gen_tactile=False, use_roi=True)}
+EXTRA_VIEWS = {"cfg5": 13}
+DEFAULT_BATCH = {"cfg5": 1}
 
 
 def peaks():
@@ -92,6 +97,7 @@ def build_model(workload: str, T: int = 0):
     from mla_b200.vlm import PrismaticVLM
     use_pc, use_tac, use_con, _ = WORKLOADS[workload]
     flags = dict(use_diff=True, use_pointcloud=use_pc, use_tactile=use_tac, use_contrastive=use_con, use_generation=False)
+    flags.update(GENERATION.get(workload, {}))
     torch.manual_seed(0)
     with torch.device("cuda"):
         cfg = LlamaConfig(vocab_size=VOCAB, hidden_size=H, intermediate_size=F, num_hidden_layers=L,
@@ -101,7 +107,7 @@ def build_model(workload: str, T: int = 0):
     with torch.no_grad():   # initialize_weights zeroes the head (prismatic.py:320): give it signal so grads flow
         mla.vlm.final_layer.mlp.fc2.weight.normal_(std=0.02)
     mla.train()
-    mla.freeze_backbones("finetune")     # scripts/sft_rlbench.sh stage
+    mla.freeze_backbones("post-training" if workload in GENERATION else "finetune")     # scripts/{post,sft}_rlbench.sh
     return mla
 
 
@@ -207,15 +213,17 @@ def run_ours(args):
     _lib.check(_lib.lib().mla_device_check())
 
     use_pc, use_tac, _, desc = WORKLOADS[args.workload]
-    B, R, Lt, T = args.batch, 4, 32, 0
+    B, R, Lt, T = (args.batch or DEFAULT_BATCH.get(args.workload, 8)), 4, 32, 0
+    views = EXTRA_VIEWS.get(args.workload, 0)
     mla = build_model(args.workload, T)
     trainer = DataParallelTrainer(mla, lr=2e-5, weight_decay=0.0, max_grad_norm=1.0)
-    S = 1 + 256 + 256 + 1 + (Lt - 1) + 1 + 1 + (T + 1)
+    S = 1 + 256 + 256 * (1 + views) + 1 + (Lt - 1) + 1 + 1 + (T + 1)
     tokens = B * R * S
     levels = [args.save_level] * L if args.save_level != "auto" else plan_save_levels(mla, tokens)
     mla.vlm.llm_backbone.llm.model.set_save_levels(levels)
 
-    host = make_batch(B, Lt, T, 672, 1024, seed=1234 + rank, use_pointcloud=use_pc, use_tactile=use_tac, pin=True)
+    host = make_batch(B, Lt, T, 672, 1024, seed=1234 + rank, use_pointcloud=use_pc, use_tactile=use_tac, pin=True,
+                      extra_views=views, generation=args.workload in GENERATION)
     devb = map_tensors(host, lambda t: t.cuda(non_blocking=True))
     kw = dict(camera_name="rlbench_front", repeated_diffusion_steps=R, use_diff=True)
 
@@ -223,7 +231,8 @@ def run_ours(args):
         loss_dict, _ = mla(input_ids=b["input_ids"], attention_mask=b["attention_mask"], labels=b["labels"],
                            actions=b["actions"], images=b["images"], point_cloud=b.get("point_cloud"),
                            tactile=b.get("tactile"), proprio=b["proprio"], gripper_xyz=b.get("gripper_xyz"),
-                           action_masks=b["action_masks"], **kw)
+                           action_masks=b["action_masks"], next_images=b.get("next_images"),
+                           next_point_cloud=b.get("next_point_cloud"), next_tactile=b.get("next_tactile"), **kw)
         loss = loss_dict["total_loss"]
         loss.backward()
         trainer.step()
@@ -295,7 +304,8 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "per_gpu_batch": B, "repeated_diffusion_steps": R,
                    "seq_len": S, "tokens_per_gpu_step": tokens, "global_batch": B * world, "parallelism": f"dp{world}",
-                   "stage": "finetune (vision tokenizers frozen)", "optimizer": "AdamW fp32 master + fp32 grads",
+                   "stage": ("post-training (generation heads on)" if args.workload in GENERATION
+                             else "finetune (vision tokenizers frozen)"), "optimizer": "AdamW fp32 master + fp32 grads",
                    "activation_save_levels": {lv: levels.count(lv) for lv in sorted(set(levels))},
                    "l2": "step streams >100 GB of weights/activations (>> 126 MB L2); no explicit flush needed",
                    "peak_mem_gb": round(mem_gb, 1)},
@@ -343,7 +353,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 8; 1 for cfg5)")
     ap.add_argument("--save-level", default="auto", choices=["auto", "layer", "mlp", "none"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

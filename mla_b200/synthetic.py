@@ -8,7 +8,8 @@ import torch
 
 
 def make_batch(B: int, Lt: int = 32, T: int = 0, image_hw: int = 672, n_points: int = 1024, seed: int = 1234,
-               use_pointcloud: bool = False, use_tactile: bool = False, extra_views: int = 0, pin: bool = False) -> Dict:
+               use_pointcloud: bool = False, use_tactile: bool = False, extra_views: int = 0, pin: bool = False,
+               generation: bool = False) -> Dict:
     g = torch.Generator().manual_seed(seed)
     ids = torch.randint(3, 31000, (B, Lt), generator=g)
     ids[:, 0] = 1
@@ -30,6 +31,11 @@ def make_batch(B: int, Lt: int = 32, T: int = 0, image_hw: int = 672, n_points: 
     if use_tactile:
         batch["tactile"] = torch.rand(B, 12, generator=g)
         batch["gripper_xyz"] = torch.rand(B, 3, generator=g) * torch.tensor([0.8, 1.0, 0.8]) + torch.tensor([-0.1, -0.5, 0.75])
+    if generation:      # post-training targets (next frame / point cloud / tactile reading)
+        batch["next_images"] = torch.randn(B, 3, image_hw, image_hw, generator=g)
+        batch["next_point_cloud"] = (torch.rand(B, n_points, 3, generator=g) * torch.tensor([0.8, 1.0, 0.8]) +
+                                     torch.tensor([-0.1, -0.5, 0.75]))
+        batch["next_tactile"] = torch.rand(B, 12, generator=g)
     if pin and torch.cuda.is_available():
         batch = map_tensors(batch, lambda t: t.pin_memory())
     return batch
