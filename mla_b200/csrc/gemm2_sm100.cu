@@ -1,0 +1,293 @@
+// bf16 GEMM on CTA PAIRS (tcgen05.mma.cta_group::2): two SMs of one TPC cooperate on a 256x256 output tile.
+//
+// Same contract, operand layouts and epilogue as gemm_sm100.cu (C = epilogue(alpha * A_op . B_op)), different machine
+// mapping: a cluster of 2 CTAs owns a 256(M) x 256(N) tile; CTA r holds rows [128r, 128r+128) of A and HALF of B
+// (columns [128r, 128r+128) of the tile) in its shared memory, the leader CTA's single MMA thread issues
+// tcgen05.mma.cta_group::2 (M=256, N=256, K=16) which reads A from both CTAs and the two B halves from both CTAs, and
+// each CTA's TMEM receives its own 128 rows x 256 columns of the accumulator.  Per CTA and k-block this stages
+// 16 KB (A) + 16 KB (half B) instead of 16 + 32 KB, so the L2->smem traffic and the smem operand reads of the tensor
+// core drop by a third — on a power-capped part that is clock headroom for the MMAs — and the 32 KB stage allows a
+// 6-deep ring instead of 4.
+//
+//   warp 0    TMA producer   both CTAs: own A tile + own half of B, completion signalled on the LEADER's full barrier
+//   warp 1    MMA issuer     leader only; tcgen05.commit multicasts "slot free" / "accumulator ready" to both CTAs
+//   warps 2-5 epilogue       both CTAs: own TMEM -> registers -> global; "accumulator drained" arrives at the leader
+#include <cstdlib>
+
+#include "gemm_epilogue.cuh"
+#include "mla_internal.cuh"
+#include "ptx.cuh"
+
+namespace mla {
+
+constexpr int G2_BM = 128;            // rows per CTA (256 per cluster)
+constexpr int G2_BN = 256;            // columns per cluster tile
+constexpr int G2_BNH = 128;           // B rows staged per CTA
+constexpr int G2_BK = 64;
+constexpr int G2_STAGES = 6;
+constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;     // 16 KB
+constexpr int G2_B_BYTES = G2_BNH * G2_BK * 2;    // 16 KB
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_THREADS = 192;
+constexpr int G2_ACC = 2;
+constexpr int G2_TMEM_COLS = 512;
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load whose completion bytes are counted on an mbarrier that may live in the peer CTA of the pair.
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                 int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the issued MMAs retired) on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(uint16_t(3))
+      : "memory");
+}
+
+__device__ __forceinline__ void tile_coords2(int tile, int tiles_m, int tiles_n, int group_m, int& tm, int& tn) {
+  int group_size = group_m * tiles_n;
+  int g = tile / group_size;
+  int first_m = g * group_m;
+  int gm = min(group_m, tiles_m - first_m);
+  int r = tile - g * group_size;
+  tm = first_m + r % gm;
+  tn = r / gm;
+}
+
+template <int A_MN, int B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
+                  int K, int group_m, GemmEpilogue ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + G2_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + G2_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + G2_ACC;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + G2_ACC);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int tiles_m = (M + 2 * G2_BM - 1) / (2 * G2_BM);
+  const int tiles_n = (N + G2_BN - 1) / G2_BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + G2_BK - 1) / G2_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < G2_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);    // leader's producer arrives (+ the bytes of both CTAs' loads)
+      mbar_init(&empty_bar[s], 1);   // one multicast commit
+    }
+    for (int s = 0; s < G2_ACC; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 8);   // 4 epilogue warps of each CTA arrive at the leader
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_base_slot, G2_TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();        // barriers of both CTAs are initialised before any remote arrive / TMA completion
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int tm, tn;
+        tile_coords2(tile, tiles_m, tiles_n, group_m, tm, tn);
+        const int m0 = tm * 2 * G2_BM + int(rank) * G2_BM;
+        const int n0 = tn * G2_BN + int(rank) * G2_BNH;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * G2_STAGE_BYTES;
+          uint8_t* sb = sa + G2_A_BYTES;
+          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+          const int k0 = kb * G2_BK;
+          if (A_MN == 0) {
+            tma_load_2d_pair(sa, &map_a, full_leader, k0, m0);              // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < G2_BM / 64; ++j)
+              tma_load_2d_pair(sa + j * (G2_BK * 128), &map_a, full_leader, m0 + j * 64, k0);
+          }
+          if (B_MN == 0) {
+            tma_load_2d_pair(sb, &map_b, full_leader, k0, n0);              // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < G2_BNH / 64; ++j)
+              tma_load_2d_pair(sb + j * (G2_BK * 128), &map_b, full_leader, n0 + j * 64, k0);
+          }
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * G2_BM, G2_BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * G2_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * G2_STAGE_BYTES);
+          const uint32_t sb = sa + G2_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < G2_BK / 16; ++k) {
+            uint64_t da = A_MN == 0 ? umma_smem_desc_sw128(sa + k * 32, 16, 1024)
+                                    : umma_smem_desc_sw128(sa + k * 2048, G2_BK * 128, 1024);
+            uint64_t db = B_MN == 0 ? umma_smem_desc_sw128(sb + k * 32, 16, 1024)
+                                    : umma_smem_desc_sw128(sb + k * 2048, G2_BK * 128, 1024);
+            umma_f16_ss_pair(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage]);      // frees this slot in both CTAs
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tmem_full_bar[acc]);      // accumulator complete -> both epilogues
+        if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps, both CTAs) =====================
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int tm, tn;
+      tile_coords2(tile, tiles_m, tiles_n, group_m, tm, tn);
+      const int64_t row = int64_t(tm) * 2 * G2_BM + int64_t(rank) * G2_BM + quarter * 32 + lane;
+      const int n0 = tn * G2_BN;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * G2_BN;
+      gemm_store_tile(ep, taddr, row, n0, M, N);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
+      if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();        // the peer may still be reading this CTA's smem / signalling its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, G2_TMEM_COLS);
+  }
+}
+
+static int encode_operand_map2(CUtensorMap* map, const void* ptr, int mn_major, int64_t rows_mn, int64_t k, int64_t ld) {
+  uint64_t dims[2];
+  uint64_t strides[1] = {uint64_t(ld) * 2};
+  uint32_t box[2];
+  if (!mn_major) {
+    dims[0] = uint64_t(k); dims[1] = uint64_t(rows_mn);
+    box[0] = G2_BK; box[1] = 128;
+  } else {
+    dims[0] = uint64_t(rows_mn); dims[1] = uint64_t(k);
+    box[0] = 64; box[1] = G2_BK;
+  }
+  return encode_tmap_2d_bf16(map, ptr, dims, strides, box);
+}
+
+template <int A_MN, int B_MN>
+static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const GemmEpilogue& ep,
+                        cudaStream_t stream) {
+  static bool attr_set = false;
+  auto kern = gemm2_bf16_kernel<A_MN, B_MN>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "cudaFuncSetAttribute(gemm2 smem): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = ((M + 2 * G2_BM - 1) / (2 * G2_BM)) * ((N + G2_BN - 1) / G2_BN);
+  const int max_clusters = num_sms() / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  int group_m = int((48ll << 20) / (int64_t(2 * G2_BM) * K * 2));
+  group_m = group_m < 2 ? 2 : (group_m > 32 ? 32 : group_m);
+  kern<<<2 * clusters, G2_THREADS, G2_SMEM_BYTES, stream>>>(ma, mb, M, N, K, group_m, ep);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "gemm2 launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return MLA_OK;
+}
+
+// Called by mla_gemm_bf16 (gemm_sm100.cu) when the pair kernel is selected; arguments are already validated.
+int gemm2_dispatch(const mla_gemm_args* g, const GemmEpilogue& ep, cudaStream_t stream) {
+  CUtensorMap ma, mb;
+  if (int rc = encode_operand_map2(&ma, g->a, g->a_mn_major, g->m, g->k, g->lda)) return rc;
+  if (int rc = encode_operand_map2(&mb, g->b, g->b_mn_major, g->n, g->k, g->ldb)) return rc;
+  const int M = int(g->m), N = int(g->n), K = int(g->k);
+  if (!g->a_mn_major && !g->b_mn_major) return launch_gemm2<0, 0>(ma, mb, M, N, K, ep, stream);
+  if (!g->a_mn_major && g->b_mn_major) return launch_gemm2<0, 1>(ma, mb, M, N, K, ep, stream);
+  if (g->a_mn_major && !g->b_mn_major) return launch_gemm2<1, 0>(ma, mb, M, N, K, ep, stream);
+  return launch_gemm2<1, 1>(ma, mb, M, N, K, ep, stream);
+}
+
+}  // namespace mla

@@ -1,0 +1,135 @@
+// Epilogue shared by the 1-CTA and the 2-CTA (cta_group::2) GEMM kernels: one thread owns one accumulator row (TMEM
+// lane) and walks the tile's 256 columns in 32-column chunks (tcgen05.ld 32x32b.x32), applying the fused
+// bias / activation / residual / rounding or the fp32 (+=) store.
+#pragma once
+#include "mla_internal.cuh"
+#include "ptx.cuh"
+
+namespace mla {
+
+constexpr int GEMM_BN = 256;
+
+struct GemmEpilogue {
+  void* c;
+  int64_t ldc;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* residual;
+  int64_t ldr;
+  __nv_bfloat16* pre_act;
+  int64_t ldp;
+  float alpha;
+  int c_dtype;      // 0 bf16, 1 fp32
+  int accumulate;   // fp32 only: C += value
+  int activation;   // MLA_ACT_*
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case MLA_ACT_RELU: return v > 0.f ? v : 0.f;
+    case MLA_ACT_GELU_ERF: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    case MLA_ACT_GELU_TANH: {
+      const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+      float u = k0 * (v + k1 * v * v * v);
+      return 0.5f * v * (1.f + tanhf(u));
+    }
+    case MLA_ACT_SILU: return v / (1.f + __expf(-v));
+    default: return v;
+  }
+}
+
+// taddr: TMEM address of this thread's warp-quarter and accumulator buffer; row: global output row of this thread.
+__device__ __forceinline__ void gemm_store_tile(const GemmEpilogue& ep, uint32_t taddr, int64_t row, int n0, int M, int N) {
+  constexpr int BN = GEMM_BN;
+  const bool row_ok = row < M;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    const int col0 = n0 + c * 32;
+    if (col0 >= N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr + c * 32, r);
+    tmem_ld_wait();
+    if (!row_ok) continue;
+    const bool full = (col0 + 32 <= N);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
+    if (ep.c_dtype == 1) {
+      // fp32 output (weight gradients): optional accumulate, no activation path.
+      float* crow = reinterpret_cast<float*>(ep.c) + row * ep.ldc + col0;
+      if (full && (ep.ldc & 3) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (ep.accumulate) {
+            float4 p = *reinterpret_cast<const float4*>(crow + j);
+            o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+          }
+          *reinterpret_cast<float4*>(crow + j) = o;
+        }
+      } else {
+        #pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) crow[j] = ep.accumulate ? crow[j] + v[j] : v[j];
+      }
+      continue;
+    }
+    // bf16 output: replicate the reference's rounding points (linear -> bf16, act -> bf16, +residual -> bf16).
+    if (ep.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (full || col0 + j < N) v[j] += __bfloat162float(ep.bias[col0 + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
+    if (ep.pre_act != nullptr) {
+      __nv_bfloat16* prow = ep.pre_act + row * ep.ldp + col0;
+      if (full && (ep.ldp & 7) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8)
+          *reinterpret_cast<uint4*>(prow + j) = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+                                                          pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+      } else {
+        #pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) prow[j] = __float2bfloat16_rn(v[j]);
+      }
+    }
+    if (ep.activation != MLA_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = bf16_round(apply_act(v[j], ep.activation));
+    }
+    if (ep.residual != nullptr) {
+      const __nv_bfloat16* rrow = ep.residual + row * ep.ldr + col0;
+      if (full && (ep.ldr & 7) == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 q = *reinterpret_cast<const uint4*>(rrow + j);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            float2 f = __bfloat1622float2(h[t]);
+            v[j + 2 * t] += f.x;
+            v[j + 2 * t + 1] += f.y;
+          }
+        }
+      } else {
+        #pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) v[j] += __bfloat162float(rrow[j]);
+      }
+    }
+    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(ep.c) + row * ep.ldc + col0;
+    if (full && (ep.ldc & 7) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8)
+        *reinterpret_cast<uint4*>(crow + j) = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+                                                        pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+    } else {
+      #pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < N) crow[j] = __float2bfloat16_rn(v[j]);
+    }
+  }
+}
+
+}  // namespace mla

@@ -14,6 +14,7 @@
 // Two 128x256 fp32 accumulators (2 x 256 TMEM columns) are double-buffered so the epilogue of tile i overlaps
 // the main loop of tile i+1.
 #include <cstdlib>
+#include "gemm_epilogue.cuh"
 #include "mla_internal.cuh"
 #include "ptx.cuh"
 
@@ -32,34 +33,6 @@ constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = 512;
 constexpr int SCHED_STAGES = 4;
 constexpr int GEMM_SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-
-struct GemmEpilogue {
-  void* c;
-  int64_t ldc;
-  const __nv_bfloat16* bias;
-  const __nv_bfloat16* residual;
-  int64_t ldr;
-  __nv_bfloat16* pre_act;
-  int64_t ldp;
-  float alpha;
-  int c_dtype;      // 0 bf16, 1 fp32
-  int accumulate;   // fp32 only: C += value
-  int activation;   // MLA_ACT_*
-};
-
-__device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case MLA_ACT_RELU: return v > 0.f ? v : 0.f;
-    case MLA_ACT_GELU_ERF: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-    case MLA_ACT_GELU_TANH: {
-      const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-      float u = k0 * (v + k1 * v * v * v);
-      return 0.5f * v * (1.f + tanhf(u));
-    }
-    case MLA_ACT_SILU: return v / (1.f + __expf(-v));
-    default: return v;
-  }
-}
 
 // Tile rasterisation: groups of GROUP_M row-tiles sweep all column-tiles, so the CTAs that run concurrently share
 // a small set of A row-panels while B streams through L2.
@@ -241,96 +214,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
-      const bool row_ok = row < M;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c * 32, r);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        const bool full = (col0 + 32 <= N);
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
-        if (ep.c_dtype == 1) {
-          // fp32 output (weight gradients): optional accumulate, no activation path.
-          float* crow = reinterpret_cast<float*>(ep.c) + row * ep.ldc + col0;
-          if (full && (ep.ldc & 3) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              if (ep.accumulate) {
-                float4 p = *reinterpret_cast<const float4*>(crow + j);
-                o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
-              }
-              *reinterpret_cast<float4*>(crow + j) = o;
-            }
-          } else {
-            #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) crow[j] = ep.accumulate ? crow[j] + v[j] : v[j];
-          }
-          continue;
-        }
-        // bf16 output: replicate the reference's rounding points (linear -> bf16, act -> bf16, +residual -> bf16).
-        if (ep.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || col0 + j < N) v[j] += __bfloat162float(ep.bias[col0 + j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
-        if (ep.pre_act != nullptr) {
-          __nv_bfloat16* prow = ep.pre_act + row * ep.ldp + col0;
-          if (full && (ep.ldp & 7) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              *reinterpret_cast<uint4*>(prow + j) = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                                                              pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
-          } else {
-            #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) prow[j] = __float2bfloat16_rn(v[j]);
-          }
-        }
-        if (ep.activation != MLA_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = bf16_round(apply_act(v[j], ep.activation));
-        }
-        if (ep.residual != nullptr) {
-          const __nv_bfloat16* rrow = ep.residual + row * ep.ldr + col0;
-          if (full && (ep.ldr & 7) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q = *reinterpret_cast<const uint4*>(rrow + j);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                float2 f = __bfloat1622float2(h[t]);
-                v[j + 2 * t] += f.x;
-                v[j + 2 * t + 1] += f.y;
-              }
-            }
-          } else {
-            #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < N) v[j] += __bfloat162float(rrow[j]);
-          }
-        }
-        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(ep.c) + row * ep.ldc + col0;
-        if (full && (ep.ldc & 7) == 0) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8)
-            *reinterpret_cast<uint4*>(crow + j) = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                                                            pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
-        } else {
-          #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < N) crow[j] = __float2bfloat16_rn(v[j]);
-        }
-      }
+      gemm_store_tile(ep, taddr, row, n0, M, N);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -388,7 +272,7 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, int M, int 
   static const int group_override = [] { const char* e = getenv("MLA_GEMM_GROUP_M"); return e ? atoi(e) : 0; }();
   int group_m = int((48ll << 20) / (int64_t(BM) * K * 2));
   group_m = group_m < 4 ? 4 : (group_m > 64 ? 64 : group_m);
-  if (group_override > 0) group_m = group_override;   // tuning switch (tools/ab_overlap.sh)
+  if (group_override > 0) group_m = group_override;   // tuning switch (tools/ab_bench.sh)
   kern<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ma, mb, M, N, K, group_m, tiles > grid ? sched : nullptr, ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
@@ -396,9 +280,21 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, int M, int 
   return MLA_OK;
 }
 
+int gemm2_dispatch(const mla_gemm_args* g, const GemmEpilogue& ep, cudaStream_t stream);   // gemm2_sm100.cu
+
+// 0 = one CTA per tile (gemm_bf16_kernel), 1 = CTA pairs (gemm2_bf16_kernel) for problems of at least 1024 rows,
+// 2 = CTA pairs always (tests).  Default from MLA_GEMM_2CTA, overridable with mla_gemm_set_mode().
+static int g_gemm_mode = [] { const char* e = getenv("MLA_GEMM_2CTA"); return e ? atoi(e) : 1; }();
+
 }  // namespace mla
 
 using namespace mla;
+
+extern "C" int mla_gemm_set_mode(int32_t mode) {
+  if (mode < 0 || mode > 2) return set_error(MLA_ERR_ARG, "gemm_set_mode: mode must be 0, 1 or 2");
+  g_gemm_mode = mode;
+  return MLA_OK;
+}
 
 extern "C" int mla_gemm_bf16(const mla_gemm_args* g, void* stream_) {
   if (g == nullptr) return set_error(MLA_ERR_ARG, "gemm: null args");
@@ -426,6 +322,7 @@ extern "C" int mla_gemm_bf16(const mla_gemm_args* g, void* stream_) {
   ep.alpha = g->alpha; ep.c_dtype = g->c_dtype; ep.accumulate = g->accumulate; ep.activation = g->activation;
   const int M = int(g->m), N = int(g->n), K = int(g->k);
   int* sched = static_cast<int*>(g->sched_ws);
+  if (sched == nullptr && (g_gemm_mode == 2 || (g_gemm_mode == 1 && M >= 1024))) return gemm2_dispatch(g, ep, stream);
   if (!g->a_mn_major && !g->b_mn_major) return launch_gemm<0, 0>(ma, mb, M, N, K, ep, sched, stream);
   if (!g->a_mn_major && g->b_mn_major) return launch_gemm<0, 1>(ma, mb, M, N, K, ep, sched, stream);
   if (g->a_mn_major && !g->b_mn_major) return launch_gemm<1, 0>(ma, mb, M, N, K, ep, sched, stream);

@@ -1,0 +1,62 @@
+"""The CTA-pair GEMM (tcgen05.mma.cta_group::2, gemm2_sm100.cu) against fp32 matmul: all four operand layouts, ragged
+M / N / K tails (a half-empty 256-row pair tile, partial column tile, K not a multiple of 64), fused epilogues, fp32
+accumulation — and bit-identical results to the one-CTA kernel (same MMA shape per row, same K order)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def pair_mode(cuda_lib):
+    assert cuda_lib.mla_gemm_set_mode(C.c_int32(2)) == 0
+    yield
+    cuda_lib.mla_gemm_set_mode(C.c_int32(1))
+
+
+def _mk(M, N, K, a_mn, b_mn):
+    a = (torch.randn((K, M) if a_mn else (M, K), device="cuda") * 0.5).bfloat16()
+    b = (torch.randn((K, N) if b_mn else (N, K), device="cuda") * 0.5).bfloat16()
+    ref = (a.float().t() if a_mn else a.float()) @ (b.float() if b_mn else b.float().t())
+    return a, b, ref
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (128, 256, 128), (384, 512, 192), (1000, 264, 520), (2048, 1024, 4096),
+                                   (552, 4096, 352), (17536, 512, 256)])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+def test_pair_gemm_layouts(pair_mode, cuda_lib, M, N, K, a_mn, b_mn):
+    from mla_b200 import ops
+    torch.manual_seed(M + N + K)
+    a, b, ref = _mk(M, N, K, a_mn, b_mn)
+    got = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn)
+    assert rel_err(got, ref) < 4e-3
+    cuda_lib.mla_gemm_set_mode(C.c_int32(0))
+    one = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn)
+    cuda_lib.mla_gemm_set_mode(C.c_int32(2))
+    assert torch.equal(got, one)
+
+
+def test_pair_gemm_epilogues(pair_mode, cuda_lib):
+    from mla_b200 import ops
+    torch.manual_seed(5)
+    M, N, K = 700, 520, 256
+    a, b, ref = _mk(M, N, K, False, False)
+    bias = torch.randn(N, device="cuda").bfloat16()
+    res = torch.randn(M, N, device="cuda").bfloat16()
+    pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    got = ops.gemm(a, b, bias=bias, act=ops.ACT_GELU_TANH, residual=res, pre_act=pre)
+    lin = (ref + bias.float()).bfloat16()
+    want = (torch.nn.functional.gelu(lin.float(), approximate="tanh").bfloat16().float() + res.float()).bfloat16()
+    assert rel_err(pre, lin) < 4e-3 and rel_err(got, want) < 6e-3
+    # fp32 output with accumulation (weight gradients)
+    a, b, ref = _mk(512, 384, 1096, True, True)
+    out = torch.randn(512, 384, device="cuda")
+    base = out.clone()
+    ops.gemm(a, b, a_mn=True, b_mn=True, out=out, accumulate=True)
+    assert rel_err(out - base, ref) < 1e-3
+    ops.gemm(a, b, a_mn=True, b_mn=True, out=out, alpha=0.5)
+    assert rel_err(out, 0.5 * ref) < 1e-3
