@@ -73,7 +73,7 @@ typedef struct mla_gemm_args {
 int mla_gemm_bf16(const mla_gemm_args* args, void* stream);
 /* Kernel selection for mla_gemm_bf16: 0 = one CTA per 128x256 tile, 1 = CTA pairs (tcgen05.mma.cta_group::2, 256x256
  * tile per 2-CTA cluster) for problems of at least 1024 rows (default), 2 = CTA pairs always.  Env MLA_GEMM_2CTA sets
- * the initial mode.  Calls that pass sched_ws (dynamic tile claiming) always use the one-CTA kernel. */
+ * the initial mode.  Both kernels honour sched_ws (dynamic tile claiming). */
 int mla_gemm_set_mode(int32_t mode);
 
 /* ---- RMSNorm ----------------------------------------------------------------------------------------------

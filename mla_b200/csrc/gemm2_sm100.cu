@@ -31,6 +31,7 @@ constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_THREADS = 192;
 constexpr int G2_ACC = 2;
 constexpr int G2_TMEM_COLS = 512;
+constexpr int G2_SCHED = 4;            // depth of the tile-id ring (dynamic scheduling)
 constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 1024 + 256;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -46,6 +47,24 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
+}
+__device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+// wait on a LOCAL barrier whose arrivals (and the data they publish) come from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
@@ -102,14 +121,18 @@ __device__ __forceinline__ void tile_coords2(int tile, int tiles_m, int tiles_n,
 template <int A_MN, int B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
-                  int K, int group_m, GemmEpilogue ep) {
+                  int K, int group_m, int* sched, GemmEpilogue ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * G2_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + G2_STAGES;
   uint64_t* tmem_full_bar = empty_bar + G2_STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + G2_ACC;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + G2_ACC);
+  uint64_t* sched_full = tmem_empty_bar + G2_ACC;       // tile-id ring (dynamic scheduling): filled by the leader's
+  uint64_t* sched_empty = sched_full + G2_SCHED;        // producer in BOTH CTAs, drained at the leader
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(sched_empty + G2_SCHED);
+  int* sched_ids = reinterpret_cast<int*>(tmem_base_slot + 1);
+  const bool dynamic = sched != nullptr;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -133,6 +156,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 8);   // 4 epilogue warps of each CTA arrive at the leader
     }
+    for (int s = 0; s < G2_SCHED; ++s) {
+      mbar_init(&sched_full[s], 1);
+      mbar_init(&sched_empty[s], 10);     // leader: MMA thread + 4 epilogue warps; peer: producer + 4 epilogue warps
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -150,7 +177,29 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      // Tile sequence: static (cluster_id, +num_clusters, ...) or claimed dynamically by the leader's producer from a
+      // global counter (a pair that starts late because an NCCL kernel holds one of its SMs then simply takes fewer
+      // tiles) and published to every other role of both CTAs through a small ring of tile ids.
+      int tile = cluster_id;
+      for (int seq = 0;; ++seq) {
+        if (dynamic) {
+          const int sl = seq & (G2_SCHED - 1);
+          const uint32_t par = (seq / G2_SCHED) & 1;
+          if (leader) {
+            mbar_wait_cluster(&sched_empty[sl], par ^ 1);
+            const int v = tile < num_tiles ? tile : -1;
+            sched_ids[sl] = v;
+            st_cluster_u32(mapa_u32(smem_u32(&sched_ids[sl]), 1), uint32_t(v));
+            mbar_arrive(&sched_full[sl]);
+            mbar_arrive_cluster(mapa_u32(smem_u32(&sched_full[sl]), 1));
+          } else {
+            mbar_wait_cluster(&sched_full[sl], par);
+            tile = sched_ids[sl];
+            mbar_arrive_cluster(mapa_u32(smem_u32(&sched_empty[sl]), 0));
+            if (tile < 0) break;
+          }
+        }
+        if (tile >= num_tiles) break;
         int tm, tn;
         tile_coords2(tile, tiles_m, tiles_n, group_m, tm, tn);
         const int m0 = tm * 2 * G2_BM + int(rank) * G2_BM;
@@ -178,6 +227,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           }
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
+        if (!dynamic) tile += num_clusters;
+        else if (leader) tile = num_clusters + atomicAdd(sched, 1);
       }
     }
   } else if (warp == 1) {
@@ -188,8 +239,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      int tile = cluster_id;
+      for (int seq = 0;; ++seq) {
+        if (dynamic) {
+          const int sl = seq & (G2_SCHED - 1);
+          mbar_wait(&sched_full[sl], (seq / G2_SCHED) & 1);
+          tile = sched_ids[sl];
+          mbar_arrive(&sched_empty[sl]);
+          if (tile < 0) break;
+        } else {
+          if (seq > 0) tile += num_clusters;
+          if (tile >= num_tiles) break;
+        }
+        mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * G2_BN;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -217,7 +279,19 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    int tile = cluster_id;
+    for (int seq = 0;; ++seq) {
+      if (dynamic) {
+        const int sl = seq & (G2_SCHED - 1);
+        mbar_wait_cluster(&sched_full[sl], (seq / G2_SCHED) & 1);
+        tile = sched_ids[sl];
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&sched_empty[sl]), 0));
+        if (tile < 0) break;
+      } else {
+        if (seq > 0) tile += num_clusters;
+        if (tile >= num_tiles) break;
+      }
       int tm, tn;
       tile_coords2(tile, tiles_m, tiles_n, group_m, tm, tn);
       const int64_t row = int64_t(tm) * 2 * G2_BM + int64_t(rank) * G2_BM + quarter * 32 + lane;
@@ -240,6 +314,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, G2_TMEM_COLS);
   }
+  if (dynamic && leader && threadIdx.x == 0) {
+    // the last cluster to finish re-arms the counters for the next launch on this stream
+    __threadfence();
+    if (atomicAdd(sched + 1, 1) == num_clusters - 1) {
+      sched[0] = 0;
+      sched[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 static int encode_operand_map2(CUtensorMap* map, const void* ptr, int mn_major, int64_t rows_mn, int64_t k, int64_t ld) {
@@ -258,7 +341,7 @@ static int encode_operand_map2(CUtensorMap* map, const void* ptr, int mn_major, 
 
 template <int A_MN, int B_MN>
 static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const GemmEpilogue& ep,
-                        cudaStream_t stream) {
+                        int* sched, cudaStream_t stream) {
   static bool attr_set = false;
   auto kern = gemm2_bf16_kernel<A_MN, B_MN>;
   if (!attr_set) {
@@ -271,7 +354,8 @@ static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, int M, int
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   int group_m = int((48ll << 20) / (int64_t(2 * G2_BM) * K * 2));
   group_m = group_m < 2 ? 2 : (group_m > 32 ? 32 : group_m);
-  kern<<<2 * clusters, G2_THREADS, G2_SMEM_BYTES, stream>>>(ma, mb, M, N, K, group_m, ep);
+  kern<<<2 * clusters, G2_THREADS, G2_SMEM_BYTES, stream>>>(ma, mb, M, N, K, group_m, tiles > clusters ? sched : nullptr,
+                                                            ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "gemm2 launch: %s", cudaGetErrorString(e));
   count_launch();
@@ -284,10 +368,11 @@ int gemm2_dispatch(const mla_gemm_args* g, const GemmEpilogue& ep, cudaStream_t 
   if (int rc = encode_operand_map2(&ma, g->a, g->a_mn_major, g->m, g->k, g->lda)) return rc;
   if (int rc = encode_operand_map2(&mb, g->b, g->b_mn_major, g->n, g->k, g->ldb)) return rc;
   const int M = int(g->m), N = int(g->n), K = int(g->k);
-  if (!g->a_mn_major && !g->b_mn_major) return launch_gemm2<0, 0>(ma, mb, M, N, K, ep, stream);
-  if (!g->a_mn_major && g->b_mn_major) return launch_gemm2<0, 1>(ma, mb, M, N, K, ep, stream);
-  if (g->a_mn_major && !g->b_mn_major) return launch_gemm2<1, 0>(ma, mb, M, N, K, ep, stream);
-  return launch_gemm2<1, 1>(ma, mb, M, N, K, ep, stream);
+  int* sched = static_cast<int*>(g->sched_ws);
+  if (!g->a_mn_major && !g->b_mn_major) return launch_gemm2<0, 0>(ma, mb, M, N, K, ep, sched, stream);
+  if (!g->a_mn_major && g->b_mn_major) return launch_gemm2<0, 1>(ma, mb, M, N, K, ep, sched, stream);
+  if (g->a_mn_major && !g->b_mn_major) return launch_gemm2<1, 0>(ma, mb, M, N, K, ep, sched, stream);
+  return launch_gemm2<1, 1>(ma, mb, M, N, K, ep, sched, stream);
 }
 
 }  // namespace mla

@@ -322,7 +322,7 @@ extern "C" int mla_gemm_bf16(const mla_gemm_args* g, void* stream_) {
   ep.alpha = g->alpha; ep.c_dtype = g->c_dtype; ep.accumulate = g->accumulate; ep.activation = g->activation;
   const int M = int(g->m), N = int(g->n), K = int(g->k);
   int* sched = static_cast<int*>(g->sched_ws);
-  if (sched == nullptr && (g_gemm_mode == 2 || (g_gemm_mode == 1 && M >= 1024))) return gemm2_dispatch(g, ep, stream);
+  if (g_gemm_mode == 2 || (g_gemm_mode == 1 && M >= 1024)) return gemm2_dispatch(g, ep, stream);
   if (!g->a_mn_major && !g->b_mn_major) return launch_gemm<0, 0>(ma, mb, M, N, K, ep, sched, stream);
   if (!g->a_mn_major && g->b_mn_major) return launch_gemm<0, 1>(ma, mb, M, N, K, ep, sched, stream);
   if (g->a_mn_major && !g->b_mn_major) return launch_gemm<1, 0>(ma, mb, M, N, K, ep, sched, stream);

@@ -60,3 +60,26 @@ def test_pair_gemm_epilogues(pair_mode, cuda_lib):
     assert rel_err(out - base, ref) < 1e-3
     ops.gemm(a, b, a_mn=True, b_mn=True, out=out, alpha=0.5)
     assert rel_err(out, 0.5 * ref) < 1e-3
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_dynamic_tile_claiming(cuda_lib, mode):
+    """sched_ws: tiles claimed from a global counter (used under DDP, where NCCL kernels hold SMs) — same bits as the
+    static order, and the counters re-arm themselves between launches (several launches back to back)."""
+    from mla_b200 import ops
+    torch.manual_seed(11)
+    cuda_lib.mla_gemm_set_mode(C.c_int32(mode))
+    try:
+        for (M, N, K, a_mn, b_mn) in [(17536, 1024, 512, False, False), (4096, 2048, 17536, True, True),
+                                      (5000, 3072, 1024, False, True)]:
+            a, b, ref = _mk(M, N, K, a_mn, b_mn)
+            ops.DYNAMIC_TILES["on"] = False
+            want = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn)
+            ops.DYNAMIC_TILES["on"] = True
+            for _ in range(4):
+                got = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn)
+                assert torch.equal(got, want)
+            assert rel_err(got, ref) < 4e-3
+    finally:
+        ops.DYNAMIC_TILES["on"] = False
+        cuda_lib.mla_gemm_set_mode(C.c_int32(1))
