@@ -69,6 +69,13 @@ typedef struct mla_gemm_args {
                                   private to one stream: tiles are then claimed dynamically (CTAs that start late because a
                                   concurrent kernel, e.g. an NCCL all-reduce, holds their SM take fewer tiles); the kernel
                                   leaves it zeroed again. */
+  /* Fused RoPE for the q|k|v projection (head_dim 128; modeling_llama.py:184-208 folded into the epilogue of :435-437):
+   * the leading rope_cols output columns (a multiple of 256 = whole q and k heads) are rotated with position =
+   * row % rope_seq; rope_cos / rope_sin: bf16 [rope_seq, 64].  rope_cols = 0 switches it off.  Plain bf16 outputs only. */
+  const void* rope_cos;
+  const void* rope_sin;
+  int32_t rope_seq;
+  int32_t rope_cols;
 } mla_gemm_args;
 int mla_gemm_bf16(const mla_gemm_args* args, void* stream);
 /* Kernel selection for mla_gemm_bf16: 0 = one CTA per 128x256 tile, 1 = CTA pairs (tcgen05.mma.cta_group::2, 256x256
@@ -99,6 +106,9 @@ int mla_rope_inplace(void* base, const void* cos_t, const void* sin_t, int64_t t
  * bwd: dgu[rows,2f] from dact[rows,f] and gu. */
 int mla_swiglu_fwd(const void* gu, void* out, int64_t rows, int32_t f, void* stream);
 int mla_swiglu_bwd(const void* dact, const void* gu, void* dgu, int64_t rows, int32_t f, void* stream);
+/* swiglu_bwd that also re-materialises act = bf16(silu(gate)) * up into act_out [rows, f] (the operand of the
+ * down-projection weight gradient), saving the separate swiglu_fwd recompute pass of backward. */
+int mla_swiglu_bwd_act(const void* dact, const void* gu, void* dgu, void* act_out, int64_t rows, int32_t f, void* stream);
 
 /* ---- causal attention ------------------------------------------------------------------------------------
  * Replaces flash_attn_func / flash_attn_varlen_func + unpad/pad_input (modeling_llama.py:540-557).

@@ -21,6 +21,11 @@ struct GemmEpilogue {
   int c_dtype;      // 0 bf16, 1 fp32
   int accumulate;   // fp32 only: C += value
   int activation;   // MLA_ACT_*
+  // fused RoPE (head_dim 128) on the leading rope_cols columns of a bf16 output: position = row % rope_seq
+  const __nv_bfloat16* rope_cos;   // bf16 [rope_seq, 64]
+  const __nv_bfloat16* rope_sin;
+  int rope_seq;
+  int rope_cols;                   // multiple of 256; 0 = off
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -37,9 +42,58 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
+// RoPE epilogue (modeling_llama.py:184-208 fused into the q|k|v projection): the 256-column tile holds two heads of
+// 128; column j < 64 of a head pairs with column j + 64, so the chunks are walked in pairs (c, c + 2).  Rounding points
+// of the bf16 path: linear -> bf16, x*cos -> bf16, rotate_half(x)*sin -> bf16, sum -> bf16.
+__device__ __forceinline__ void gemm_store_tile_rope(const GemmEpilogue& ep, uint32_t taddr, int64_t row, int n0, int M) {
+  const bool row_ok = row < M;
+  const int pos = int(row % ep.rope_seq);
+#pragma unroll 1
+  for (int pair = 0; pair < 4; ++pair) {
+    const int c1 = (pair >> 1) * 4 + (pair & 1);     // chunks 0,1 (head 0) and 4,5 (head 1): first halves
+    const int c2 = c1 + 2;                           // matching second halves
+    uint32_t r1[32], r2[32];
+    tmem_ld_32x32b_x32(taddr + c1 * 32, r1);
+    tmem_ld_32x32b_x32(taddr + c2 * 32, r2);
+    tmem_ld_wait();
+    if (!row_ok) continue;
+    const __nv_bfloat16* cs = ep.rope_cos + int64_t(pos) * 64 + (pair & 1) * 32;
+    const __nv_bfloat16* sn = ep.rope_sin + int64_t(pos) * 64 + (pair & 1) * 32;
+    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(ep.c) + row * ep.ldc + n0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const uint4 cq = *reinterpret_cast<const uint4*>(cs + j);
+      const uint4 sq = *reinterpret_cast<const uint4*>(sn + j);
+      const __nv_bfloat162* ch = reinterpret_cast<const __nv_bfloat162*>(&cq);
+      const __nv_bfloat162* sh = reinterpret_cast<const __nv_bfloat162*>(&sq);
+      float o1[8], o2[8];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 cf = __bfloat1622float2(ch[t]), sf = __bfloat1622float2(sh[t]);
+        const float cc[2] = {cf.x, cf.y}, ss[2] = {sf.x, sf.y};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const float x1 = bf16_round(__uint_as_float(r1[j + 2 * t + u]) * ep.alpha);
+          const float x2 = bf16_round(__uint_as_float(r2[j + 2 * t + u]) * ep.alpha);
+          o1[2 * t + u] = bf16_round(x1 * cc[u]) + bf16_round(-x2 * ss[u]);
+          o2[2 * t + u] = bf16_round(x2 * cc[u]) + bf16_round(x1 * ss[u]);
+        }
+      }
+      *reinterpret_cast<uint4*>(crow + c1 * 32 + j) = make_uint4(pack_bf16x2(o1[0], o1[1]), pack_bf16x2(o1[2], o1[3]),
+                                                                 pack_bf16x2(o1[4], o1[5]), pack_bf16x2(o1[6], o1[7]));
+      *reinterpret_cast<uint4*>(crow + c2 * 32 + j) = make_uint4(pack_bf16x2(o2[0], o2[1]), pack_bf16x2(o2[2], o2[3]),
+                                                                 pack_bf16x2(o2[4], o2[5]), pack_bf16x2(o2[6], o2[7]));
+    }
+  }
+}
+
 // taddr: TMEM address of this thread's warp-quarter and accumulator buffer; row: global output row of this thread.
 __device__ __forceinline__ void gemm_store_tile(const GemmEpilogue& ep, uint32_t taddr, int64_t row, int n0, int M, int N) {
   constexpr int BN = GEMM_BN;
+  if (n0 < ep.rope_cols) {      // warp-uniform (whole tile inside the rotated q|k column block)
+    gemm_store_tile_rope(ep, taddr, row, n0, M);
+    return;
+  }
   const bool row_ok = row < M;
 #pragma unroll 1
   for (int c = 0; c < BN / 32; ++c) {

@@ -320,6 +320,15 @@ extern "C" int mla_gemm_bf16(const mla_gemm_args* g, void* stream_) {
   ep.residual = static_cast<const __nv_bfloat16*>(g->residual); ep.ldr = g->ldr;
   ep.pre_act = static_cast<__nv_bfloat16*>(g->pre_act); ep.ldp = g->ldp;
   ep.alpha = g->alpha; ep.c_dtype = g->c_dtype; ep.accumulate = g->accumulate; ep.activation = g->activation;
+  ep.rope_cos = static_cast<const __nv_bfloat16*>(g->rope_cos);
+  ep.rope_sin = static_cast<const __nv_bfloat16*>(g->rope_sin);
+  ep.rope_seq = g->rope_seq; ep.rope_cols = g->rope_cols;
+  if (g->rope_cols != 0) {
+    if (g->rope_cols < 0 || (g->rope_cols & 255) || g->rope_cols > g->n || g->rope_seq <= 0 || !g->rope_cos || !g->rope_sin)
+      return set_error(MLA_ERR_ARG, "gemm: fused RoPE needs rope_cols a multiple of 256 within N, rope_seq > 0 and both tables");
+    if (g->c_dtype != 0 || g->bias || g->residual || g->pre_act || g->activation != MLA_ACT_NONE || (g->ldc & 7))
+      return set_error(MLA_ERR_ARG, "gemm: fused RoPE applies to a plain bf16 projection (no bias/activation/residual), ldc % 8 == 0");
+  }
   const int M = int(g->m), N = int(g->n), K = int(g->k);
   int* sched = static_cast<int*>(g->sched_ws);
   if (g_gemm_mode == 2 || (g_gemm_mode == 1 && M >= 1024)) return gemm2_dispatch(g, ep, stream);

@@ -75,6 +75,58 @@ __global__ void rmsnorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __
   }
 }
 
+// Register-resident variant for h <= 256*8*VPT: every element is read from HBM exactly once (the generic kernel above
+// re-reads the row for the scaling pass) and one CTA walks rows blockIdx.x, +gridDim.x, ... with the next row's loads in
+// flight across the reduction.
+template <int VPT>
+__global__ void __launch_bounds__(256) rmsnorm_fwd_reg_kernel(const __nv_bfloat16* __restrict__ x,
+                                                              const __nv_bfloat16* __restrict__ w,
+                                                              __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out,
+                                                              int64_t rows, int h, int64_t ldx, int64_t ldy, float eps) {
+  __shared__ float red[32];
+  const int nvec = h >> 3;
+  uint4 wp[VPT], nx[VPT];
+#pragma unroll
+  for (int v = 0; v < VPT; ++v) {
+    const int i = threadIdx.x + v * blockDim.x;
+    wp[v] = i < nvec ? *reinterpret_cast<const uint4*>(w + i * 8) : make_uint4(0, 0, 0, 0);
+  }
+  auto prefetch = [&](int64_t r) {
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int i = threadIdx.x + v * blockDim.x;
+      nx[v] = (r < rows && i < nvec) ? *reinterpret_cast<const uint4*>(x + r * ldx + i * 8) : make_uint4(0, 0, 0, 0);
+    }
+  };
+  int64_t row = blockIdx.x;
+  prefetch(row);
+  for (; row < rows; row += gridDim.x) {
+    float xf[VPT][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      unpack8(nx[v], xf[v]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += xf[v][j] * xf[v][j];
+    }
+    prefetch(row + gridDim.x);
+    ss = block_sum(ss, red);
+    const float rstd = rsqrtf(ss / float(h) + eps);
+    if (threadIdx.x == 0 && rstd_out) rstd_out[row] = rstd;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int i = threadIdx.x + v * blockDim.x;
+      if (i < nvec) {
+        float g[8], o[8];
+        unpack8(wp[v], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = g[j] * bf16_round(xf[v][j] * rstd);
+        *reinterpret_cast<uint4*>(y + row * ldy + i * 8) = pack8(o);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ RMSNorm bwd
 // dn = dy*w ; dx = rstd*(dn - n*mean(dn*n)) (+ dres) ; dw += sum_rows dy*n.   Each CTA walks rows blockIdx.x,
 // +gridDim.x, ... keeping its dw partial in registers, then does one fp32 atomicAdd per column.
@@ -235,15 +287,18 @@ __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfl
 }
 
 // d_gu[:, :f] = d_act*u*silu'(g) ; d_gu[:, f:] = d_act*silu(g)
+// With act_out the kernel also re-materialises act = bf16(silu(g)) * u (what swiglu_fwd produced), which backward needs
+// as the operand of the down-projection weight gradient: one pass over gate|up instead of two.
 __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dact, const __nv_bfloat16* __restrict__ gu,
-                                  __nv_bfloat16* __restrict__ dgu, int64_t rows, int f) {
+                                  __nv_bfloat16* __restrict__ dgu, __nv_bfloat16* __restrict__ act_out, int64_t rows,
+                                  int f) {
   const int cpr = f >> 3;
   const int64_t total = rows * cpr;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
     const int64_t r = idx / cpr;
     const int c = int(idx % cpr);
-    float g[8], u[8], d[8], dg[8], du[8];
+    float g[8], u[8], d[8], dg[8], du[8], ac[8];
     unpack8(*reinterpret_cast<const uint4*>(gu + r * 2 * f + c * 8), g);
     unpack8(*reinterpret_cast<const uint4*>(gu + r * 2 * f + f + c * 8), u);
     unpack8(*reinterpret_cast<const uint4*>(dact + r * f + c * 8), d);
@@ -251,12 +306,14 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dact, const 
     for (int j = 0; j < 8; ++j) {
       const float s = sigmoidf_(g[j]);
       const float a = bf16_round(g[j] * s);
+      ac[j] = a * u[j];
       du[j] = d[j] * a;
       const float da = bf16_round(d[j] * u[j]);
       dg[j] = da * (s * (1.f + g[j] * (1.f - s)));
     }
     *reinterpret_cast<uint4*>(dgu + r * 2 * f + c * 8) = pack8(dg);
     *reinterpret_cast<uint4*>(dgu + r * 2 * f + f + c * 8) = pack8(du);
+    if (act_out) *reinterpret_cast<uint4*>(act_out + r * f + c * 8) = pack8(ac);
   }
 }
 
@@ -278,6 +335,21 @@ extern "C" int mla_rmsnorm_fwd(const void* x, const void* w, void* y, void* rstd
   if (mode != 0 && mode != 1) return set_error(MLA_ERR_ARG, "rmsnorm_fwd: mode must be 0 (mean-square) or 1 (variance)");
   int block = (h / 8 + 31) / 32 * 32;
   block = block > 256 ? 256 : block;
+  const int vpt = (h / 8 + block - 1) / block;
+  if (mode == 0 && vpt <= 4) {
+    const int grid = int(rows < int64_t(num_sms()) * 6 ? rows : int64_t(num_sms()) * 6);
+    auto s_ = (cudaStream_t)stream;
+#define LAUNCH_RF(V)                                                                                             \
+  rmsnorm_fwd_reg_kernel<V><<<grid, block, 0, s_>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,            \
+                                                    (__nv_bfloat16*)y, (float*)rstd, rows, h, ldx, ldy, eps)
+    if (vpt == 1) LAUNCH_RF(1);
+    else if (vpt == 2) LAUNCH_RF(2);
+    else if (vpt == 3) LAUNCH_RF(3);
+    else LAUNCH_RF(4);
+#undef LAUNCH_RF
+    MLA_CHECK_LAUNCH("rmsnorm_fwd");
+    return MLA_OK;
+  }
   rmsnorm_fwd_kernel<<<(unsigned)rows, block, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (__nv_bfloat16*)y, (float*)rstd, rows, h, ldx, ldy, eps, mode);
   MLA_CHECK_LAUNCH("rmsnorm_fwd");
@@ -338,7 +410,19 @@ extern "C" int mla_swiglu_bwd(const void* dact, const void* gu, void* dgu, int64
   if (rows <= 0) return MLA_OK;
   if (f <= 0 || (f & 7)) return set_error(MLA_ERR_ARG, "swiglu_bwd: f must be a multiple of 8");
   swiglu_bwd_kernel<<<ew_grid(rows * (f / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dact, (const __nv_bfloat16*)gu, (__nv_bfloat16*)dgu, rows, f);
+      (const __nv_bfloat16*)dact, (const __nv_bfloat16*)gu, (__nv_bfloat16*)dgu, nullptr, rows, f);
   MLA_CHECK_LAUNCH("swiglu_bwd");
+  return MLA_OK;
+}
+
+extern "C" int mla_swiglu_bwd_act(const void* dact, const void* gu, void* dgu, void* act_out, int64_t rows, int32_t f,
+                                  void* stream) {
+  if (int rc = device_check()) return rc;
+  if (rows <= 0) return MLA_OK;
+  if (f <= 0 || (f & 7)) return set_error(MLA_ERR_ARG, "swiglu_bwd_act: f must be a multiple of 8");
+  if (act_out == nullptr) return set_error(MLA_ERR_ARG, "swiglu_bwd_act: null act_out");
+  swiglu_bwd_kernel<<<ew_grid(rows * (f / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)dact, (const __nv_bfloat16*)gu, (__nv_bfloat16*)dgu, (__nv_bfloat16*)act_out, rows, f);
+  MLA_CHECK_LAUNCH("swiglu_bwd_act");
   return MLA_OK;
 }

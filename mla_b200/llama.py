@@ -32,6 +32,7 @@ from . import ops
 # as a tested switch (tests/test_trainer_gpu.py proves the two orders are bit-identical), not as the default.
 OVERLAP = {"wgrad": os.environ.get("MLA_WGRAD_STREAM", "0") == "1"}
 _SIDE_STREAMS: dict = {}
+FUSE_ROPE = {"on": os.environ.get("MLA_FUSE_ROPE", "1") == "1"}     # RoPE inside the q|k|v GEMM epilogue (head_dim 128)
 
 
 def side_stream(device) -> "torch.cuda.Stream":
@@ -183,8 +184,12 @@ class LlamaDecoderLayer(nn.Module):
     def _attn_half(self, x: torch.Tensor, sh: LayerShape, keep: bool):
         wqkv, wo, _, _, l1, _ = self.compute_weights()
         n1 = ops.rmsnorm_fwd(x, l1, self.eps)
-        qkv = ops.gemm(n1, wqkv)
-        ops.rope_(qkv, 0, 2 * sh.H, sh.D, sh.S, sh.cos, sh.sin)          # q and k heads are contiguous
+        if sh.D == 128 and FUSE_ROPE["on"]:
+            # RoPE in the projection's epilogue (q and k heads = the leading 2*H*D columns), no extra HBM pass
+            qkv = ops.gemm(n1, wqkv, rope=(sh.cos, sh.sin, sh.S, 2 * sh.H * sh.D))
+        else:
+            qkv = ops.gemm(n1, wqkv)
+            ops.rope_(qkv, 0, 2 * sh.H, sh.D, sh.S, sh.cos, sh.sin)      # q and k heads are contiguous
         ctx, lse = ops.attn_fwd(qkv, sh.B, sh.S, sh.H, sh.D, sh.mask)
         x_mid = ops.gemm(ctx, wo, residual=x)
         return n1, qkv, ctx, lse, x_mid
@@ -219,7 +224,7 @@ class LlamaDecoderLayer(nn.Module):
             n1 = ops.rmsnorm_fwd(x, l1, self.eps)
             n2 = ops.rmsnorm_fwd(x_mid, l2, self.eps)
             gu = saved[5] if save_level == "none" else ops.gemm(n2, wgu)
-            act = ops.swiglu_fwd(gu)
+            act = None          # re-materialised by the fused SwiGLU backward below
         acc = self._attach_grads()
         gqkv, go, ggu, gd, g1, g2 = self._g
         if not acc:
@@ -240,11 +245,11 @@ class LlamaDecoderLayer(nn.Module):
             a.record_stream(side)
 
         # ---- MLP half
-        wgrad(dy, act, gd)                                                           # dWd  = dy^T act
         dact = ops.gemm(dy, wd, b_mn=True)                                           # dact = dy Wd
-        del act
-        dgu = ops.swiglu_bwd(dact, gu)
+        dgu, act = ops.swiglu_bwd_act(dact, gu)                                      # + act = swiglu(gu), one pass
         del dact, gu
+        wgrad(dy, act, gd)                                                           # dWd  = dy^T act
+        del act
         wgrad(dgu, n2, ggu)                                                          # dWgu = dgu^T n2
         dn2 = ops.gemm(dgu, wgu, b_mn=True)                                          # dn2  = dgu Wgu
         del dgu, n2
@@ -275,8 +280,7 @@ class LlamaDecoderLayer(nn.Module):
         _, _, wgu, _, _, l2 = self.compute_weights()
         n2 = ops.rmsnorm_fwd(x_mid, l2, self.eps)
         gu = ops.gemm(n2, wgu)
-        act = ops.swiglu_fwd(gu)
-        return n2, gu, act, None
+        return n2, gu, None, None
 
 
 class _LayerFn(torch.autograd.Function):

@@ -39,10 +39,12 @@ def _rowmajor_2d(t: torch.Tensor, name: str) -> int:
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False,
          out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
          bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, residual: Optional[torch.Tensor] = None,
-         pre_act: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = False) -> torch.Tensor:
+         pre_act: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = False,
+         rope: Optional[tuple] = None) -> torch.Tensor:
     """C = epilogue(alpha * A_op @ B_op).
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True);  b: [N,K] (b_mn=False, nn.Linear weight) or [K,N] (b_mn=True).
+    rope = (cos [S,64] bf16, sin [S,64] bf16, S, n_cols): rotate the leading n_cols columns (head_dim 128) in the epilogue.
     """
     _req(a, torch.bfloat16, "a")
     _req(b, torch.bfloat16, "b")
@@ -79,6 +81,13 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         _req(pre_act, torch.bfloat16, "pre_act")
         g.ldp = _rowmajor_2d(pre_act, "pre_act")
     g.pre_act = _ptr(pre_act)
+    if rope is not None:
+        cos_t, sin_t, seq, ncols = rope
+        _req(cos_t, torch.bfloat16, "rope cos")
+        _req(sin_t, torch.bfloat16, "rope sin")
+        if tuple(cos_t.shape) != (seq, 64) or tuple(sin_t.shape) != (seq, 64) or not (cos_t.is_contiguous() and sin_t.is_contiguous()):
+            raise _lib.MlaError("gemm: fused RoPE needs contiguous [seq, 64] tables (head_dim 128)")
+        g.rope_cos, g.rope_sin, g.rope_seq, g.rope_cols = cos_t.data_ptr(), sin_t.data_ptr(), seq, ncols
     if DYNAMIC_TILES["on"]:
         g.sched_ws = _sched_ws(a.device).data_ptr()
     check(_lib.lib().mla_gemm_bf16(C.byref(g), _stream()))
@@ -86,8 +95,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
 
 
 # Dynamic tile scheduling of the persistent GEMM (see include/mla_b200.h: sched_ws).  One 8-byte counter per
-# (device, stream); switched on by the data-parallel trainer, whose NCCL all-reduces share the SMs with the GEMMs.
-DYNAMIC_TILES = {"on": __import__("os").environ.get("MLA_DYNAMIC_TILES", "0") == "1"}
+# (device, stream).  On by default: measured on one B200 (tools/ab_inproc.py, interleaved) 678.9 -> 660.1 ms per step,
+# and under DDP the NCCL all-reduces share the SMs with the GEMMs, where a static order stalls whole waves.
+DYNAMIC_TILES = {"on": __import__("os").environ.get("MLA_DYNAMIC_TILES", "1") == "1"}
 _SCHED_WS: dict = {}
 
 
@@ -172,6 +182,20 @@ def swiglu_bwd(dact: torch.Tensor, gu: torch.Tensor) -> torch.Tensor:
     dgu = torch.empty_like(gu)
     check(_lib.lib().mla_swiglu_bwd(_p(dact), _p(gu), _p(dgu), C.c_int64(rows), C.c_int32(f2 // 2), _stream()))
     return dgu
+
+
+def swiglu_bwd_act(dact: torch.Tensor, gu: torch.Tensor):
+    """(d_gu, act): swiglu_bwd fused with the recompute of act = swiglu_fwd(gu)."""
+    _req(dact, torch.bfloat16, "dact")
+    _req(gu, torch.bfloat16, "gu")
+    rows, f2 = gu.shape
+    if not (gu.is_contiguous() and dact.is_contiguous()):
+        raise _lib.MlaError("swiglu_bwd_act: inputs must be contiguous")
+    dgu = torch.empty_like(gu)
+    act = torch.empty((rows, f2 // 2), dtype=torch.bfloat16, device=gu.device)
+    check(_lib.lib().mla_swiglu_bwd_act(_p(dact), _p(gu), _p(dgu), _p(act), C.c_int64(rows), C.c_int32(f2 // 2),
+                                        _stream()))
+    return dgu, act
 
 
 # ---------------------------------------------------------------------------------------------- attention

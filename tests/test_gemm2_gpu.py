@@ -83,3 +83,24 @@ def test_dynamic_tile_claiming(cuda_lib, mode):
     finally:
         ops.DYNAMIC_TILES["on"] = False
         cuda_lib.mla_gemm_set_mode(C.c_int32(1))
+
+
+@pytest.mark.parametrize("mode", [0, 2])
+def test_fused_rope_epilogue(cuda_lib, mode):
+    """RoPE folded into the q|k|v projection's epilogue == projection followed by the in-place RoPE kernel, bit for bit
+    (q and k heads rotated, v columns untouched; rows beyond one sequence wrap their position)."""
+    from mla_b200 import ops
+    torch.manual_seed(21)
+    cuda_lib.mla_gemm_set_mode(C.c_int32(mode))
+    try:
+        B, S, H, D, h = 3, 150, 4, 128, 512
+        x = (torch.randn(B * S, h, device="cuda") * 0.5).bfloat16()
+        w = (torch.randn(3 * h, h, device="cuda") * 0.05).bfloat16()
+        ang = torch.rand(S, D // 2, device="cuda") * 6.28
+        cos, sin = ang.cos().bfloat16().contiguous(), ang.sin().bfloat16().contiguous()
+        want = ops.gemm(x, w)
+        ops.rope_(want, 0, 2 * H, D, S, cos, sin)
+        got = ops.gemm(x, w, rope=(cos, sin, S, 2 * H * D))
+        assert torch.equal(got, want)
+    finally:
+        cuda_lib.mla_gemm_set_mode(C.c_int32(1))

@@ -72,6 +72,9 @@ def test_swiglu_fwd_bwd(cuda_lib):
     (torch.nn.functional.silu(gf[:, :f]) * gf[:, f:]).backward(torch.ones(rows, f, device="cuda"))
     d = ops.swiglu_bwd(_bf(torch.ones(rows, f, device="cuda")), gu)
     assert rel_err(d, gf.grad) < 8e-3
+    # fused backward + re-materialisation of act: same bits as the two separate kernels
+    d2, act2 = ops.swiglu_bwd_act(_bf(torch.ones(rows, f, device="cuda")), gu)
+    assert torch.equal(d2, d) and torch.equal(act2, out)
 
 
 @pytest.mark.parametrize("B,S,H,D,masked", [(2, 44, 4, 32, False), (2, 150, 2, 128, False), (3, 131, 2, 64, True),
