@@ -91,7 +91,7 @@ def step_flops(tokens: int, S: int) -> float:
 
 
 # ----------------------------------------------------------------------------------------------------------- ours
-def build_model(workload: str, T: int = 0):
+def build_model(workload: str, T: int = 0, stage: str = ""):
     from mla_b200.backbone import LLMBackbone, LlamaConfig
     from mla_b200.mla import MLA
     from mla_b200.vlm import PrismaticVLM
@@ -107,7 +107,8 @@ def build_model(workload: str, T: int = 0):
     with torch.no_grad():   # initialize_weights zeroes the head (prismatic.py:320): give it signal so grads flow
         mla.vlm.final_layer.mlp.fc2.weight.normal_(std=0.02)
     mla.train()
-    mla.freeze_backbones("post-training" if workload in GENERATION else "finetune")     # scripts/{post,sft}_rlbench.sh
+    # scripts/{post,sft}_rlbench.sh; --stage pretrain (scripts/pretrain_*.sh) also trains the two tokenizers
+    mla.freeze_backbones(stage or ("post-training" if workload in GENERATION else "finetune"))
     return mla
 
 
@@ -215,11 +216,13 @@ def run_ours(args):
     use_pc, use_tac, _, desc = WORKLOADS[args.workload]
     B, R, Lt, T = (args.batch or DEFAULT_BATCH.get(args.workload, 8)), 4, 32, 0
     views = EXTRA_VIEWS.get(args.workload, 0)
-    mla = build_model(args.workload, T)
+    mla = build_model(args.workload, T, args.stage)
     trainer = DataParallelTrainer(mla, lr=2e-5, weight_decay=0.0, max_grad_norm=1.0)
     S = 1 + 256 + 256 * (1 + views) + 1 + (Lt - 1) + 1 + 1 + (T + 1)
     tokens = B * R * S
-    levels = [args.save_level] * L if args.save_level != "auto" else plan_save_levels(mla, tokens)
+    # stage pretrain keeps the tokenizers' pre-BatchNorm activations (~8 GB for 32 clouds) + their backward transients
+    reserve = 10.0 + (14.0 if args.stage == "pretrain" else 0.0)
+    levels = [args.save_level] * L if args.save_level != "auto" else plan_save_levels(mla, tokens, reserve_gb=reserve)
     mla.vlm.llm_backbone.llm.model.set_save_levels(levels)
 
     host = make_batch(B, Lt, T, 672, 1024, seed=1234 + rank, use_pointcloud=use_pc, use_tactile=use_tac, pin=True,
@@ -304,7 +307,8 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "per_gpu_batch": B, "repeated_diffusion_steps": R,
                    "seq_len": S, "tokens_per_gpu_step": tokens, "global_batch": B * world, "parallelism": f"dp{world}",
-                   "stage": ("post-training (generation heads on)" if args.workload in GENERATION
+                   "stage": ("pretrain (vision tokenizers trained)" if args.stage == "pretrain" else
+                             "post-training (generation heads on)" if args.workload in GENERATION
                              else "finetune (vision tokenizers frozen)"), "optimizer": "AdamW fp32 master + fp32 grads",
                    "activation_save_levels": {lv: levels.count(lv) for lv in sorted(set(levels))},
                    "l2": "step streams >100 GB of weights/activations (>> 126 MB L2); no explicit flush needed",
@@ -356,6 +360,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 8; 1 for cfg5)")
     ap.add_argument("--save-level", default="auto", choices=["auto", "layer", "mlp", "none"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage", default="", choices=["", "pretrain", "finetune", "post-training"],
+                    help="freeze_backbones stage (default: finetune; post-training for cfg5)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

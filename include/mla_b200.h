@@ -219,6 +219,11 @@ int mla_tac_nce_bwd(const void* q, const void* keys, const void* pos, const void
 int mla_project_points(const void* xyz, const void* cam, int64_t n, float sx, float sy, float total_stride,
                        int32_t patch_h, int32_t patch_w, float img_w, float img_h, void* patch_idx, void* valid,
                        void* stream);
+/* Tactile positives (models/vlm/prismatic.py:742-749, torch.cdist + topk(1)): gripper_xyz f32 [batch,arms,3], centers f32
+ * [batch,groups,3], patch_idx int64 [batch,groups,2] (from mla_project_points) -> pos_pc int64 [batch,arms] = nearest
+ * centre (lowest index on ties), lin_img int64 [batch,arms] = row*patch_w + col of that centre's image patch. */
+int mla_nearest_center(const void* gripper_xyz, const void* centers, const void* patch_idx, int32_t batch, int32_t arms,
+                       int32_t groups, int32_t patch_w, void* pos_pc, void* lin_img, void* stream);
 
 /* ---- point-cloud tokenizer (models/mla/pointcloud/backbone/Point_PN.py) -----------------------------------------
  * fps: furthest_point_sample (:6-21): xyz f32 [B,n,3], start int64 [B] (the reference's torch.randint draw) ->
@@ -229,8 +234,8 @@ int mla_project_points(const void* xyz, const void* cam, int64_t n, float sx, fl
  *   feat [B,n,c] (bf16 or f32) -> rows (b,g,k) x 2c channels, written as f32 and as a bf16 copy.
  * bn_*: train-mode BatchNorm over rows of a bf16 [rows,c] matrix: sums f32 [2c] (zero it first), coef f32 [2c] =
  *   mean | invstd, running stats updated with `momentum`; bn_relu: out = bf16(relu(bn(y)));
- *   bn_res_relu: v = relu(bf16(bn(y)) + x) (Linear2Layer :219) written as f32 + bf16, or max-pooled over the k rows
- *   of each group when `pooled` is non-NULL (Pooling :161-170). */
+ *   bn_res_relu: v = relu(bf16(bn(y)) + x) (Linear2Layer :219); whichever of x_f32_out, x_bf16_out and pooled
+ *   (max over the k rows of each group, Pooling :161-170) is non-NULL is written. */
 int mla_fps(const void* xyz, const void* start, void* idx_out, void* centers, int32_t batch, int32_t n,
             int32_t npoint, void* stream);
 int mla_knn(const void* xyz, const void* query, void* knn_idx, int32_t batch, int32_t n, int32_t groups, int32_t k,
@@ -245,6 +250,35 @@ int mla_bn_relu(const void* y, const void* coef, const void* w, const void* bias
                 void* stream);
 int mla_bn_res_relu(const void* y, const void* coef, const void* w, const void* bias, const void* x, void* x_f32_out,
                     void* x_bf16_out, void* pooled, int64_t groups, int32_t k, int32_t c, void* stream);
+
+/* ---- tokenizer backward: stage "pretrain" trains vision_tower_2d / vision_tower_3d (models/vlm/prismatic.py:427-434)
+ * The GEMM gradients run on mla_gemm_bf16; these are the autograd formulas of the ops between them.
+ * local_attn_bwd: backward of mla_local_attn (vision_tokenizer.py:40-45): dout [groups,c] -> dq [groups,c],
+ *   dkv [groups*win, 2c] (bf16); the 9-way softmax is recomputed from q, kv.
+ * layernorm_bwd: backward of mla_layernorm_fwd (nn.LayerNorm of LocalAttention.q[0] / kv[0], :19-24) on bf16 rows;
+ *   statistics recomputed; dx = LN-backward (+ dres[row]) (+ dgrp[row / win] / win): the optional addends are the
+ *   `reduced_features +` residual (:46) and F.avg_pool2d's broadcast (:28) into the same tensor.  dw, db f32 [h] +=.
+ * bn_bwd: backward of the train-mode BatchNorm of mla_bn_stats/finalize (Point_PN.py:173-219) over bf16 rows y
+ *   [rows,c] with coef = mean | invstd.  Upstream `up` (f32 if up_is_f32 else bf16) is masked first: mode 0 none;
+ *   mode 1 by relu(bn(y)) > 0 (conv-BN-ReLU, :176-181,:192-196); mode 2 by xnew > 0, xnew f32 = relu(bn(y) + x) the
+ *   Linear2Layer output (:219) — then the masked f32 gradient is also the residual input's and is written to dres.
+ *   sums f32 [2c]: on return db = sums[0..c), dw = sums[c..2c).  dy bf16 [rows,c] = gradient of the conv output.
+ * maxpool_bwd: backward of x.max(-1) over the k neighbours (:157): d_xnew f32 [groups,k,c] from d_pooled [groups,c].
+ * group_pose_bwd: backward of mla_group_pose's two gathers (index_points, :41-58,:116-122): dx f32 [B*groups*k, 2c]
+ *   -> dfeat f32 [B*n, c] += (zero it first).
+ * diag_block_sum: out f32 [m,n] = sum_s x[s*m+i, s*n+j], x f32 [parts*m, parts*n]: folds a weight-gradient GEMM
+ *   whose very long reduction (rows of neighbours) was spread over `parts` row-interleaved tiles. */
+int mla_local_attn_bwd(const void* q, const void* kv, const void* dout, void* dq, void* dkv, int64_t groups, int32_t c,
+                       int32_t heads, int32_t win, float scale, void* stream);
+int mla_layernorm_bwd(const void* dy, const void* x, const void* w, const void* dres, const void* dgrp, int32_t win,
+                      void* dx, void* dw, void* db, int64_t rows, int32_t h, float eps, void* stream);
+int mla_bn_bwd(const void* up, int32_t up_is_f32, const void* y, const void* coef, const void* w, const void* bias,
+               const void* xnew, int32_t mode, void* sums, void* dy, void* dres, int64_t rows, int32_t c, void* stream);
+int mla_maxpool_bwd(const void* xnew, const void* dpooled, void* dxnew, int64_t groups, int32_t k, int32_t c,
+                    void* stream);
+int mla_group_pose_bwd(const void* dx, const void* fps_idx, const void* knn_idx, void* dfeat, int32_t batch, int32_t n,
+                       int32_t groups, int32_t k, int32_t c, void* stream);
+int mla_diag_block_sum(const void* x, void* out, int32_t m, int32_t n, int32_t parts, void* stream);
 
 /* ---- optimizer step of the data-parallel trainer (training/strategies/fsdp.py:242-257,:310) ------------------
  * sumsq: out[0] += sum(x^2) (f32).  clip_coef: scale[0] = min(1, max_norm/(||g||*inv_world + 1e-6)) * inv_world,

@@ -258,6 +258,39 @@ __global__ void project_kernel(const float* __restrict__ xyz, const float* __res
   valid[i] = ok ? 1 : 0;
 }
 
+
+// Tactile positives (models/vlm/prismatic.py:742-749): for every gripper position the nearest point-cloud centre
+// (torch.cdist + topk(k=1, largest=False)) and the linear index row*patch_w + col of the image patch that centre
+// projects to.  One warp per (sample, arm); fp32 squared distances, lowest index wins ties.
+__global__ void nearest_center_kernel(const float* __restrict__ grip, const float* __restrict__ centers,
+                                      const int64_t* __restrict__ patch_idx, int n_query, int arms, int G, int patch_w,
+                                      int64_t* __restrict__ pos_pc, int64_t* __restrict__ lin_img) {
+  const int wq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wq >= n_query) return;
+  const int b = wq / arms;
+  const float gx = grip[wq * 3], gy = grip[wq * 3 + 1], gz = grip[wq * 3 + 2];
+  float best = INFINITY;
+  int bi = 0x7fffffff;
+  for (int g = lane; g < G; g += 32) {
+    const float* c = centers + (int64_t(b) * G + g) * 3;
+    const float dx = gx - c[0], dy = gy - c[1], dz = gz - c[2];
+    const float d = dx * dx + dy * dy + dz * dz;
+    if (d < best) { best = d; bi = g; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) {
+    if (bi >= G) bi = 0;   // all distances NaN/inf: torch.topk would still return an index
+    pos_pc[wq] = bi;
+    const int64_t* pi = patch_idx + (int64_t(b) * G + bi) * 2;
+    lin_img[wq] = pi[0] * patch_w + pi[1];
+  }
+}
+
 }  // namespace mla
 
 using namespace mla;
@@ -350,5 +383,19 @@ extern "C" int mla_project_points(const void* xyz, const void* cam, int64_t n, f
                                                                     total_stride, patch_h, patch_w, img_w, img_h,
                                                                     (int64_t*)patch_idx, (uint8_t*)valid);
   MLA_CHECK_LAUNCH("project_points");
+  return MLA_OK;
+}
+
+extern "C" int mla_nearest_center(const void* gripper_xyz, const void* centers, const void* patch_idx, int32_t batch,
+                                  int32_t arms, int32_t groups, int32_t patch_w, void* pos_pc, void* lin_img,
+                                  void* stream) {
+  if (int rc = device_check()) return rc;
+  if (batch <= 0 || arms <= 0) return MLA_OK;
+  if (groups <= 0) return set_error(MLA_ERR_ARG, "nearest_center: no centres");
+  const int nq = batch * arms;
+  nearest_center_kernel<<<(nq * 32 + 127) / 128, 128, 0, S_(stream)>>>(
+      (const float*)gripper_xyz, (const float*)centers, (const int64_t*)patch_idx, nq, arms, groups, patch_w,
+      (int64_t*)pos_pc, (int64_t*)lin_img);
+  MLA_CHECK_LAUNCH("nearest_center");
   return MLA_OK;
 }

@@ -250,8 +250,8 @@ __global__ void bn_relu_kernel(const __nv_bfloat16* __restrict__ y, const float*
     out[i] = __float2bfloat16_rn(fmaxf(v, 0.f));
   }
 }
-// v = relu(bf16(bn(y)) + x);  writes xf/xb (f32 + bf16 copy) unless pooled != null, in which case only
-// pooled[g, c] = max_k v is written (fused max-pool over the K rows of each group).  One CTA per group.
+// v = relu(bf16(bn(y)) + x);  writes whichever of xf (f32), xb (bf16 copy for the next GEMM) and
+// pooled[g, c] = max_k v (fused max-pool over the K rows of each group) is non-null.  One CTA per group.
 __global__ void bn_res_relu_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ coef,
                                    const float* __restrict__ w, const float* __restrict__ bias,
                                    const float* __restrict__ x, float* __restrict__ xf_out,
@@ -264,12 +264,9 @@ __global__ void bn_res_relu_kernel(const __nv_bfloat16* __restrict__ y, const fl
       const int64_t o = (g * K + k) * C + c;
       const float bn = bf16_round((__bfloat162float(y[o]) - mean) * inv * ww + bb);
       const float v = fmaxf(bn + x[o], 0.f);
-      if (pooled) {
-        mx = fmaxf(mx, v);
-      } else {
-        xf_out[o] = v;
-        xb_out[o] = __float2bfloat16_rn(v);
-      }
+      mx = fmaxf(mx, v);
+      if (xf_out) xf_out[o] = v;
+      if (xb_out) xb_out[o] = __float2bfloat16_rn(v);
     }
     if (pooled) pooled[g * C + c] = mx;
   }

@@ -230,14 +230,15 @@ class PrismaticVLM(nn.Module):
                 raise ValueError(f"Unexpected tactile shape {tuple(tactile.shape)}.")
             tac = self.tactile_embedder(t_flat.reshape(B * n_arms, self.tactile_dim)).view(B, n_arms, -1)
             parts.append(tac)
-            # nearest point-cloud centre to each gripper (:742-749); tiny [B, n_arms, 256] problem
-            g = gripper_xyz.to(dev).view(B, n_arms, 3).float()
-            d = torch.cdist(g, centers)
-            pos_pc = torch.topk(d, k=1, dim=2, largest=False)[1]
+            # nearest point-cloud centre to each gripper and its image patch (:742-749)
+            g = gripper_xyz.to(dev).view(B, n_arms, 3).float().contiguous()
             patch_w = int(front.shape[1] ** 0.5)
-            sel = torch.gather(patch_indices.unsqueeze(1).expand(-1, n_arms, -1, -1), 2,
-                               pos_pc.unsqueeze(-1).expand(-1, -1, -1, 2))
-            lin_img = sel[..., 0] * patch_w + sel[..., 1]
+            pos_pc = torch.empty((B, n_arms, 1), dtype=torch.long, device=dev)
+            lin_img = torch.empty((B, n_arms, 1), dtype=torch.long, device=dev)
+            _lib.check(_lib.lib().mla_nearest_center(
+                ops._p(g), ops._p(centers.contiguous()), ops._p(patch_indices.contiguous()), C.c_int32(B),
+                C.c_int32(n_arms), C.c_int32(centers.shape[1]), C.c_int32(patch_w), ops._p(pos_pc), ops._p(lin_img),
+                ops._stream()))
         else:
             parts.append(torch.zeros((B, 1, self.token_size), dtype=front.dtype, device=dev))
         fused = torch.cat(parts, dim=1)
