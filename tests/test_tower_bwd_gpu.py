@@ -130,7 +130,12 @@ def test_bn_bwd_kernel(cuda_lib, mode, up_f32):
     assert rel_err(dw, w32.grad) < tol, rel_err(dw, w32.grad)
     assert rel_err(db, b32.grad) < tol, rel_err(db, b32.grad)
     if mode == 2:
-        assert rel_err(dres, x32.grad) < 5e-3, rel_err(dres, x32.grad)
+        # the forward rounds bn(y) to bf16 before the residual add (the reference's BatchNorm output dtype), so the
+        # ReLU mask may differ from the fp32 graph's where the sum is within rounding of zero: compare away from it
+        clear = out.detach().abs() > 2e-2
+        assert clear.float().mean().item() > 0.45
+        assert rel_err(dres[clear], x32.grad[clear]) < 1e-6, rel_err(dres[clear], x32.grad[clear])
+        assert rel_err(dres, x32.grad) < 5e-2, rel_err(dres, x32.grad)
 
 
 def test_maxpool_and_gather_bwd_kernels(cuda_lib):
