@@ -280,6 +280,25 @@ int mla_group_pose_bwd(const void* dx, const void* fps_idx, const void* knn_idx,
                        int32_t groups, int32_t k, int32_t c, void* stream);
 int mla_diag_block_sum(const void* x, void* out, int32_t m, int32_t n, int32_t parts, void* stream);
 
+/* ---- inference denoise loop (MLA.predict_action_diff, models/mla/model_mla.py:592-775) -----------------------------
+ * The decoder prefix (everything in front of [t | x_0..x_T]) runs once on the training-path kernels; its post-RoPE K/V
+ * stay in the per-layer q|k|v buffers and each DDIM step runs only the suffix rows.
+ * gemv_bf16: skinny nn.Linear for m <= 64 rows (HBM-bound weight streaming): out[m,n] = bf16(bf16(x w^T) + residual),
+ *   x bf16 [m,k] (pitch ldx), w bf16 [n,k] (pitch ldw), residual optional; k and pitches multiples of 8.
+ * decode_attn: the last len_q positions of a length-len_k sequence attend to the cached keys with the bottom-right
+ *   aligned causal mask of flash-attn (modeling_llama.py:540-557): q row (b,i) at q + (b*len_q+i)*ldq + h*d, K/V row
+ *   (b,j) at k|v + (b*len_k+j)*ldkv + h*d; query i sees j <= len_k - len_q + i.  head_dim in {32,64,128,256}.
+ * ddim_step: x_{t-1} of GaussianDiffusion.ddim_sample with eta = 0, clip_denoised=False, epsilon-predicting model
+ *   (models/diffusion/gaussian_diffusion.py:342-352,:522-571): x, out f32 [n]; eps bf16 (or f32); coef f32 [4] =
+ *   sqrt(1/ac_t), sqrt(1/ac_t - 1), sqrt(ac_prev), sqrt(1 - ac_prev).  Bit-exact with the reference's fp32 op order. */
+int mla_gemv_bf16(const void* x, const void* w, void* out, const void* residual, int32_t m, int32_t n, int32_t k,
+                  int64_t ldx, int64_t ldw, int64_t ldo, int64_t ldr, void* stream);
+int mla_decode_attn(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* o, int64_t ldo,
+                    int32_t batch, int32_t heads, int32_t len_q, int32_t len_k, int32_t head_dim, float scale,
+                    void* stream);
+int mla_ddim_step(const void* x, const void* eps, int32_t eps_is_f32, const void* coef, void* out, int64_t n,
+                  void* stream);
+
 /* ---- optimizer step of the data-parallel trainer (training/strategies/fsdp.py:242-257,:310) ------------------
  * sumsq: out[0] += sum(x^2) (f32).  clip_coef: scale[0] = min(1, max_norm/(||g||*inv_world + 1e-6)) * inv_world,
  * scale[1] = the mean-gradient norm — clip_grad_norm_ without the host round trip (g holds rank-summed gradients).

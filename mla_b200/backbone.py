@@ -182,6 +182,31 @@ class _OfflineTokenizer:
         return [sum(map(ord, s)) % 20000 + 100]
 
 
+class PurePromptBuilder:
+    """`In: <message>\nOut: <reply></s>` turns (models/backbones/llm/prompting/base_prompter.py:27-77): the prompt of
+    predict_action_diff is one human turn."""
+
+    def __init__(self, model_family: str, system_prompt: Optional[str] = None) -> None:
+        self.model_family, self.system_prompt = model_family, system_prompt
+        self.bos, self.eos = "<s>", "</s>"
+        self.prompt, self.turn_count = "", 0
+
+    def add_turn(self, role: str, message: str) -> str:
+        human = self.turn_count % 2 == 0
+        assert role == ("human" if human else "gpt")
+        message = message.replace("<image>", "").strip()
+        wrapped = f"In: {message}\nOut: " if human else f"{message}{self.eos}"
+        self.prompt += wrapped
+        self.turn_count += 1
+        return wrapped
+
+    def get_potential_prompt(self, message: str) -> str:
+        return (self.prompt + f"In: {message}\nOut: ").removeprefix(self.bos).rstrip()
+
+    def get_prompt(self) -> str:
+        return self.prompt.removeprefix(self.bos).rstrip()
+
+
 class LLMBackbone(nn.Module):
     """models/backbones/llm/base_llm.py LLMBackbone + HFCausalLLMBackbone surface on our LlamaForCausalLM."""
 
@@ -218,7 +243,9 @@ class LLMBackbone(nn.Module):
 
     @property
     def prompt_builder_fn(self):
-        raise NotImplementedError("prompt templating is data-side (models/backbones/llm/prompting), out of scope")
+        """llama2-*-pure (the backbone of every MLA recipe) uses the "pure" template (llama2.py:81-83); the chat /
+        vicuna templates belong to other LLM families (out of scope)."""
+        return PurePromptBuilder
 
     @property
     def transformer_layer_cls(self):

@@ -276,6 +276,33 @@ class LlamaDecoderLayer(nn.Module):
                 self._grad_ready_cb(self)
         return dx
 
+    # ------------------------------------------------------------------ inference: prefix once, suffix per DDIM step
+    def prefill(self, x: torch.Tensor, sh: LayerShape, cache: torch.Tensor, total: int) -> torch.Tensor:
+        """Training-path forward of the prefix rows x [B*P, h] (no autograd); the post-RoPE k | v of every prefix
+        position are copied into cache [B*total, 2h] (rows b*total + j, j < P)."""
+        _, qkv, _, _, x_mid = self._attn_half(x, sh, False)
+        h = self.hidden_size
+        cache.view(sh.B, total, 2 * h)[:, :sh.S].copy_(qkv.view(sh.B, sh.S, 3 * h)[:, :, h:])
+        del qkv
+        return self._mlp_half(x_mid)[3]
+
+    def decode(self, x: torch.Tensor, cache: torch.Tensor, B: int, P: int, n: int, cos: torch.Tensor,
+               sin: torch.Tensor) -> torch.Tensor:
+        """The n suffix rows per sample, x [B*n, h], at positions P..P+n-1 against the cached prefix K/V.  Every
+        linear is a weight-streaming skinny GEMM (ops.gemv); cos/sin are the RoPE table rows P..P+n-1."""
+        wqkv, wo, wgu, wd, l1, l2 = self.compute_weights()
+        h, H = self.hidden_size, self.heads
+        D = h // H
+        n1 = ops.rmsnorm_fwd(x, l1, self.eps)
+        qkv = ops.gemv(n1, wqkv)
+        ops.rope_(qkv, 0, 2 * H, D, n, cos, sin)
+        cache.view(B, P + n, 2 * h)[:, P:].copy_(qkv.view(B, n, 3 * h)[:, :, h:])
+        ctx = ops.decode_attn(qkv, cache, B, H, n, P + n, D)
+        x_mid = ops.gemv(ctx, wo, residual=x)
+        n2 = ops.rmsnorm_fwd(x_mid, l2, self.eps)
+        act = ops.swiglu_fwd(ops.gemv(n2, wgu))
+        return ops.gemv(act, wd, residual=x_mid)
+
     def _mlp_half_no_down(self, x_mid: torch.Tensor):
         _, _, wgu, _, _, l2 = self.compute_weights()
         n2 = ops.rmsnorm_fwd(x_mid, l2, self.eps)
@@ -351,3 +378,27 @@ class LlamaModel(nn.Module):
             x = _LayerFn.apply(x, self._anchor, layer, sh)
         hs.append(ops.RMSNormFn.apply(x, self.norm.weight, self.eps))
         return hs
+
+    # ------------------------------------------------------------------ inference (KV-cached denoise loop)
+    @torch.no_grad()
+    def prefill(self, x: torch.Tensor, B: int, P: int, extra: int) -> List[torch.Tensor]:
+        """Run the P prefix rows per sample (x bf16 [B*P, h], no padding) through every layer once.  Returns one
+        k | v cache per layer, bf16 [B*(P+extra), 2h], with room for `extra` suffix positions."""
+        D = self.hidden_size // self.heads
+        cos, sin = self.rope_tables(P + extra, x.device)
+        sh = LayerShape(B, P, self.heads, D, None, cos[:P], sin[:P])
+        caches = []
+        for layer in self.layers:
+            cache = torch.empty((B * (P + extra), 2 * self.hidden_size), dtype=torch.bfloat16, device=x.device)
+            x = layer.prefill(x, sh, cache, P + extra)
+            caches.append(cache)
+        return caches
+
+    @torch.no_grad()
+    def decode(self, x: torch.Tensor, caches: List[torch.Tensor], B: int, P: int, n: int) -> torch.Tensor:
+        """n suffix rows per sample (x bf16 [B*n, h]) at positions P..P+n-1 -> final-norm hidden states [B*n, h]."""
+        cos, sin = self.rope_tables(P + n, x.device)
+        cs, sn = cos[P:P + n].contiguous(), sin[P:P + n].contiguous()
+        for layer, cache in zip(self.layers, caches):
+            x = layer.decode(x, cache, B, P, n, cs, sn)
+        return ops.rmsnorm_fwd(x, ops.bf16_of(self.norm.weight), self.eps)

@@ -7,7 +7,10 @@ t ~ randint(0, 100)), loss assembly — including the in-place aliasing that mak
   * identical image tensors of the `repeated_diffusion_steps` copies are tokenised once (the frozen tokenizer is
     deterministic) and the tokens are tiled, instead of tiling 4x the 7 MB/sample pixel tensors (:159-165);
   * no `print(loss_dict)` host sync per step (:233) unless MLA.verbose is set.
-Inference (`predict_action_*`), `from_pretrained` and EMA are out of the hot-path scope.
+Inference: `denoise_actions` is the device-side core of `predict_action_diff` (:592-775) — the DDIM loop over the
+diffusion head — with the decoder prefix computed once and K/V-cached (the reference re-encodes all 548 tokens at each
+of the 8 steps); `predict_action_diff` wraps it with the reference's prompt / normalisation plumbing.  The
+autoregressive samplers (`predict_action_ar`, `_diff_ar`, `_batch`), `from_pretrained` and EMA are out of scope.
 """
 from __future__ import annotations
 
@@ -144,3 +147,112 @@ class MLA(nn.Module):
         if self.verbose:
             print(loss_dict)
         return loss_dict, output
+
+    # ------------------------------------------------------------------ inference (models/mla/model_mla.py:592-775)
+    def create_ddim(self, ddim_step: int = 10, noise_schedule: str = "squaredcos_cap_v2", diffusion_steps: int = 100):
+        """model_mla.py:1166-1173."""
+        self.ddim_diffusion = create_diffusion(timestep_respacing="ddim" + str(ddim_step), noise_schedule=noise_schedule,
+                                               diffusion_steps=diffusion_steps, sigma_small=True, learn_sigma=False)
+        self._ddim_steps = ddim_step
+        return self.ddim_diffusion
+
+    @torch.no_grad()
+    def denoise_actions(self, input_ids, images, point_cloud=None, proprio=None, camera_name: str = "rlbench_front",
+                        noise: Optional[torch.Tensor] = None, num_ddim_steps: int = 8, use_kv_cache: bool = True,
+                        tactile=None, gripper_xyz=None) -> torch.Tensor:
+        """`prepare_diffusion` + `sample_diffusion` of predict_action_diff (:709-766) without classifier-free guidance
+        (cfg_scale <= 1: the only live branch — the reference's CFG branch calls a `forward_with_cfg` that
+        PrismaticVLM does not define).  input_ids end with the tag token 29871 (the reference strips its last three
+        ids, :714-715).  Returns the normalised action chunk f32 [B, T+1, action_dim] (on the device).
+
+        use_kv_cache=True: prefix once + per-step suffix (see PrismaticVLM.denoise_prefill).  False: the reference's
+        schedule — the whole eval forward (tokenizers included) at every step."""
+        self.vlm.eval()
+        dev = self.vlm.llm_backbone.llm.lm_head.weight.device
+        if getattr(self, "ddim_diffusion", None) is None or getattr(self, "_ddim_steps", None) != num_ddim_steps:
+            self.create_ddim(ddim_step=num_ddim_steps)
+        B = input_ids.shape[0]
+        if noise is None:
+            noise = torch.randn(B, self.future_action_window_size + 1, self.vlm.action_dim, device=dev)
+        noise = noise.to(dev).float()
+        if use_kv_cache:
+            st = self.vlm.denoise_prefill(input_ids, images, point_cloud=point_cloud, proprio=proprio,
+                                          camera_name=camera_name, tactile=tactile, gripper_xyz=gripper_xyz,
+                                          n_x=noise.shape[1])
+            model = lambda x, t: self.vlm.denoise_step(st, x, t)
+            return self.ddim_diffusion.ddim_sample_loop(model, noise.shape, noise, clip_denoised=False, eta=0.0)
+        kw = dict(input_ids=input_ids, images=images, point_cloud=point_cloud, proprio=proprio, camera_name=camera_name,
+                  tactile=tactile, gripper_xyz=gripper_xyz)
+        return self.ddim_diffusion.ddim_sample_loop(self.vlm.forward, noise.shape, noise, clip_denoised=False,
+                                                    model_kwargs=kw, eta=0.0)
+
+    @torch.no_grad()
+    def predict_action_diff(self, image=None, pointcloud=None, instruction: Optional[str] = None, cur_robot_state=None,
+                            unnorm_key: Optional[str] = None, cfg_scale: float = 0.0, use_ddim: bool = True,
+                            num_ddim_steps: int = 8, action_dim: int = 7, camera_name: str = "rlbench_front",
+                            use_kv_cache: bool = True, **kwargs):
+        """model_mla.py:592-775 — prompt, CLIP preprocessing, proprio normalisation and action un-normalisation are the
+        reference's host-side plumbing (HF tokenizer / image processor objects owned by the backbone); the denoise
+        loop is `denoise_actions`.  Returns the un-normalised action(s) as a numpy array, like the reference."""
+        import numpy as np
+        if cfg_scale > 1.0:
+            raise NotImplementedError("classifier-free guidance: the reference's branch calls PrismaticVLM."
+                                      "forward_with_cfg, which it does not define")
+        if not use_ddim or num_ddim_steps is None:
+            raise NotImplementedError("DDPM ancestral sampling (use_ddim=False) is not built; the reference's "
+                                      "evaluation uses DDIM")
+        self.vlm.eval()
+        dev = self.vlm.llm_backbone.llm.lm_head.weight.device
+        tokenizer = self.vlm.llm_backbone.tokenizer
+        prompt_builder = self.vlm.get_prompt_builder()
+        prompt_builder.add_turn(role="human", message=f"What action should the robot take to {instruction.lower()}?")
+        input_ids = tokenizer(prompt_builder.get_prompt(), truncation=True, return_tensors="pt").input_ids.to(dev)
+        if not torch.all(input_ids[:, -1] == 29871):                                          # :642-643
+            input_ids = torch.cat((input_ids, torch.tensor([[29871, 32001, 32002, 29871]], device=dev)), dim=1)
+        input_ids = input_ids[:, :-3]                                                         # :714-715
+        px = self.vlm.get_vision_tower_2d().image_processor.preprocess(image, return_tensors="pt")["pixel_values"][0]
+        px = torch.cat([px, torch.ones(1, px.shape[-2], px.shape[-1])], dim=0).unsqueeze(0).to(dev)
+        if isinstance(pointcloud, np.ndarray):
+            pointcloud = torch.from_numpy(pointcloud)
+        if pointcloud is not None:
+            pointcloud = pointcloud.to(dev).contiguous()
+        proprio = None
+        if cur_robot_state is not None:
+            st = self.get_proprio_stats(unnorm_key)
+            mask = st.get("mask", np.ones_like(st["q01"], dtype=bool))
+            hi, lo = np.array(st["q99"]), np.array(st["q01"])
+            cur = np.clip(np.where(mask, 2 * (cur_robot_state - lo) / (hi - lo + 1e-8) - 1, cur_robot_state), -1, 1)
+            proprio = torch.tensor(cur, dtype=torch.float32).unsqueeze(0).unsqueeze(0).to(dev)
+        samples = self.denoise_actions(input_ids, {"front_image": px}, point_cloud=pointcloud, proprio=proprio,
+                                       camera_name=camera_name, num_ddim_steps=num_ddim_steps,
+                                       use_kv_cache=use_kv_cache)
+        normalized = np.clip(samples[0].cpu().numpy(), -1, 1)
+        if normalized.ndim == 1:                                                              # :683-700 gripper bit(s)
+            for g in range(6, normalized.shape[0], 7):
+                normalized[g] = np.where(normalized[g] < 0.5, 0, 1)
+        else:
+            for g in range(6, normalized.shape[1], 7):
+                normalized[:, g] = np.where(normalized[:, g] < 0.5, 0, 1)
+        st = self.get_action_stats(unnorm_key)
+        mask = st.get("mask", np.ones_like(st["q01"], dtype=bool))
+        hi, lo = np.array(st["q99"]), np.array(st["q01"])
+        return np.where(mask, 0.5 * (normalized + 1) * (hi - lo) + lo, normalized)
+
+    @staticmethod
+    def _check_unnorm_key(norm_stats, unnorm_key):
+        """model_mla.py:1175-1192."""
+        if unnorm_key is None:
+            assert len(norm_stats) == 1, (f"Your model was trained on more than one dataset, please pass a `unnorm_key` "
+                                          f"from the following options to choose the statistics used for "
+                                          f"un-normalizing actions: {norm_stats.keys()}")
+            unnorm_key = next(iter(norm_stats.keys()))
+        assert unnorm_key in norm_stats, (f"The `unnorm_key` you chose is not in the set of available statistics; "
+                                          f"choose from: {norm_stats.keys()}")
+        return unnorm_key
+
+    def get_action_stats(self, unnorm_key=None):
+        """model_mla.py:1199-1204."""
+        return self.norm_stats[self._check_unnorm_key(self.norm_stats, unnorm_key)]["action"]
+
+    def get_proprio_stats(self, unnorm_key=None):
+        return self.norm_stats[self._check_unnorm_key(self.norm_stats, unnorm_key)]["proprio"]

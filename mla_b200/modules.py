@@ -209,9 +209,11 @@ class GaussianDiffusion:
 
 
 def create_diffusion(timestep_respacing="", noise_schedule="squaredcos_cap_v2", diffusion_steps=100, **_unused):
-    """models/diffusion/__init__.py:11-47 restricted to what the training step uses."""
-    if timestep_respacing not in (None, "", [diffusion_steps]):
-        raise NotImplementedError("timestep respacing is inference-only (out of the hot-path scope)")
+    """models/diffusion/__init__.py:11-47: the training process (empty respacing) or, for "ddim<N>", the respaced
+    sampler MLA.create_ddim builds for inference (mla_b200/sampler.py)."""
+    ddim = isinstance(timestep_respacing, str) and timestep_respacing.startswith("ddim")
+    if not ddim and timestep_respacing not in (None, "", [diffusion_steps]):
+        raise NotImplementedError("section-count respacing is not used by any MLA recipe")
     if noise_schedule == "squaredcos_cap_v2":
         betas = betas_for_alpha_bar(diffusion_steps, lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2)
     elif noise_schedule == "linear":
@@ -219,4 +221,8 @@ def create_diffusion(timestep_respacing="", noise_schedule="squaredcos_cap_v2", 
         betas = np.linspace(scale * 0.0001, scale * 0.02, diffusion_steps, dtype=np.float64)
     else:
         raise NotImplementedError(f"unknown beta schedule: {noise_schedule}")
+    if ddim:
+        from .sampler import SpacedDiffusion, space_timesteps_ddim
+        base = GaussianDiffusion(betas)
+        return SpacedDiffusion(base.alphas_cumprod, space_timesteps_ddim(diffusion_steps, int(timestep_respacing[4:])))
     return GaussianDiffusion(betas)

@@ -552,3 +552,58 @@ class CrossEntropyFn(torch.autograd.Function):
         check(_lib.lib().mla_ce_bwd(_p(d), C.c_int64(d.stride(0)), _p(labels), C.c_int64(B * S), C.c_int32(S),
                                     C.c_int32(logits.shape[1]), _p(lse), _p(acc), _p(gs), _stream()))
         return d, None
+
+
+# ---------------------------------------------------------------------------------------------- inference (decode)
+def gemv(x: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Skinny nn.Linear for a handful of rows (HBM-bound weight streaming, csrc/decode.cu): x bf16 [m,k], w bf16 [n,k]
+    -> bf16 [m,n] (+ residual).  Falls through to the tcgen05 GEMM above 64 rows."""
+    _req(x, torch.bfloat16, "x")
+    _req(w, torch.bfloat16, "w")
+    m, k = x.shape
+    n = w.shape[0]
+    if w.shape[1] != k:
+        raise _lib.MlaError(f"gemv: contraction mismatch {k} vs {w.shape[1]}")
+    if m > 64:
+        return gemm(x, w, residual=residual, out=out)
+    ldx, ldw = _rowmajor_2d(x, "x"), _rowmajor_2d(w, "w")
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.bfloat16, device=x.device)
+    ldr = 0
+    if residual is not None:
+        _req(residual, torch.bfloat16, "residual")
+        ldr = _rowmajor_2d(residual, "residual")
+    check(_lib.lib().mla_gemv_bf16(_p(x), _p(w), _p(out), _p(residual), C.c_int32(m), C.c_int32(n), C.c_int32(k),
+                                   C.c_int64(ldx), C.c_int64(ldw), C.c_int64(_rowmajor_2d(out, "out")), C.c_int64(ldr),
+                                   _stream()))
+    return out
+
+
+def decode_attn(q: torch.Tensor, kv: torch.Tensor, B: int, H: int, Lq: int, Lk: int, D: int) -> torch.Tensor:
+    """q: bf16 [B*Lq, >= H*D] (queries in the leading H*D columns, any row pitch); kv: bf16 [B*Lk, 2*H*D] (k | v), the
+    cache of a length-Lk sequence whose last Lq positions are the queries.  Returns ctx bf16 [B*Lq, H*D]."""
+    _req(q, torch.bfloat16, "q")
+    _req(kv, torch.bfloat16, "kv")
+    if tuple(kv.shape) != (B * Lk, 2 * H * D) or not kv.is_contiguous():
+        raise _lib.MlaError(f"decode_attn: kv cache must be contiguous [{B * Lk}, {2 * H * D}], got {tuple(kv.shape)}")
+    if q.shape[0] != B * Lq or q.shape[1] < H * D:
+        raise _lib.MlaError(f"decode_attn: q shape {tuple(q.shape)} does not hold [{B * Lq}, {H * D}] queries")
+    ctx = torch.empty((B * Lq, H * D), dtype=torch.bfloat16, device=q.device)
+    check(_lib.lib().mla_decode_attn(_p(q), C.c_int64(_rowmajor_2d(q, "q")), _p(kv),
+                                     C.c_void_p(kv.data_ptr() + 2 * H * D), C.c_int64(kv.stride(0)), _p(ctx),
+                                     C.c_int64(ctx.stride(0)), C.c_int32(B), C.c_int32(H), C.c_int32(Lq), C.c_int32(Lk),
+                                     C.c_int32(D), C.c_float(D ** -0.5), _stream()))
+    return ctx
+
+
+def ddim_step(x: torch.Tensor, eps: torch.Tensor, coef: torch.Tensor) -> torch.Tensor:
+    """x_{t-1} = ddim_sample(x_t, eps) with eta = 0 (see mla_ddim_step); x f32, eps bf16/f32, coef f32 [4] on device."""
+    _req(x, torch.float32, "x")
+    x, eps = x.contiguous(), eps.contiguous()
+    if eps.dtype not in (torch.float32, torch.bfloat16) or eps.numel() != x.numel():
+        raise _lib.MlaError("ddim_step: eps must be bf16 or f32 with as many elements as x")
+    out = torch.empty_like(x)
+    check(_lib.lib().mla_ddim_step(_p(x), _p(eps), C.c_int32(int(eps.dtype == torch.float32)), _p(coef), _p(out),
+                                   C.c_int64(x.numel()), _stream()))
+    return out

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 from functools import partial
+from types import SimpleNamespace
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -114,6 +115,10 @@ class PrismaticVLM(nn.Module):
         self._err_flag = None
 
     # ------------------------------------------------------------------ reference API surface
+    def get_prompt_builder(self, system_prompt: Optional[str] = None):
+        """prismatic.py:411-413."""
+        return self.llm_backbone.prompt_builder_fn(self.model_family, system_prompt=system_prompt)
+
     def get_vision_tower_2d(self):
         return self.vision_tower_2d
 
@@ -244,22 +249,11 @@ class PrismaticVLM(nn.Module):
         fused = torch.cat(parts, dim=1)
         return fused, patch_indices, valid_mask, pos_pc, lin_img, centers
 
-    # ------------------------------------------------------------------ forward
-    def forward(self, x=None, t=None, z=None, proprio=None, gripper_xyz=None, input_ids=None, attention_mask=None,
-                images=None, camera_name=None, point_cloud=None, tactile=None, labels=None, inputs_embeds=None,
-                past_key_values=None, use_cache=None, output_attentions=None, output_hidden_states=True,
-                return_dict=None, multimodal_indices=None, gen_discret_action=None, use_diff=None, next_images=None,
-                next_point_cloud=None, next_tactile=None, image_repeat: int = 1, **kwargs):
-        if use_diff is not None:
-            self.use_diff = use_diff
-        if past_key_values is not None or (input_ids is not None and input_ids.shape[1] == 1):
-            raise NotImplementedError("cached single-token decoding is inference-only (out of the hot-path scope)")
-        if images is None:
-            raise RuntimeError("Invalid `forward()` call!")
-        if multimodal_indices is not None and len(multimodal_indices) != len(input_ids):
-            raise NotImplementedError("unimodal/mixed batches (multimodal_indices) are not part of the VLA training path")
-        llm = self.llm_backbone.llm
-        dev = llm.lm_head.weight.device
+    def _fused_sequence(self, x, t, proprio, input_ids, attention_mask, labels, images, point_cloud, tactile,
+                        gripper_xyz, camera_name, image_repeat: int = 1):
+        """Tokenizers, embedders and the splice of prismatic.py:926-1042: returns the decoder input rows and the index
+        tensors around them (shared by the training forward and the inference prefill)."""
+        dev = self.llm_backbone.llm.lm_head.weight.device
         h = self.token_size
         eos_tag = 2 if self.training else 29871            # tag_0 (:882-887)
 
@@ -312,6 +306,30 @@ class PrismaticVLM(nn.Module):
             ops._p(head_rows), ops._p(self._err_flag), ops._stream()))
         embeds = ops.GatherRowsFn.apply(table, src_idx.view(-1))                              # [B*S, h]
 
+        return SimpleNamespace(embeds=embeds, mask=mask, fused_labels=fused_labels, lti=lti, head_rows=head_rows, B=B, S=S,
+                               F=F, h=h, n_x=n_x, n_ins=n_ins, fused=fused, patch_indices=patch_indices,
+                               valid_mask=valid_mask, pos_pc=pos_pc, lin_img=lin_img, N_pc=N_pc, N_img=N_img, dev=dev)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x=None, t=None, z=None, proprio=None, gripper_xyz=None, input_ids=None, attention_mask=None,
+                images=None, camera_name=None, point_cloud=None, tactile=None, labels=None, inputs_embeds=None,
+                past_key_values=None, use_cache=None, output_attentions=None, output_hidden_states=True,
+                return_dict=None, multimodal_indices=None, gen_discret_action=None, use_diff=None, next_images=None,
+                next_point_cloud=None, next_tactile=None, image_repeat: int = 1, **kwargs):
+        if use_diff is not None:
+            self.use_diff = use_diff
+        if past_key_values is not None or (input_ids is not None and input_ids.shape[1] == 1):
+            raise NotImplementedError("cached single-token decoding is inference-only (out of the hot-path scope)")
+        if images is None:
+            raise RuntimeError("Invalid `forward()` call!")
+        if multimodal_indices is not None and len(multimodal_indices) != len(input_ids):
+            raise NotImplementedError("unimodal/mixed batches (multimodal_indices) are not part of the VLA training path")
+        q = self._fused_sequence(x, t, proprio, input_ids, attention_mask, labels, images, point_cloud, tactile,
+                                 gripper_xyz, camera_name, image_repeat)
+        embeds, mask, fused_labels, lti, head_rows = q.embeds, q.mask, q.fused_labels, q.lti, q.head_rows
+        B, S, h, n_x, dev, fused = q.B, q.S, q.h, q.n_x, q.dev, q.fused
+        patch_indices, valid_mask, pos_pc, lin_img, N_pc, N_img = (q.patch_indices, q.valid_mask, q.pos_pc, q.lin_img,
+                                                                   q.N_pc, q.N_img)
         pc_idx = (1, 1 + N_pc)
         img_idx = (1 + N_pc, 1 + N_pc + N_img)
         tac_idx = (img_idx[1], img_idx[1] + self.action_dim // 7) if self.use_tactile else None
@@ -359,6 +377,49 @@ class PrismaticVLM(nn.Module):
         if self.training:
             return output, generation_outputs, generation_losses
         return output
+
+    # ------------------------------------------------------------------ inference: KV-cached denoise loop
+    @torch.no_grad()
+    def denoise_prefill(self, input_ids, images, point_cloud=None, proprio=None, camera_name=None, tactile=None,
+                        gripper_xyz=None, n_x: Optional[int] = None) -> SimpleNamespace:
+        """Everything of the eval-mode forward that does not depend on the DDIM step: tokenizers, projectors, the
+        splice, and the decoder over the prefix [BOS | fused | text.. | proprio] (prismatic.py:983-992 puts
+        [proprio | t | x..] in front of the last tag token 29871).  Under the causal mask the rows behind x (the tag
+        token itself) cannot influence the noise prediction read at the x rows (:1121-1124), so they are dropped.
+        Returns the per-layer K/V caches and the sizes `denoise_step` needs."""
+        if self.training:
+            raise RuntimeError("denoise_prefill is the inference path: call .eval() first (predict_action_diff does)")
+        if not self.use_diff:
+            raise RuntimeError("the denoise loop needs the diffusion head (use_diff=True)")
+        n_x = n_x if n_x is not None else self.future_action_window_size + 1
+        dev = self.llm_backbone.llm.lm_head.weight.device
+        B = input_ids.shape[0]
+        x0 = torch.zeros((B, n_x, self.action_dim), dtype=torch.float32, device=dev)
+        t0 = torch.zeros((B,), dtype=torch.long, device=dev)
+        q = self._fused_sequence(x0, t0, proprio, input_ids, None, None, images, point_cloud, tactile, gripper_xyz,
+                                 camera_name)
+        self._front_px = None
+        self.check_errors()
+        lti = q.lti.tolist()                     # one host read per action (the per-step loop has none)
+        if len(set(lti)) != 1:
+            raise NotImplementedError("KV-cached denoising needs the tag token at the same position in every sample "
+                                      "of the batch (use use_kv_cache=False for ragged prompts)")
+        P = lti[0] + 1                           # prefix rows: everything up to and including the proprio token
+        prefix = q.embeds.view(B, q.S, q.h)[:, :P].reshape(B * P, q.h).contiguous()
+        caches = self.llm_backbone.llm.model.prefill(prefix, B, P, 1 + n_x)
+        return SimpleNamespace(caches=caches, B=B, P=P, n_x=n_x, h=q.h, dev=dev)
+
+    @torch.no_grad()
+    def denoise_step(self, st: SimpleNamespace, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+        """Noise prediction for x_t [B, n_x, action_dim] at timestep t [B] from the cached prefix: only the
+        [t | x_0..x_T] rows run through the decoder."""
+        dev, B, n = st.dev, st.B, 1 + st.n_x
+        xe = self.x_embedder(x.to(dev).to(torch.bfloat16))                                    # [B, n_x, h]
+        te = self.t_embedder(t.to(dev)).unsqueeze(1)                                          # [B, 1, h]
+        rows = torch.cat([te, xe], dim=1).reshape(B * n, st.h).contiguous()
+        hid = self.llm_backbone.llm.model.decode(rows, st.caches, B, st.P, n)                 # [B*n, h], final norm
+        xrows = hid.view(B, n, st.h)[:, 1:].reshape(B * st.n_x, st.h).contiguous()
+        return self.final_layer(xrows).reshape(B, st.n_x, self.action_dim)
 
     def check_errors(self) -> None:
         """Deferred device-side error check (one sync): raises what the reference would have raised eagerly."""

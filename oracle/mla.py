@@ -251,18 +251,31 @@ def batchnorm_train(x: Tensor, w: Tensor, b: Tensor, eps: float = 1e-5, native: 
     return ((xf - mean) * torch.rsqrt(var + eps) * w.float().view(shape) + b.float().view(shape)).to(x.dtype)
 
 
+def batchnorm_eval(x: Tensor, w: Tensor, b: Tensor, mean: Tensor, var: Tensor, eps: float = 1e-5) -> Tensor:
+    """nn.BatchNorm{1,2}d in eval mode (inference, MLA.predict_action_diff calls self.vlm.eval()): running statistics."""
+    shape = [1, -1] + [1] * (x.dim() - 2)
+    xf = x.float()
+    return ((xf - mean.float().view(shape)) * torch.rsqrt(var.float().view(shape) + eps) * w.float().view(shape)
+            + b.float().view(shape)).to(x.dtype)
+
+
 def point_tokens(c: Ctx, pre: str, p: Tensor, starts: List[Tensor], k_neighbors: int = 81,
                  alpha: float = 1000.0, beta: float = 100.0, knn_override: Optional[List[Tensor]] = None,
-                 record: Optional[dict] = None) -> Tuple[Tensor, Tensor]:
+                 record: Optional[dict] = None, bn_eval: bool = False) -> Tuple[Tensor, Tensor]:
     """PointTokenizer.forward -> Point_PN_scan -> EncP.forward — pointvit.py:59-82, Point_PN.py:284-298 with
     FPS_kNN :84-94, LGA :112-158 ('scan' normalisation), PosE_Geo :228-249, Linear2Layer :188-219, max pooling.
     p [B,N,3] f32; starts = FPS start indices per stage.  Returns (tokens [B,G,768], centres [B,G,3])."""
     e = pre + ".patch_embed.EncP"
+
+    def bn(x_, q_):
+        if bn_eval:
+            return batchnorm_eval(x_, c.p(q_ + ".weight"), c.p(q_ + ".bias"), c.p(q_ + ".running_mean"), c.p(q_ + ".running_var"))
+        return batchnorm_train(x_, c.p(q_ + ".weight"), c.p(q_ + ".bias"), native=c.cpu_bf16)
     xyz = p.float()
     x = p.float().transpose(1, 2).contiguous()                                                # [B,3,N]
     w = c.p(e + ".raw_point_embed.net.0.weight").to(c.dt)
     x = F.conv1d(x.to(c.dt), w)
-    x = F.relu(batchnorm_train(x, c.p(e + ".raw_point_embed.net.1.weight"), c.p(e + ".raw_point_embed.net.1.bias"), native=c.cpu_bf16))
+    x = F.relu(bn(x, e + ".raw_point_embed.net.1"))
     out_dim, blocks = x.shape[1], [2, 1]
     for i in range(2):
         out_dim *= 2
@@ -291,9 +304,9 @@ def point_tokens(c: Ctx, pre: str, p: Tensor, starts: List[Tensor], k_neighbors:
         for j in range(blocks[i]):
             q = f"{e}.LGA_list.{i}.linear2.{j}"
             y = F.conv2d(xw.to(c.dt), c.p(q + ".net1.0.weight").to(c.dt), c.p(q + ".net1.0.bias").to(c.dt))
-            y = F.relu(batchnorm_train(y, c.p(q + ".net1.1.weight"), c.p(q + ".net1.1.bias"), native=c.cpu_bf16))
+            y = F.relu(bn(y, q + ".net1.1"))
             y = F.conv2d(y.to(c.dt), c.p(q + ".net2.0.weight").to(c.dt), c.p(q + ".net2.0.bias").to(c.dt))
-            y = batchnorm_train(y, c.p(q + ".net2.1.weight"), c.p(q + ".net2.1.bias"), native=c.cpu_bf16)
+            y = bn(y, q + ".net2.1")
             xw = F.relu(y + xw)
         x = xw.max(-1)[0]
     tok = c.lin(x.transpose(1, 2), pre + ".proj")
@@ -314,12 +327,19 @@ def forward(sd: Dict[str, Tensor], batch: Dict, cfg: Dict, draws: Dict, compute_
     R = cfg["repeated_diffusion_steps"]
     T = cfg["future_action_window_size"]
     rep = lambda v: v.repeat(R, *([1] * (v.dim() - 1)))                                        # model_mla.py:147-176
-    proprio, actions = rep(batch["proprio"]), rep(batch["actions"])
-    ids, am, labels = rep(batch["input_ids"]), rep(batch["attention_mask"]), rep(batch["labels"])
+    evalm = bool(cfg.get("eval"))          # inference: PrismaticVLM.forward in eval mode, x_t and t given by the sampler
+    proprio = rep(batch["proprio"])
+    ids = rep(batch["input_ids"])
+    am = rep(batch["attention_mask"]) if batch.get("attention_mask") is not None else torch.ones_like(ids, dtype=torch.bool)
     images = {k: rep(v) for k, v in batch["images"].items()}
-    a_future = actions[:, -(T + 1):, :]
-    noise, t = draws["noise"], draws["timestep"]
-    x = q_sample(a_future, t, noise)                                                          # :180
+    t = draws["timestep"]
+    if "x" in draws:
+        x, noise = draws["x"], draws.get("noise")
+    else:
+        a_future = rep(batch["actions"])[:, -(T + 1):, :]
+        noise = draws["noise"]
+        x = q_sample(a_future, t, noise)                                                      # :180
+    tag = 29871 if evalm else 2                                                               # prismatic.py:882-887
 
     V = "vlm."
     # ---- get_fused_tokens (prismatic.py:598-769)
@@ -328,7 +348,8 @@ def forward(sd: Dict[str, Tensor], batch: Dict, cfg: Dict, draws: Dict, compute_
     centers = None
     if cfg.get("use_pointcloud"):
         pc_emb, centers = point_tokens(c, V + "vision_tower_3d", rep(batch["point_cloud"]), draws["fps_starts"],
-                                       k_neighbors=cfg.get("k_neighbors", 81), knn_override=draws.get("knn_idx"))
+                                       k_neighbors=cfg.get("k_neighbors", 81), knn_override=draws.get("knn_idx"),
+                                       bn_eval=evalm)
         pc_tok = c.lin(F.gelu(c.lin(pc_emb, V + "projector_3d.projector.0")), V + "projector_3d.projector.2")
         patch_idx, valid = project_3d_to_2d(centers, cfg["camera_name"])
     else:
@@ -363,7 +384,7 @@ def forward(sd: Dict[str, Tensor], batch: Dict, cfg: Dict, draws: Dict, compute_
     te = timestep_embed(c, V + "t_embedder", t.to(torch.bfloat16)).unsqueeze(1)
     seqs, masks, ltis = [], [], []
     for i in range(B):
-        lti = int(torch.where(ids[i] == 2)[0][-1]) + F_
+        lti = int(torch.where(ids[i] == tag)[0][-1]) + F_
         ltis.append(lti)
         seqs.append(torch.cat([z[i, :lti], pr[i], te[i], xe[i], z[i, lti:]], 0).unsqueeze(0))
         masks.append(torch.cat([am[i, :1], torch.ones(F_, dtype=torch.bool), am[i, 1:lti - F_],
@@ -433,6 +454,8 @@ def forward(sd: Dict[str, Tensor], batch: Dict, cfg: Dict, draws: Dict, compute_
     y = timm_rmsnorm(last, sd[V + "final_layer.norm_final.weight"], 1e-6, cfg.get("rmsnorm_variance_mode", False))
     y = timm_mlp(c, V + "final_layer.mlp", y)
     noise_pred = torch.cat([y[i, l + 2:l + T + 3].unsqueeze(0) for i, l in enumerate(ltis)], 0)
-    diff = ((noise_pred - noise) ** 2).mean()
-    out.update(noise_pred=noise_pred, diff_loss=diff, total_loss=diff + total_extra)
+    out["noise_pred"] = noise_pred
+    if noise is not None:
+        diff = ((noise_pred - noise) ** 2).mean()
+        out.update(diff_loss=diff, total_loss=diff + total_extra)
     return out
