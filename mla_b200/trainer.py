@@ -170,6 +170,69 @@ class DataParallelTrainer:
         """Mean-gradient global norm of the last step (device scalar)."""
         return self._scale[1]
 
+    # ------------------------------------------------------------------ checkpoints (training/strategies/fsdp.py:100-160)
+    def save_checkpoint(self, run_dir, global_step: int, epoch: int, train_loss: Optional[float] = None,
+                        only_trainable: bool = True, save_optimizer: bool = True):
+        """Writes `<run_dir>/checkpoints/step-XXXXXX-epoch-XX-loss=Y.pt` = {"model": {module_key: state_dict}} with the
+        reference's module keys ("vlm." stripped, fsdp.py:133-136) and parameter names, so MLA.from_pretrained /
+        load_from_checkpoint of the reference read it.  Every data-parallel replica holds the full model: rank 0 writes
+        its own copy, no gather.  With save_optimizer the AdamW moments and the step counter go to the `.optimizer`
+        file next to it (the path the reference reserves, :158-160, but never writes): resume is exact."""
+        from collections import OrderedDict
+        from pathlib import Path
+        model = self.model
+        keys = model.trainable_module_keys if only_trainable else model.all_module_keys
+        full = model.state_dict()
+        out = {k: OrderedDict() for k in keys}
+        for name, v in full.items():
+            for k in keys:
+                if name.startswith(k + "."):
+                    out[k][name[len(k) + 1:]] = v.detach().to("cpu", copy=True)
+        out = {(k[4:] if k.startswith("vlm.") else k): v for k, v in out.items()}
+        ckpt_dir = Path(run_dir) / "checkpoints"
+        loss = "inf" if train_loss is None else f"{train_loss:.4f}"
+        path = ckpt_dir / f"step-{global_step:06d}-epoch-{epoch:02d}-loss={loss}.pt"
+        rank0 = self.world == 1 or dist.get_rank(self.pg) == 0
+        if rank0:
+            ckpt_dir.mkdir(parents=True, exist_ok=True)
+            torch.save({"model": out}, path)
+            if save_optimizer:
+                names = {id(p): n for n, p in model.named_parameters()}
+                opt = {names[i]: (m.detach().cpu(), v.detach().cpu()) for i, (m, v) in self.state.items() if i in names}
+                torch.save({"optimizer": {"state": opt, "step": self.step_count, "lr": self.lr, "betas": self.betas,
+                                          "eps": self.eps, "weight_decay": self.weight_decay},
+                            "scheduler": {"epoch": epoch, "global_step": global_step}}, path.with_suffix(".optimizer"))
+        if self.world > 1:
+            dist.barrier(group=self.pg)
+        return path
+
+    def load_checkpoint(self, path, load_optimizer: bool = True) -> dict:
+        """Inverse of save_checkpoint (also reads checkpoints written by the reference's FSDPStrategy: same layout).
+        Returns the scheduler record ({"epoch", "global_step"}) when an optimizer file was found, else {}."""
+        from pathlib import Path
+        path = Path(path)
+        blob = torch.load(path, map_location="cpu", weights_only=True)["model"]
+        sd = {}
+        for mkey, sub in blob.items():
+            for name, v in sub.items():
+                sd[f"vlm.{mkey}.{name}"] = v
+        missing, unexpected = self.model.load_state_dict(sd, strict=False)
+        if unexpected:
+            raise KeyError(f"checkpoint holds parameters this model does not have: {unexpected[:5]}")
+        for p in self.model.parameters():            # loaded in place: invalidate the cached bf16 compute copies
+            torch.autograd.graph.increment_version(p)
+        opt_path = path.with_suffix(".optimizer")
+        if not (load_optimizer and opt_path.exists()):
+            return {}
+        rec = torch.load(opt_path, map_location="cpu", weights_only=True)
+        named = dict(self.model.named_parameters())
+        self.state.clear()
+        for name, (m, v) in rec["optimizer"]["state"].items():
+            p = named[name]
+            self.state[id(p)] = (m.to(p.device).contiguous(), v.to(p.device).contiguous())
+        self.step_count = int(rec["optimizer"]["step"])
+        return rec.get("scheduler", {})
+
 
 class _nullctx:
     def __enter__(self):
