@@ -184,6 +184,20 @@ int mla_window_mean(const void* x, void* out, int64_t groups, int32_t c, int32_t
 int mla_local_attn(const void* q, const void* kv, void* out, int64_t groups, int32_t c, int32_t heads, int32_t win,
                    float scale, void* stream);
 
+/* ---- image preprocessing on uint8 camera frames (data side: vla/datasets/datasets.py:53-69, model_mla.py:661-665) ----
+ * CLIPImageProcessor(672) = PIL bicubic resize + rescale 1/255 + CLIP mean/std, + all-ones mask channel, bit-exact.
+ * frames u8 [batch, h, w, 3]; tab_h int32 [size, 2+taps_h], tab_v int32 [size, 2+taps_v] = per output column / row the
+ * first input index, the tap count and PIL's 22-bit fixed-point bicubic taps; lut f32 [3,256] = uint8 -> normalised
+ * value per channel (host-built in the reference's float64/float32 arithmetic).
+ * clip_preprocess: out f32 [batch, out_channels (3, or 4 with the ones mask), size, size].
+ * patchify_u8: the same pixels written straight as bf16 im2col rows (layout of mla_patchify). */
+int mla_clip_preprocess(const void* frames_u8, const void* tab_h, const void* tab_v, const void* lut, void* out,
+                        int32_t batch, int32_t h, int32_t w, int32_t size, int32_t taps_h, int32_t taps_v,
+                        int32_t out_channels, void* stream);
+int mla_patchify_u8(const void* frames_u8, const void* tab_h, const void* tab_v, const void* lut, void* out, int32_t batch,
+                    int32_t h, int32_t w, int32_t size, int32_t taps_h, int32_t taps_v, int32_t patch,
+                    int32_t conv_stride, int32_t k_pad, void* stream);
+
 /* ---- multimodal sequence splice (models/vlm/prismatic.py:949-1042,:1121-1124) -----------------------------------
  * Builds, without host syncs, the row map of [BOS | fused(n_fused) | text.. | proprio,t,x.. | EOS..] per sample:
  * src_idx int32 [B,S] into a row table (text at text_base+b*lt+j, fused at fused_base+b*n_fused+j, inserted rows at

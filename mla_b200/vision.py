@@ -112,6 +112,7 @@ class VisionTokenizer(nn.Module):
         self._image_processor = None
         self.patch_stride = 14
         self.conv_stride = 3
+        self.image_size = 672          # CLIPImageProcessor(size=672, crop_size=672), vision_tokenizer.py:98-105
         self.patch_embedding = nn.Conv2d(3, input_size, kernel_size=14, stride=14, bias=False)
         self.class_embedding = nn.Parameter(torch.randn(input_size))
         self.split_embedding = nn.Parameter(torch.randn(input_size))
@@ -142,17 +143,25 @@ class VisionTokenizer(nn.Module):
 
     def _pooled_impl(self, pixel_values: torch.Tensor, tape: Optional[dict]) -> Tuple[torch.Tensor, int, int]:
         """The kernel sequence of the forward; with `tape` the intermediates the backward needs are kept in it."""
-        B, Ct, H, W = pixel_values.shape
         P, cs, Cdim = self.patch_stride, self.conv_stride, self.hidden_size
-        h, w = H // (P * cs), W // (P * cs)
-        px = pixel_values.float().contiguous()
         lib = _lib.lib()
         s = ops._stream()
         wpatch = ops.bf16_of(self.patch_embedding.weight.view(Cdim, -1), pad2d=True)           # [C, 592]
         k_pad = wpatch.shape[1]
-        cols = torch.empty((B * h * w * cs * cs, k_pad), dtype=torch.bfloat16, device=px.device)
-        check(lib.mla_patchify(ops._p(px), ops._p(cols), C.c_int32(B), C.c_int32(Ct), C.c_int32(H), C.c_int32(W),
-                               C.c_int32(P), C.c_int32(cs), C.c_int32(k_pad), s))
+        if pixel_values.dtype == torch.uint8:
+            # raw camera frames [B, H, W, 3]: CLIP preprocessing fused into the im2col (csrc/preprocess.cu)
+            from .preprocess import patchify_frames
+            B = pixel_values.shape[0]
+            h = w = self.image_size // (P * cs)
+            px = pixel_values
+            cols = patchify_frames(pixel_values, self.image_size, P, cs, k_pad)
+        else:
+            B, Ct, H, W = pixel_values.shape
+            h, w = H // (P * cs), W // (P * cs)
+            px = pixel_values.float().contiguous()
+            cols = torch.empty((B * h * w * cs * cs, k_pad), dtype=torch.bfloat16, device=px.device)
+            check(lib.mla_patchify(ops._p(px), ops._p(cols), C.c_int32(B), C.c_int32(Ct), C.c_int32(H), C.c_int32(W),
+                                   C.c_int32(P), C.c_int32(cs), C.c_int32(k_pad), s))
         feat = ops.gemm(cols, wpatch)                                                          # [B*G*9, C]
         G = B * h * w
         red = torch.empty((G, Cdim), dtype=torch.bfloat16, device=px.device)
@@ -172,6 +181,8 @@ class VisionTokenizer(nn.Module):
 
     def pooled_features(self, pixel_values: torch.Tensor) -> Tuple[torch.Tensor, int, int]:
         """pixel_values f32 [B, 4, H, W] (RGB + all-ones mask channel) -> pooled bf16 [B*h*w, C], (h, w).
+        Also accepts the raw uint8 camera frames [B, Hc, Wc, 3]: the reference's CPU-side CLIP preprocessing is then
+        applied inside the im2col kernel, bit-exactly, and the 7.2 MB/sample f32 image is never materialised.
 
         Frozen in the finetune / post-training stages (prismatic.py:460,:493): runs without autograd.  Stage
         'pretrain' trains the tokenizer (:427-428): the same kernels run inside one autograd node whose backward is
@@ -179,7 +190,10 @@ class VisionTokenizer(nn.Module):
         masks the data pipeline emits (vla/datasets/datasets.py:68-69); other masks are rejected because downstream
         asserts 256 tokens anyway."""
         P, cs = self.patch_stride, self.conv_stride
-        h, w = pixel_values.shape[2] // (P * cs), pixel_values.shape[3] // (P * cs)
+        if pixel_values.dtype == torch.uint8:
+            h = w = self.image_size // (P * cs)
+        else:
+            h, w = pixel_values.shape[2] // (P * cs), pixel_values.shape[3] // (P * cs)
         params = self._tower_params()
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _VisionTowerFn.apply(self, pixel_values, *params), h, w

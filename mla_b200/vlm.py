@@ -209,6 +209,14 @@ class PrismaticVLM(nn.Module):
         dev = self.llm_backbone.llm.lm_head.weight.device
         self._front_px = views["front_image"].to(dev, non_blocking=True)     # kept for the image generation head
         front = self._image_tokens(self._front_px, image_repeat)
+        if self._front_px.dtype == torch.uint8:
+            # raw frames were tokenised through the fused preprocess+im2col; the generation head's pixel losses need
+            # the reference's f32 tensor, everything else does not
+            if self.use_generation and self.gen_image and self.training:
+                from .preprocess import clip_preprocess
+                self._front_px = clip_preprocess(self._front_px, self.vision_tower_2d.image_size)
+            else:
+                self._front_px = None
         B, n_img, _ = front.shape
         centers = None
         if self.use_pointcloud and pointcloud is not None:
