@@ -273,6 +273,46 @@ def run_ours(args):
     launches = (_lib.launch_count() - n0) // args.steps
     call(host)
     ms_e2e, last_loss = timed(args.steps, host, True)
+
+    # forward-only and forward+backward (no exchange / optimizer) — BASELINE.json quotes "fwd+bwd ms" next to tokens/s
+    model_ = mla.vlm.llm_backbone.llm.model
+    layer_ids = {id(p) for l in trainer.layers for p in l._masters()}
+    small = [p for p in mla.parameters() if p.requires_grad and id(p) not in layer_ids]
+
+    def fwd_only(b):
+        with torch.no_grad():
+            return fwd_loss(b)
+
+    def fwd_loss(b):
+        loss_dict, _ = mla(input_ids=b["input_ids"], attention_mask=b["attention_mask"], labels=b["labels"],
+                           actions=b["actions"], images=b["images"], point_cloud=b.get("point_cloud"),
+                           tactile=b.get("tactile"), proprio=b["proprio"], gripper_xyz=b.get("gripper_xyz"),
+                           action_masks=b["action_masks"], next_images=b.get("next_images"),
+                           next_point_cloud=b.get("next_point_cloud"), next_tactile=b.get("next_tactile"), **kw)
+        return loss_dict["total_loss"]
+
+    def fwd_bwd(b):
+        fwd_loss(b).backward()
+        model_.mark_grads_fresh()           # next backward overwrites the arenas (what zero_grad does in the step)
+        for p in small:
+            p.grad = None
+
+    def time_fn(fn, n):
+        fn(devb)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn(devb)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / n
+
+    ms_fwd = time_fn(fwd_only, max(2, args.steps // 2))
+    ms_fwd_bwd = time_fn(fwd_bwd, max(2, args.steps // 2))
     clocks = sampler.stop() if rank == 0 else None
     mla.vlm.check_errors()
     mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
@@ -304,6 +344,7 @@ def run_ours(args):
     out = {
         "metric": "multimodal_tokens_per_sec", "value": round(world * tokens / ms_dev * 1e3, 1), "unit": "tokens/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev, 2),
+        "fwd_ms": round(ms_fwd, 2), "fwd_bwd_ms": round(ms_fwd_bwd, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "per_gpu_batch": B, "repeated_diffusion_steps": R,
                    "seq_len": S, "tokens_per_gpu_step": tokens, "global_batch": B * world, "parallelism": f"dp{world}",
