@@ -381,17 +381,19 @@ class LlamaModel(nn.Module):
 
     # ------------------------------------------------------------------ inference (KV-cached denoise loop)
     @torch.no_grad()
-    def prefill(self, x: torch.Tensor, B: int, P: int, extra: int) -> List[torch.Tensor]:
+    def prefill(self, x: torch.Tensor, B: int, P: int, extra: int,
+                caches: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
         """Run the P prefix rows per sample (x bf16 [B*P, h], no padding) through every layer once.  Returns one
-        k | v cache per layer, bf16 [B*(P+extra), 2h], with room for `extra` suffix positions."""
+        k | v cache per layer, bf16 [B*(P+extra), 2h], with room for `extra` suffix positions (written into `caches`
+        when given: static buffers of a CUDA-graph session)."""
         D = self.hidden_size // self.heads
         cos, sin = self.rope_tables(P + extra, x.device)
-        sh = LayerShape(B, P, self.heads, D, None, cos[:P], sin[:P])
-        caches = []
-        for layer in self.layers:
-            cache = torch.empty((B * (P + extra), 2 * self.hidden_size), dtype=torch.bfloat16, device=x.device)
+        sh = LayerShape(B, P, self.heads, D, None, cos[:P].contiguous(), sin[:P].contiguous())
+        if caches is None:
+            caches = [torch.empty((B * (P + extra), 2 * self.hidden_size), dtype=torch.bfloat16, device=x.device)
+                      for _ in self.layers]
+        for layer, cache in zip(self.layers, caches):
             x = layer.prefill(x, sh, cache, P + extra)
-            caches.append(cache)
         return caches
 
     @torch.no_grad()

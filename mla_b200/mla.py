@@ -159,14 +159,16 @@ class MLA(nn.Module):
     @torch.no_grad()
     def denoise_actions(self, input_ids, images, point_cloud=None, proprio=None, camera_name: str = "rlbench_front",
                         noise: Optional[torch.Tensor] = None, num_ddim_steps: int = 8, use_kv_cache: bool = True,
-                        tactile=None, gripper_xyz=None) -> torch.Tensor:
+                        tactile=None, gripper_xyz=None, use_cuda_graph: bool = True) -> torch.Tensor:
         """`prepare_diffusion` + `sample_diffusion` of predict_action_diff (:709-766) without classifier-free guidance
         (cfg_scale <= 1: the only live branch — the reference's CFG branch calls a `forward_with_cfg` that
         PrismaticVLM does not define).  input_ids end with the tag token 29871 (the reference strips its last three
         ids, :714-715).  Returns the normalised action chunk f32 [B, T+1, action_dim] (on the device).
 
-        use_kv_cache=True: prefix once + per-step suffix (see PrismaticVLM.denoise_prefill).  False: the reference's
-        schedule — the whole eval forward (tokenizers included) at every step."""
+        use_kv_cache=True: prefix once + per-step suffix (see PrismaticVLM.denoise_prefill); with use_cuda_graph the
+        decoder prefill and the whole DDIM loop are replayed as two CUDA graphs (PrismaticVLM.denoise_session) — the
+        tokenizers and the splice stay eager.  use_kv_cache=False: the reference's schedule — the whole eval forward
+        (tokenizers included) at every step."""
         self.vlm.eval()
         dev = self.vlm.llm_backbone.llm.lm_head.weight.device
         if getattr(self, "ddim_diffusion", None) is None or getattr(self, "_ddim_steps", None) != num_ddim_steps:
@@ -175,6 +177,16 @@ class MLA(nn.Module):
         if noise is None:
             noise = torch.randn(B, self.future_action_window_size + 1, self.vlm.action_dim, device=dev)
         noise = noise.to(dev).float()
+        if use_kv_cache and use_cuda_graph:
+            q = self.vlm.denoise_prefill(input_ids, images, point_cloud=point_cloud, proprio=proprio,
+                                         camera_name=camera_name, tactile=tactile, gripper_xyz=gripper_xyz,
+                                         n_x=noise.shape[1], embeds_only=True)
+            sess = self.vlm.denoise_session(q.B, q.P, q.n_x, self.ddim_diffusion)
+            sess.prefix.copy_(q.prefix)
+            sess.noise.copy_(noise)
+            sess.g_prefill.replay()
+            sess.g_loop.replay()
+            return sess.out.clone()
         if use_kv_cache:
             st = self.vlm.denoise_prefill(input_ids, images, point_cloud=point_cloud, proprio=proprio,
                                           camera_name=camera_name, tactile=tactile, gripper_xyz=gripper_xyz,

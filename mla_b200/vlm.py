@@ -389,7 +389,7 @@ class PrismaticVLM(nn.Module):
     # ------------------------------------------------------------------ inference: KV-cached denoise loop
     @torch.no_grad()
     def denoise_prefill(self, input_ids, images, point_cloud=None, proprio=None, camera_name=None, tactile=None,
-                        gripper_xyz=None, n_x: Optional[int] = None) -> SimpleNamespace:
+                        gripper_xyz=None, n_x: Optional[int] = None, embeds_only: bool = False) -> SimpleNamespace:
         """Everything of the eval-mode forward that does not depend on the DDIM step: tokenizers, projectors, the
         splice, and the decoder over the prefix [BOS | fused | text.. | proprio] (prismatic.py:983-992 puts
         [proprio | t | x..] in front of the last tag token 29871).  Under the causal mask the rows behind x (the tag
@@ -414,8 +414,60 @@ class PrismaticVLM(nn.Module):
                                       "of the batch (use use_kv_cache=False for ragged prompts)")
         P = lti[0] + 1                           # prefix rows: everything up to and including the proprio token
         prefix = q.embeds.view(B, q.S, q.h)[:, :P].reshape(B * P, q.h).contiguous()
+        if embeds_only:
+            return SimpleNamespace(prefix=prefix, B=B, P=P, n_x=n_x, h=q.h, dev=dev)
         caches = self.llm_backbone.llm.model.prefill(prefix, B, P, 1 + n_x)
         return SimpleNamespace(caches=caches, B=B, P=P, n_x=n_x, h=q.h, dev=dev)
+
+    @torch.no_grad()
+    def denoise_session(self, B: int, P: int, n_x: int, sampler) -> SimpleNamespace:
+        """Static buffers + two CUDA graphs for one (batch, prefix length, action rows, DDIM schedule): `g_prefill`
+        (prefix embeddings -> per-layer K/V caches) and `g_loop` (the whole DDIM loop: noise -> sample).  A denoise
+        step is ~320 launches of a few microseconds each over 2-34 rows; issued from Python one by one it is
+        host-bound, replayed as a graph it runs at the weight-streaming rate.  Built on first use, replayed afterwards
+        (weights are read through the layers' persistent bf16 copies, refreshed in place when the masters change)."""
+        key = (B, P, n_x, tuple(sampler.timestep_map))
+        sessions = self.__dict__.setdefault("_denoise_sessions", {})
+        model = self.llm_backbone.llm.model
+        dev = self.llm_backbone.llm.lm_head.weight.device
+        fp = sum(p._version for p in self.parameters())
+        sess = sessions.get(key)
+        if sess is not None and sess.fp == fp:
+            return sess
+        h = self.token_size
+        if sess is None:
+            sess = SimpleNamespace(prefix=torch.zeros((B * P, h), dtype=torch.bfloat16, device=dev),
+                                   noise=torch.zeros((B, n_x, self.action_dim), dtype=torch.float32, device=dev),
+                                   caches=[torch.empty((B * (P + 1 + n_x), 2 * h), dtype=torch.bfloat16, device=dev)
+                                           for _ in model.layers], g_prefill=None, g_loop=None, out=None, fp=None)
+        st = SimpleNamespace(caches=sess.caches, B=B, P=P, n_x=n_x, h=h, dev=dev)
+
+        def run_prefill():
+            model.prefill(sess.prefix, B, P, 1 + n_x, caches=sess.caches)
+
+        def run_loop():
+            return sampler.ddim_sample_loop(lambda x, t: self.denoise_step(st, x, t), sess.noise.shape, sess.noise,
+                                            clip_denoised=False, eta=0.0)
+
+        # eager pass on a side stream: lazy initialisation (bf16 weight copies, RoPE / timestep tables, kernel
+        # attributes) happens here, never inside a capture; it also refreshes the copies after a weight update
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            run_prefill()
+            run_loop()
+        cur.wait_stream(side)
+        if sess.g_prefill is None:
+            sess.g_prefill = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(sess.g_prefill):
+                run_prefill()
+            sess.g_loop = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(sess.g_loop, pool=sess.g_prefill.pool()):
+                sess.out = run_loop()
+        sess.fp = fp
+        sessions[key] = sess
+        return sess
 
     @torch.no_grad()
     def denoise_step(self, st: SimpleNamespace, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:

@@ -134,6 +134,17 @@ def test_denoise_loop_matches_reference_sample(cuda_lib):
                                use_kv_cache=False)
     cached = mla.denoise_actions(cb["input_ids"], cb["images"], proprio=cb["proprio"], noise=noise, num_ddim_steps=n,
                                  use_kv_cache=True)
+    # default = prefill + whole DDIM loop replayed as CUDA graphs; eager launches of the same kernels agree, and a
+    # second replay (new noise, same session) is consistent with a fresh eager run
+    eager = mla.denoise_actions(cb["input_ids"], cb["images"], proprio=cb["proprio"], noise=noise, num_ddim_steps=n,
+                                use_kv_cache=True, use_cuda_graph=False)
+    assert rel_err(cached, eager) < 1e-3, rel_err(cached, eager)
+    noise2 = torch.randn_like(noise)
+    g2 = mla.denoise_actions(cb["input_ids"], cb["images"], proprio=cb["proprio"], noise=noise2, num_ddim_steps=n)
+    e2 = mla.denoise_actions(cb["input_ids"], cb["images"], proprio=cb["proprio"], noise=noise2, num_ddim_steps=n,
+                             use_cuda_graph=False)
+    assert rel_err(g2, e2) < 1e-3, rel_err(g2, e2)
+    assert len(mla.vlm._denoise_sessions) == 1
     gold = torch.from_numpy(z["sample"])
     sd32 = {k: (v.float() if torch.is_floating_point(v) else v) for k, v in sd.items()}
     cfg = dict(oracle_cfg(c), eval=True, repeated_diffusion_steps=1)
@@ -186,3 +197,23 @@ def test_ragged_tag_positions_are_rejected(cuda_lib):
         mla.denoise_actions(ids, cb["images"], proprio=cb["proprio"], num_ddim_steps=8, use_kv_cache=True)
     out = mla.denoise_actions(ids, cb["images"], proprio=cb["proprio"], num_ddim_steps=8, use_kv_cache=False)
     assert torch.isfinite(out).all()
+
+
+def test_graph_session_follows_weight_updates(cuda_lib):
+    """The CUDA-graph session reads weights through persistent bf16 copies: after the masters change (a training
+    step), the next call refreshes them and the replay matches a fresh eager run."""
+    name = "ddim_tiny_img"
+    z, batch = load_ddim(name)
+    c, mla, sd = build_cuda_model(z, DDIM_CASES[name])
+    cb = to_cuda_batch(batch)
+    noise = torch.from_numpy(z["noise"]).cuda()
+    kw = dict(proprio=cb["proprio"], noise=noise, num_ddim_steps=8)
+    before = mla.denoise_actions(cb["input_ids"], cb["images"], **kw)
+    with torch.no_grad():
+        for n_, p_ in mla.named_parameters():
+            if n_.endswith(("q_proj.weight", "final_layer.mlp.fc1.weight", "x_embedder.mlp.fc2.weight")):
+                p_.mul_(1.05)
+    after_graph = mla.denoise_actions(cb["input_ids"], cb["images"], **kw)
+    after_eager = mla.denoise_actions(cb["input_ids"], cb["images"], use_cuda_graph=False, **kw)
+    assert rel_err(after_graph, after_eager) < 1e-3, rel_err(after_graph, after_eager)
+    assert rel_err(after_graph, before) > 1e-3
