@@ -307,6 +307,24 @@ int mla_diag_block_sum(const void* x, void* out, int32_t m, int32_t n, int32_t p
  *   sqrt(1/ac_t), sqrt(1/ac_t - 1), sqrt(ac_prev), sqrt(1 - ac_prev).  Bit-exact with the reference's fp32 op order. */
 int mla_gemv_bf16(const void* x, const void* w, void* out, const void* residual, int32_t m, int32_t n, int32_t k,
                   int64_t ldx, int64_t ldw, int64_t ldo, int64_t ldr, void* stream);
+/* gemv_fused: the same skinny linear with an optional prologue applied to the activations as they are loaded (m <= 4,
+ * k <= 12288): prologue 1 = LlamaRMSNorm (modeling_llama.py:85-90) with ln_weight bf16 [k] and eps; prologue 2 = SwiGLU
+ * of LlamaMLP (:240), x = [gate | up] bf16 [m, 2k].  prologue 0 = mla_gemv_bf16. */
+typedef struct mla_gemv_args {
+  const void *x, *w;
+  void* out;
+  const void *residual, *ln_weight;
+  int32_t m, n, k;
+  int64_t ldx, ldw, ldo, ldr;
+  int32_t prologue;
+  float eps;
+} mla_gemv_args;
+int mla_gemv_fused(const mla_gemv_args* a, void* stream);
+/* rope_cache: the n new rows per sample of a packed q|k|v projection bf16 [batch*n, 3*heads*head_dim] at positions
+ * prefix..prefix+n-1: RoPE (modeling_llama.py:184-208) on q in place and on k into cache row (b*(prefix+n) + prefix + i),
+ * v copied beside it; cache bf16 [batch*(prefix+n), 2*heads*head_dim] = k | v; cos/sin bf16 [n, head_dim/2]. */
+int mla_rope_cache(void* qkv, void* cache, const void* cos_t, const void* sin_t, int32_t batch, int32_t n,
+                   int32_t prefix, int32_t heads, int32_t head_dim, void* stream);
 int mla_decode_attn(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* o, int64_t ldo,
                     int32_t batch, int32_t heads, int32_t len_q, int32_t len_k, int32_t head_dim, float scale,
                     void* stream);

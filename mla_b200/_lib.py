@@ -90,3 +90,12 @@ class GenImageArgs(C.Structure):
         ("sums", C.c_void_p), ("losses", C.c_void_p), ("coef", C.c_void_p),
         ("grad_scale", C.c_void_p), ("d_delta_raw", C.c_void_p), ("d_ao_raw", C.c_void_p),
     ]
+
+
+class GemvArgs(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w", C.c_void_p), ("out", C.c_void_p), ("residual", C.c_void_p), ("ln_weight", C.c_void_p),
+        ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
+        ("ldx", C.c_int64), ("ldw", C.c_int64), ("ldo", C.c_int64), ("ldr", C.c_int64),
+        ("prologue", C.c_int32), ("eps", C.c_float),
+    ]

@@ -34,48 +34,227 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 }
 
 // ---------------------------------------------------------------------------------------------- skinny GEMM
-// out[m, n] = bf16( bf16(sum_k x[m,k] w[n,k]) + residual[m,n] ),  m < M (any M; processed MB rows at a time), w [N,K]
-// row-major (nn.Linear layout).  K % 8 == 0, all row pitches multiples of 8 elements, 16-byte aligned bases.
-constexpr int GEMV_MB = 8;
-constexpr int GEMV_WARPS = 8;
-__global__ void __launch_bounds__(GEMV_WARPS * 32) gemv_bf16_kernel(
-    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ out,
-    const __nv_bfloat16* __restrict__ res, int M, int N, int K, int64_t ldx, int64_t ldw, int64_t ldo, int64_t ldr) {
-  const int n = blockIdx.x * GEMV_WARPS + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (n >= N) return;
-  const __nv_bfloat16* wr = w + int64_t(n) * ldw;
-  const int chunks = K >> 3;
-  for (int m0 = 0; m0 < M; m0 += GEMV_MB) {
-    const int mb = M - m0 < GEMV_MB ? M - m0 : GEMV_MB;
-    float acc[GEMV_MB];
+// out[m, n] = bf16( bf16(sum_k x'[m,k] w[n,k]) + residual[m,n] ),  w [N,K] row-major (nn.Linear layout), m < M <= 64.
+//
+// Pure weight streaming, organised the way the DMA engine likes it: ONE producer thread per CTA issues a
+// cp.async.bulk (TMA, no tensor map) per weight row — 8-22 KB contiguous — into a multi-stage shared-memory ring
+// guarded by full/empty mbarriers; 16 consumer warps take the dot products from shared memory.  One persistent CTA per
+// SM owns ~190 KB of ring, so ~150 KB per SM is always in flight.  A slot holds RPI consecutive weight rows; per slot
+// the consumers do one warp-shuffle + one named-barrier reduction.
+//   fast path (M <= 4): the activations live in REGISTERS for the whole kernel (thread t always multiplies the same
+//     k-chunks), optionally produced on the fly by a fused prologue:
+//       PRO_RMSNORM  x' = bf16(g * bf16(x * rstd))            (LlamaRMSNorm, modeling_llama.py:85-90)
+//       PRO_SWIGLU   x' = bf16(bf16(silu(gate)) * up), x = [gate | up]   (LlamaMLP, :240)
+//   general path (M <= 64): 8 activation rows per pass from L1/L2, several passes over the SAME shared-memory slot —
+//     the weights still cross HBM exactly once.
+constexpr int GV_CWARPS = 16;
+constexpr int GV_CONSUMERS = GV_CWARPS * 32;
+constexpr int GV_THREADS = GV_CONSUMERS + 32;
+constexpr int GV_MAX_STAGES = 8;
+constexpr int GV_RING_BYTES = 192 * 1024;
+enum { GV_PRO_NONE = 0, GV_PRO_RMSNORM = 1, GV_PRO_SWIGLU = 2 };
+
+struct GemvParams {
+  const __nv_bfloat16 *x, *w, *res, *ln_w;
+  __nv_bfloat16* out;
+  int M, N, K;
+  int64_t ldx, ldw, ldo, ldr;
+  float eps;
+  int stages;          // ring depth
+  uint32_t pitch;      // bytes per weight row in the ring (K*2 rounded up to 128)
+};
+
+__device__ __forceinline__ void bulk_load_row(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void consumers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(GV_CONSUMERS) : "memory"); }
+__device__ __forceinline__ uint4 pack8f(const float* f) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+__device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float acc) {
+  float fa[8], fb[8];
+  unpack8(a, fa);
+  unpack8(b, fb);
 #pragma unroll
-    for (int r = 0; r < GEMV_MB; ++r) acc[r] = 0.f;
-#pragma unroll 4
-    for (int c = lane; c < chunks; c += 32) {
-      float wf[8];
-      // the first pass streams the weight row from HBM; later row blocks find it in L2
-      unpack8(ld_stream16(wr + 8 * c), wf);
+  for (int e = 0; e < 8; ++e) acc = fmaf(fa[e], fb[e], acc);
+  return acc;
+}
+
+// MB: activation rows held per thread (fast path: M <= MB, registers) — or 8 in the general path (GEN = 1).
+// CPT: k-chunks (8 bf16) per consumer thread (fast path).  RPI: weight rows per ring slot.
+template <int MB, int CPT, int RPI, int PRO, int GEN>
+__global__ void __launch_bounds__(GV_THREADS, 1) gemv_ring_kernel(GemvParams p) {
+  extern __shared__ uint8_t gv_smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gv_smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ uint64_t full_bar[GV_MAX_STAGES], empty_bar[GV_MAX_STAGES];
+  __shared__ float partial[2][GV_CWARPS][RPI * MB];
+  __shared__ float red_ss[GV_CWARPS][MB];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunks = p.K >> 3;
+  const uint32_t row_bytes = uint32_t(p.K) * 2u;
+  const uint32_t slot_bytes = p.pitch * RPI;
+  const int groups = (p.N + RPI - 1) / RPI;
+  if (tid == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], GV_CWARPS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == GV_CWARPS) {
+    // ===================== producer: one thread streams this CTA's weight rows =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int g = blockIdx.x; g < groups; g += gridDim.x, ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        const int n0 = g * RPI;
+        const int valid = p.N - n0 < RPI ? p.N - n0 : RPI;
+        mbar_arrive_expect_tx(&full_bar[s], row_bytes * valid);
+        for (int r = 0; r < valid; ++r)
+          bulk_load_row(ring + size_t(s) * slot_bytes + size_t(r) * p.pitch, p.w + int64_t(n0 + r) * p.ldw, row_bytes,
+                        &full_bar[s]);
+      }
+    }
+    return;
+  }
+
+  // ===================== consumers =====================
+  uint4 xr[GEN ? 1 : MB][GEN ? 1 : CPT];
+  if (!GEN) {
+    float ss[MB];
 #pragma unroll
-      for (int r = 0; r < GEMV_MB; ++r) {
-        if (r < mb) {
-          float xf[8];
-          unpack8(__ldg(reinterpret_cast<const uint4*>(x + int64_t(m0 + r) * ldx + 8 * c)), xf);
+    for (int r = 0; r < MB; ++r) ss[r] = 0.f;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[r] = fmaf(xf[e], wf[e], acc[r]);
+    for (int r = 0; r < MB; ++r) {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = tid + j * GV_CONSUMERS;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r < p.M && c < chunks) {
+          if (PRO == GV_PRO_SWIGLU) {
+            float g[8], u[8], o[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p.x + int64_t(r) * p.ldx + 8 * c)), g);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p.x + int64_t(r) * p.ldx + p.K + 8 * c)), u);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = bf16_round(g[e] * (1.f / (1.f + __expf(-g[e])))) * u[e];
+            v = pack8f(o);
+          } else {
+            v = __ldg(reinterpret_cast<const uint4*>(p.x + int64_t(r) * p.ldx + 8 * c));
+            if (PRO == GV_PRO_RMSNORM) {
+              float f[8];
+              unpack8(v, f);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) ss[r] = fmaf(f[e], f[e], ss[r]);
+            }
+          }
+        }
+        xr[r][j] = v;
+      }
+    }
+    if (PRO == GV_PRO_RMSNORM) {
+#pragma unroll
+      for (int r = 0; r < MB; ++r) {
+        const float t = d_wsum(ss[r]);
+        if (lane == 0) red_ss[warp][r] = t;
+      }
+      consumers_sync();
+#pragma unroll
+      for (int r = 0; r < MB; ++r) {
+        float t = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < GV_CWARPS; ++w2) t += red_ss[w2][r];
+        const float rstd = rsqrtf(t / float(p.K) + p.eps);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          const int c = tid + j * GV_CONSUMERS;
+          if (c < chunks) {
+            float f[8], g[8], o[8];
+            unpack8(xr[r][j], f);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p.ln_w + 8 * c)), g);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = g[e] * bf16_round(f[e] * rstd);
+            xr[r][j] = pack8f(o);
+          }
         }
       }
     }
+  }
+
+  int it = 0, pb = 0;
+  for (int g = blockIdx.x; g < groups; g += gridDim.x, ++it) {
+    const int s = it % p.stages;
+    const uint32_t ph = (it / p.stages) & 1;
+    mbar_wait(&full_bar[s], ph);
+    const uint8_t* slot = ring + size_t(s) * slot_bytes;
+    const int n0 = g * RPI;
+    const int passes = GEN ? (p.M + MB - 1) / MB : 1;
+    for (int pass = 0; pass < passes; ++pass) {
+      const int m0 = pass * MB;
+      float acc[RPI][MB];
 #pragma unroll
-    for (int r = 0; r < GEMV_MB; ++r) {
-      if (r < mb) {
-        const float s = d_wsum(acc[r]);
-        if (lane == r) {
-          float v = bf16_round(s);
-          if (res) v += __bfloat162float(res[int64_t(m0 + r) * ldr + n]);
-          out[int64_t(m0 + r) * ldo + n] = __float2bfloat16_rn(v);
+      for (int rr = 0; rr < RPI; ++rr)
+#pragma unroll
+        for (int r = 0; r < MB; ++r) acc[rr][r] = 0.f;
+      if (!GEN) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+          const int c = tid + j * GV_CONSUMERS;
+          if (c < chunks) {
+#pragma unroll
+            for (int rr = 0; rr < RPI; ++rr) {
+              const uint4 wv = *reinterpret_cast<const uint4*>(slot + size_t(rr) * p.pitch + 16 * c);
+#pragma unroll
+              for (int r = 0; r < MB; ++r) acc[rr][r] = dot8(wv, xr[r][j], acc[rr][r]);
+            }
+          }
+        }
+      } else {
+        for (int c = tid; c < chunks; c += GV_CONSUMERS) {
+          uint4 wv[RPI];
+#pragma unroll
+          for (int rr = 0; rr < RPI; ++rr) wv[rr] = *reinterpret_cast<const uint4*>(slot + size_t(rr) * p.pitch + 16 * c);
+#pragma unroll
+          for (int r = 0; r < MB; ++r) {
+            if (m0 + r < p.M) {
+              const uint4 xv = __ldg(reinterpret_cast<const uint4*>(p.x + int64_t(m0 + r) * p.ldx + 8 * c));
+#pragma unroll
+              for (int rr = 0; rr < RPI; ++rr) acc[rr][r] = dot8(wv[rr], xv, acc[rr][r]);
+            }
+          }
         }
       }
+      if (pass == passes - 1) {           // this warp no longer reads the slot: hand it back to the producer
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+      }
+#pragma unroll
+      for (int rr = 0; rr < RPI; ++rr)
+#pragma unroll
+        for (int r = 0; r < MB; ++r) {
+          const float t = d_wsum(acc[rr][r]);
+          if (lane == 0) partial[pb][warp][rr * MB + r] = t;
+        }
+      consumers_sync();
+      if (tid < RPI * MB) {
+        const int rr = tid / MB, r = tid % MB;
+        const int n = n0 + rr, m = m0 + r;
+        if (n < p.N && m < p.M) {
+          float t = 0.f;
+#pragma unroll
+          for (int w2 = 0; w2 < GV_CWARPS; ++w2) t += partial[pb][w2][tid];
+          float v = bf16_round(t);
+          if (p.res) v += __bfloat162float(p.res[int64_t(m) * p.ldr + n]);
+          p.out[int64_t(m) * p.ldo + n] = __float2bfloat16_rn(v);
+        }
+      }
+      pb ^= 1;      // the next reduction writes the other buffer; this one is re-used only after another barrier
     }
   }
 }
@@ -171,6 +350,49 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------- RoPE + cache append
+// The n new rows per sample of a packed q|k|v projection [B*n, 3h] at positions P..P+n-1: q is rotated in place (the
+// attention kernel reads it there), k is rotated into the cache row (b*Lk + P + i) columns [0,h), v is copied to
+// columns [h,2h).  Same arithmetic and rounding points as rope_kernel (norm_rope_act.cu; modeling_llama.py:184-208).
+// cos/sin bf16 [n, d/2] = the table rows of positions P..P+n-1.  One thread per (row, head, 8-element chunk of d/2).
+__global__ void rope_cache_kernel(__nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ cache,
+                                  const __nv_bfloat16* __restrict__ cos_t, const __nv_bfloat16* __restrict__ sin_t,
+                                  int B, int n, int P, int heads, int d) {
+  const int half = d >> 1, cpr = half >> 3, h = heads * d;
+  const int64_t total = int64_t(B) * n * heads * cpr;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int c = int(idx % cpr);
+    const int hd = int((idx / cpr) % heads);
+    const int64_t t = idx / (int64_t(cpr) * heads);         // row of qkv: b*n + i
+    const int i = int(t % n), b = int(t / n);
+    float cs[8], sn[8];
+    unpack8(*reinterpret_cast<const uint4*>(cos_t + int64_t(i) * half + c * 8), cs);
+    unpack8(*reinterpret_cast<const uint4*>(sin_t + int64_t(i) * half + c * 8), sn);
+    __nv_bfloat16* row = qkv + t * 3 * int64_t(h);
+    __nv_bfloat16* crow = cache + (int64_t(b) * (P + n) + P + i) * 2 * int64_t(h);
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {                 // 0: q (in place), 1: k (into the cache)
+      const __nv_bfloat16* src = row + part * h + int64_t(hd) * d + c * 8;
+      __nv_bfloat16* dst = part == 0 ? row + int64_t(hd) * d + c * 8 : crow + int64_t(hd) * d + c * 8;
+      float x1[8], x2[8], o1[8], o2[8];
+      unpack8(*reinterpret_cast<const uint4*>(src), x1);
+      unpack8(*reinterpret_cast<const uint4*>(src + half), x2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o1[j] = bf16_round(x1[j] * cs[j]) + bf16_round(-x2[j] * sn[j]);
+        o2[j] = bf16_round(x2[j] * cs[j]) + bf16_round(x1[j] * sn[j]);
+      }
+      *reinterpret_cast<uint4*>(dst) = pack8f(o1);
+      *reinterpret_cast<uint4*>(dst + half) = pack8f(o2);
+    }
+    const __nv_bfloat16* vs = row + 2 * h + int64_t(hd) * d + c * 8;
+    __nv_bfloat16* vd = crow + h + int64_t(hd) * d + c * 8;
+    *reinterpret_cast<uint4*>(vd) = *reinterpret_cast<const uint4*>(vs);
+    *reinterpret_cast<uint4*>(vd + half) = *reinterpret_cast<const uint4*>(vs + half);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- DDIM update
 // coef f32 [4] = sqrt(1/ac_t), sqrt(1/ac_t - 1), sqrt(ac_prev), sqrt(1 - ac_prev) of the current respaced step.
 //   pred_xstart = c0*x - c1*eps ; eps' = (c0*x - pred_xstart)/c1 ; out = pred_xstart*c2 + c3*eps'
@@ -194,20 +416,85 @@ __global__ void ddim_step_kernel(const float* __restrict__ x, const EpsT* __rest
 using namespace mla;
 #define S_(x) ((cudaStream_t)(x))
 
-extern "C" int mla_gemv_bf16(const void* x, const void* w, void* out, const void* residual, int32_t m, int32_t n,
-                             int32_t k, int64_t ldx, int64_t ldw, int64_t ldo, int64_t ldr, void* stream) {
+template <int MB, int CPT, int RPI, int PRO, int GEN>
+static int launch_gemv(const GemvParams& p, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = gemv_ring_kernel<MB, CPT, RPI, PRO, GEN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GV_RING_BYTES + 128);
+    if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "cudaFuncSetAttribute(gemv smem): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  kern<<<grid, GV_THREADS, smem, stream>>>(p);
+  return MLA_OK;
+}
+
+template <int PRO>
+static int dispatch_gemv_fast(const GemvParams& p, int mb, bool small_k, int grid, size_t smem, cudaStream_t st) {
+  // small_k: K <= 4096 -> one k-chunk per thread, 4 weight rows per slot; else 3 chunks per thread, 2 rows per slot
+  if (small_k) {
+    if (mb == 1) return launch_gemv<1, 1, 4, PRO, 0>(p, grid, smem, st);
+    if (mb == 2) return launch_gemv<2, 1, 4, PRO, 0>(p, grid, smem, st);
+    return launch_gemv<4, 1, 4, PRO, 0>(p, grid, smem, st);
+  }
+  if (mb == 1) return launch_gemv<1, 3, 2, PRO, 0>(p, grid, smem, st);
+  if (mb == 2) return launch_gemv<2, 3, 2, PRO, 0>(p, grid, smem, st);
+  return launch_gemv<4, 3, 2, PRO, 0>(p, grid, smem, st);
+}
+
+extern "C" int mla_gemv_fused(const mla_gemv_args* a, void* stream) {
   if (int rc = device_check()) return rc;
-  if (m <= 0 || n <= 0) return MLA_OK;
-  if (k <= 0 || (k & 7) || (ldx & 7) || (ldw & 7))
-    return set_error(MLA_ERR_ARG, "gemv: k and the row pitches of x and w must be multiples of 8 (k=%d)", k);
-  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15)
+  if (a == nullptr) return set_error(MLA_ERR_ARG, "gemv: null args");
+  if (a->m <= 0 || a->n <= 0) return MLA_OK;
+  const int M = a->m, N = a->n, K = a->k;
+  if (K <= 0 || (K & 7) || (a->ldx & 7) || (a->ldw & 7))
+    return set_error(MLA_ERR_ARG, "gemv: k and the row pitches of x and w must be multiples of 8 (k=%d)", K);
+  if ((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->w)) & 15)
     return set_error(MLA_ERR_ARG, "gemv: x and w must be 16-byte aligned");
-  if (m > 64) return set_error(MLA_ERR_ARG, "gemv: m=%d rows is a GEMM, use mla_gemm_bf16", m);
-  gemv_bf16_kernel<<<(n + GEMV_WARPS - 1) / GEMV_WARPS, GEMV_WARPS * 32, 0, S_(stream)>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, (__nv_bfloat16*)out, (const __nv_bfloat16*)residual, m, n, k,
-      ldx, ldw, ldo, ldr);
+  if (M > 64) return set_error(MLA_ERR_ARG, "gemv: m=%d rows is a GEMM, use mla_gemm_bf16", M);
+  if (a->prologue < GV_PRO_NONE || a->prologue > GV_PRO_SWIGLU) return set_error(MLA_ERR_ARG, "gemv: unknown prologue");
+  if (a->prologue == GV_PRO_RMSNORM && (!a->ln_weight || (reinterpret_cast<uintptr_t>(a->ln_weight) & 15)))
+    return set_error(MLA_ERR_ARG, "gemv: the RMSNorm prologue needs a 16-byte aligned weight vector");
+  const bool small_k = K <= GV_CONSUMERS * 8;
+  const bool fast = M <= 4 && K <= GV_CONSUMERS * 8 * 3;
+  if (a->prologue != GV_PRO_NONE && !fast)
+    return set_error(MLA_ERR_ARG, "gemv: fused prologues need m <= 4 and k <= %d", GV_CONSUMERS * 8 * 3);
+  GemvParams p;
+  p.x = (const __nv_bfloat16*)a->x; p.w = (const __nv_bfloat16*)a->w; p.res = (const __nv_bfloat16*)a->residual;
+  p.ln_w = (const __nv_bfloat16*)a->ln_weight; p.out = (__nv_bfloat16*)a->out;
+  p.M = M; p.N = N; p.K = K; p.ldx = a->ldx; p.ldw = a->ldw; p.ldo = a->ldo; p.ldr = a->ldr; p.eps = a->eps;
+  p.pitch = (uint32_t(K) * 2u + 127u) & ~127u;
+  const int rpi = small_k ? 4 : 2;
+  const size_t slot = size_t(p.pitch) * rpi;
+  int stages = int(GV_RING_BYTES / slot);
+  if (stages < 2) return set_error(MLA_ERR_ARG, "gemv: k=%d does not fit the shared-memory ring, use mla_gemm_bf16", K);
+  p.stages = stages > GV_MAX_STAGES ? GV_MAX_STAGES : stages;
+  const size_t smem = slot * p.stages + 128;
+  const int groups = (N + rpi - 1) / rpi;
+  const int grid = groups < num_sms() ? groups : num_sms();
+  cudaStream_t st = S_(stream);
+  int rc;
+  if (fast) {
+    const int mb = M <= 1 ? 1 : (M <= 2 ? 2 : 4);
+    if (a->prologue == GV_PRO_RMSNORM) rc = dispatch_gemv_fast<GV_PRO_RMSNORM>(p, mb, small_k, grid, smem, st);
+    else if (a->prologue == GV_PRO_SWIGLU) rc = dispatch_gemv_fast<GV_PRO_SWIGLU>(p, mb, small_k, grid, smem, st);
+    else rc = dispatch_gemv_fast<GV_PRO_NONE>(p, mb, small_k, grid, smem, st);
+  } else {
+    rc = small_k ? launch_gemv<8, 1, 4, GV_PRO_NONE, 1>(p, grid, smem, st)
+                 : launch_gemv<8, 1, 2, GV_PRO_NONE, 1>(p, grid, smem, st);
+  }
+  if (rc) return rc;
   MLA_CHECK_LAUNCH("gemv_bf16");
   return MLA_OK;
+}
+
+extern "C" int mla_gemv_bf16(const void* x, const void* w, void* out, const void* residual, int32_t m, int32_t n,
+                             int32_t k, int64_t ldx, int64_t ldw, int64_t ldo, int64_t ldr, void* stream) {
+  mla_gemv_args a;
+  a.x = x; a.w = w; a.out = out; a.residual = residual; a.ln_weight = nullptr;
+  a.m = m; a.n = n; a.k = k; a.ldx = ldx; a.ldw = ldw; a.ldo = ldo; a.ldr = ldr;
+  a.prologue = GV_PRO_NONE; a.eps = 0.f;
+  return mla_gemv_fused(&a, stream);
 }
 
 extern "C" int mla_decode_attn(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* o,
@@ -247,5 +534,19 @@ extern "C" int mla_ddim_step(const void* x, const void* eps, int32_t eps_is_f32,
     ddim_step_kernel<__nv_bfloat16><<<grid, 256, 0, S_(stream)>>>((const float*)x, (const __nv_bfloat16*)eps,
                                                                   (const float*)coef, (float*)out, n);
   MLA_CHECK_LAUNCH("ddim_step");
+  return MLA_OK;
+}
+
+extern "C" int mla_rope_cache(void* qkv, void* cache, const void* cos_t, const void* sin_t, int32_t batch, int32_t n,
+                              int32_t prefix, int32_t heads, int32_t head_dim, void* stream) {
+  if (int rc = device_check()) return rc;
+  if (batch <= 0 || n <= 0) return MLA_OK;
+  if (heads <= 0 || head_dim <= 0 || (head_dim & 15)) return set_error(MLA_ERR_ARG, "rope_cache: head_dim must be a multiple of 16");
+  if (prefix < 0) return set_error(MLA_ERR_ARG, "rope_cache: negative prefix length");
+  const int64_t total = int64_t(batch) * n * heads * (head_dim / 16);
+  const int grid = int((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  rope_cache_kernel<<<grid, 256, 0, S_(stream)>>>((__nv_bfloat16*)qkv, (__nv_bfloat16*)cache, (const __nv_bfloat16*)cos_t,
+                                                  (const __nv_bfloat16*)sin_t, batch, n, prefix, heads, head_dim);
+  MLA_CHECK_LAUNCH("rope_cache");
   return MLA_OK;
 }

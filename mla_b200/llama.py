@@ -293,15 +293,14 @@ class LlamaDecoderLayer(nn.Module):
         wqkv, wo, wgu, wd, l1, l2 = self.compute_weights()
         h, H = self.hidden_size, self.heads
         D = h // H
-        n1 = ops.rmsnorm_fwd(x, l1, self.eps)
-        qkv = ops.gemv(n1, wqkv)
-        ops.rope_(qkv, 0, 2 * H, D, n, cos, sin)
-        cache.view(B, P + n, 2 * h)[:, P:].copy_(qkv.view(B, n, 3 * h)[:, :, h:])
+        # 6 launches: RMSNorm and SwiGLU ride in the prologues of the skinny GEMMs (ops.gemv), RoPE + cache append
+        # are one kernel
+        qkv = ops.gemv(x, wqkv, norm=(l1, self.eps))
+        ops.rope_cache(qkv, cache, cos, sin, B, n, P, H, D)
         ctx = ops.decode_attn(qkv, cache, B, H, n, P + n, D)
         x_mid = ops.gemv(ctx, wo, residual=x)
-        n2 = ops.rmsnorm_fwd(x_mid, l2, self.eps)
-        act = ops.swiglu_fwd(ops.gemv(n2, wgu))
-        return ops.gemv(act, wd, residual=x_mid)
+        gu = ops.gemv(x_mid, wgu, norm=(l2, self.eps))
+        return ops.gemv(gu, wd, residual=x_mid, swiglu=True)
 
     def _mlp_half_no_down(self, x_mid: torch.Tensor):
         _, _, wgu, _, _, l2 = self.compute_weights()

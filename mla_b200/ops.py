@@ -556,28 +556,57 @@ class CrossEntropyFn(torch.autograd.Function):
 
 # ---------------------------------------------------------------------------------------------- inference (decode)
 def gemv(x: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = None,
-         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, norm: Optional[tuple] = None, swiglu: bool = False) -> torch.Tensor:
     """Skinny nn.Linear for a handful of rows (HBM-bound weight streaming, csrc/decode.cu): x bf16 [m,k], w bf16 [n,k]
-    -> bf16 [m,n] (+ residual).  Falls through to the tcgen05 GEMM above 64 rows."""
+    -> bf16 [m,n] (+ residual).  Optional prologues on the activations, fused for m <= 4: norm = (ln_weight bf16 [k],
+    eps) applies LlamaRMSNorm first; swiglu=True takes x = [gate | up] bf16 [m, 2k].  Above 4 rows the prologue runs
+    as its own kernel; above 64 rows this is the tcgen05 GEMM."""
     _req(x, torch.bfloat16, "x")
     _req(w, torch.bfloat16, "w")
-    m, k = x.shape
-    n = w.shape[0]
-    if w.shape[1] != k:
-        raise _lib.MlaError(f"gemv: contraction mismatch {k} vs {w.shape[1]}")
+    m = x.shape[0]
+    n, k = w.shape
+    if x.shape[1] != (2 * k if swiglu else k):
+        raise _lib.MlaError(f"gemv: contraction mismatch {x.shape[1]} vs {k}")
+    fused = m <= 4 and k <= 12288
+    if not fused:
+        if norm is not None:
+            x, norm = rmsnorm_fwd(x, norm[0], norm[1]), None
+        if swiglu:
+            x, swiglu = swiglu_fwd(x.contiguous()), False
     if m > 64:
         return gemm(x, w, residual=residual, out=out)
-    ldx, ldw = _rowmajor_2d(x, "x"), _rowmajor_2d(w, "w")
     if out is None:
         out = torch.empty((m, n), dtype=torch.bfloat16, device=x.device)
-    ldr = 0
+    a = _lib.GemvArgs()
+    a.x, a.w, a.out = x.data_ptr(), w.data_ptr(), out.data_ptr()
+    a.m, a.n, a.k = m, n, k
+    a.ldx, a.ldw, a.ldo = _rowmajor_2d(x, "x"), _rowmajor_2d(w, "w"), _rowmajor_2d(out, "out")
     if residual is not None:
         _req(residual, torch.bfloat16, "residual")
-        ldr = _rowmajor_2d(residual, "residual")
-    check(_lib.lib().mla_gemv_bf16(_p(x), _p(w), _p(out), _p(residual), C.c_int32(m), C.c_int32(n), C.c_int32(k),
-                                   C.c_int64(ldx), C.c_int64(ldw), C.c_int64(_rowmajor_2d(out, "out")), C.c_int64(ldr),
-                                   _stream()))
+        a.residual, a.ldr = residual.data_ptr(), _rowmajor_2d(residual, "residual")
+    if norm is not None:
+        _req(norm[0], torch.bfloat16, "ln_weight")
+        a.prologue, a.ln_weight, a.eps = 1, norm[0].data_ptr(), float(norm[1])
+    elif swiglu:
+        a.prologue = 2
+    check(_lib.lib().mla_gemv_fused(C.byref(a), _stream()))
     return out
+
+
+def rope_cache(qkv: torch.Tensor, cache: torch.Tensor, cos_t: torch.Tensor, sin_t: torch.Tensor, B: int, n: int, P: int,
+               H: int, D: int) -> None:
+    """RoPE on the q and k of the n new rows per sample of qkv [B*n, 3*H*D] (q in place, k into the cache) + v copy;
+    cache bf16 [B*(P+n), 2*H*D], cos/sin = table rows P..P+n-1."""
+    _req(qkv, torch.bfloat16, "qkv")
+    _req(cache, torch.bfloat16, "cache")
+    if tuple(qkv.shape) != (B * n, 3 * H * D) or not qkv.is_contiguous():
+        raise _lib.MlaError(f"rope_cache: qkv must be contiguous [{B * n}, {3 * H * D}]")
+    if tuple(cache.shape) != (B * (P + n), 2 * H * D) or not cache.is_contiguous():
+        raise _lib.MlaError(f"rope_cache: cache must be contiguous [{B * (P + n)}, {2 * H * D}]")
+    if tuple(cos_t.shape) != (n, D // 2) or not (cos_t.is_contiguous() and sin_t.is_contiguous()):
+        raise _lib.MlaError("rope_cache: cos/sin must be contiguous [n, D/2]")
+    check(_lib.lib().mla_rope_cache(_p(qkv), _p(cache), _p(cos_t), _p(sin_t), C.c_int32(B), C.c_int32(n), C.c_int32(P),
+                                    C.c_int32(H), C.c_int32(D), _stream()))
 
 
 def decode_attn(q: torch.Tensor, kv: torch.Tensor, B: int, H: int, Lq: int, Lk: int, D: int) -> torch.Tensor:

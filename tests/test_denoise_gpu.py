@@ -19,12 +19,12 @@ def _bf(x):
     return x.to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("m", [1, 2, 17, 34])
+@pytest.mark.parametrize("m", [1, 2, 3, 4, 8, 17, 34])
 @pytest.mark.parametrize("residual", [False, True])
 def test_gemv_kernel(cuda_lib, m, residual):
     from mla_b200 import ops
     torch.manual_seed(m)
-    for n, k in ((1536, 512), (384, 1376)):
+    for n, k in ((1536, 512), (384, 1376), (1027, 4096), (130, 11008)):
         x = _bf(torch.randn(m, k, device="cuda"))
         w = _bf(torch.randn(n, k, device="cuda") * k ** -0.5)
         r = _bf(torch.randn(m, n, device="cuda")) if residual else None
@@ -38,6 +38,50 @@ def test_gemv_kernel(cuda_lib, m, residual):
     wide = _bf(torch.randn(m, 3 * 512, device="cuda"))
     w = _bf(torch.randn(256, 512, device="cuda") * 512 ** -0.5)
     assert rel_err(ops.gemv(wide[:, :512], w), wide[:, :512].float() @ w.float().t()) < 4e-3
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4, 6])
+def test_gemv_fused_prologues(cuda_lib, m):
+    """RMSNorm / SwiGLU applied while the activations are loaded == the separate kernels followed by the plain gemv
+    (m <= 4 runs fused, m = 6 exercises the unfused fallback of the same call)."""
+    from mla_b200 import ops
+    torch.manual_seed(10 + m)
+    for n, k in ((512, 128), (1024, 4096), (256, 11008)):
+        x = _bf(torch.randn(m, k, device="cuda") * 1.7)
+        lnw = _bf(1 + 0.1 * torch.randn(k, device="cuda"))
+        w = _bf(torch.randn(n, k, device="cuda") * k ** -0.5)
+        r = _bf(torch.randn(m, n, device="cuda"))
+        want = ops.gemv(ops.rmsnorm_fwd(x, lnw, 1e-5), w, residual=r)
+        got = ops.gemv(x, w, residual=r, norm=(lnw, 1e-5))
+        assert rel_err(got, want) < 3e-3, ("norm", n, k, rel_err(got, want))
+        gu = _bf(torch.randn(m, 2 * k, device="cuda"))
+        want = ops.gemv(ops.swiglu_fwd(gu), w, residual=r)
+        got = ops.gemv(gu, w, residual=r, swiglu=True)
+        assert rel_err(got, want) < 1e-6, ("swiglu", n, k, rel_err(got, want))
+        # and against fp32 math
+        ref = torch.nn.functional.silu(gu[:, :k].float()) * gu[:, k:].float()
+        assert rel_err(got, _bf(_bf(ref).float() @ w.float().t()).float() + r.float()) < 1e-2
+
+
+def test_rope_cache_kernel(cuda_lib):
+    """RoPE of the new rows + append to the K/V cache in one kernel == rope_ in place followed by the copy."""
+    from mla_b200 import ops
+    torch.manual_seed(4)
+    for D, H in ((32, 4), (128, 8)):
+        B, n, P = 2, 3, 11
+        h = H * D
+        qkv = _bf(torch.randn(B * n, 3 * h, device="cuda"))
+        cache = _bf(torch.randn(B * (P + n), 2 * h, device="cuda"))
+        pos = torch.arange(P + n, device="cuda").float()
+        inv = 1.0 / (10000 ** (torch.arange(0, D, 2, device="cuda").float() / D))
+        fr = pos[:, None] * inv[None]
+        cos, sin = _bf(fr.cos())[P:].contiguous(), _bf(fr.sin())[P:].contiguous()
+        q2, c2 = qkv.clone(), cache.clone()
+        ops.rope_(q2, 0, 2 * H, D, n, cos, sin)
+        c2.view(B, P + n, 2 * h)[:, P:] = q2.view(B, n, 3 * h)[:, :, h:]
+        ops.rope_cache(qkv, cache, cos, sin, B, n, P, H, D)
+        assert torch.equal(qkv[:, :h], q2[:, :h])            # q rotated in place
+        assert torch.equal(cache, c2)                        # k rotated into the cache, v copied, prefix untouched
 
 
 @pytest.mark.parametrize("D", [32, 128])
