@@ -297,7 +297,7 @@ int mla_diag_block_sum(const void* x, void* out, int32_t m, int32_t n, int32_t p
 /* ---- inference denoise loop (MLA.predict_action_diff, models/mla/model_mla.py:592-775) -----------------------------
  * The decoder prefix (everything in front of [t | x_0..x_T]) runs once on the training-path kernels; its post-RoPE K/V
  * stay in the per-layer q|k|v buffers and each DDIM step runs only the suffix rows.
- * gemv_bf16: skinny nn.Linear for m <= 64 rows (HBM-bound weight streaming): out[m,n] = bf16(bf16(x w^T) + residual),
+ * gemv_bf16: skinny nn.Linear for m <= 16 rows (HBM-bound weight streaming): out[m,n] = bf16(bf16(x w^T) + residual),
  *   x bf16 [m,k] (pitch ldx), w bf16 [n,k] (pitch ldw), residual optional; k and pitches multiples of 8.
  * decode_attn: the last len_q positions of a length-len_k sequence attend to the cached keys with the bottom-right
  *   aligned causal mask of flash-attn (modeling_llama.py:540-557): q row (b,i) at q + (b*len_q+i)*ldq + h*d, K/V row
@@ -307,8 +307,8 @@ int mla_diag_block_sum(const void* x, void* out, int32_t m, int32_t n, int32_t p
  *   sqrt(1/ac_t), sqrt(1/ac_t - 1), sqrt(ac_prev), sqrt(1 - ac_prev).  Bit-exact with the reference's fp32 op order. */
 int mla_gemv_bf16(const void* x, const void* w, void* out, const void* residual, int32_t m, int32_t n, int32_t k,
                   int64_t ldx, int64_t ldw, int64_t ldo, int64_t ldr, void* stream);
-/* gemv_fused: the same skinny linear with an optional prologue applied to the activations as they are loaded (m <= 4,
- * k <= 12288): prologue 1 = LlamaRMSNorm (modeling_llama.py:85-90) with ln_weight bf16 [k] and eps; prologue 2 = SwiGLU
+/* gemv_fused: the same skinny linear with an optional prologue applied to the activations as they are loaded (m <= 4
+ * with k <= 4096, or m <= 2 with k <= 12288): prologue 1 = LlamaRMSNorm (modeling_llama.py:85-90) with ln_weight bf16 [k] and eps; prologue 2 = SwiGLU
  * of LlamaMLP (:240), x = [gate | up] bf16 [m, 2k].  prologue 0 = mla_gemv_bf16. */
 typedef struct mla_gemv_args {
   const void *x, *w;
@@ -320,6 +320,9 @@ typedef struct mla_gemv_args {
   float eps;
 } mla_gemv_args;
 int mla_gemv_fused(const mla_gemv_args* a, void* stream);
+/* gemv launches carry programmaticStreamSerialization (their weight prefetch overlaps the previous kernel's tail; the
+ * consumers griddepcontrol.wait before touching activations).  0 turns it off (env MLA_DECODE_PDL=0 does the same). */
+int mla_decode_set_pdl(int32_t on);
 /* rope_cache: the n new rows per sample of a packed q|k|v projection bf16 [batch*n, 3*heads*head_dim] at positions
  * prefix..prefix+n-1: RoPE (modeling_llama.py:184-208) on q in place and on k into cache row (b*(prefix+n) + prefix + i),
  * v copied beside it; cache bf16 [batch*(prefix+n), 2*heads*head_dim] = k | v; cos/sin bf16 [n, head_dim/2]. */

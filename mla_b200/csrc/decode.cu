@@ -11,6 +11,8 @@
 //                           flash-attn / modeling_llama.py:540-557), keys split over the warps of a CTA, online softmax
 //   * ddim_step_kernel    — x_{t-1} of ddim_sample with eta = 0 (gaussian_diffusion.py:342-352,:522-571), in the
 //                           reference's fp32 op order (no FMA contraction) so the update is bit-exact.
+#include <cstdlib>
+
 #include "mla_internal.cuh"
 #include "ptx.cuh"
 
@@ -38,20 +40,25 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 //
 // Pure weight streaming, organised the way the DMA engine likes it: ONE producer thread per CTA issues a
 // cp.async.bulk (TMA, no tensor map) per weight row — 8-22 KB contiguous — into a multi-stage shared-memory ring
-// guarded by full/empty mbarriers; 16 consumer warps take the dot products from shared memory.  One persistent CTA per
-// SM owns ~190 KB of ring, so ~150 KB per SM is always in flight.  A slot holds RPI consecutive weight rows; per slot
-// the consumers do one warp-shuffle + one named-barrier reduction.
+// guarded by full/empty mbarriers; 8 consumer warps take the dot products from shared memory.  One persistent CTA per
+// SM owns a ~100 KB ring, 66-80 KB of it in flight.  A slot holds RPI consecutive weight rows; per slot the consumers
+// do one warp-shuffle + one named-barrier reduction.
+//   Launch overlap (programmatic dependent launch): a decode step is ~200 dependent kernels of 5-30 us, so launch gaps
+//   and ramp-up cost as much as the streaming itself.  The weights do not depend on the previous kernel — only the
+//   activations do — so every gemv is launched with programmaticStreamSerialization: its CTAs become resident next
+//   to the previous kernel's (the ring is sized for two CTAs per SM), the producer starts streaming immediately, and
+//   only the consumers execute griddepcontrol.wait before they touch the activations.
 //   fast path (M <= 4): the activations live in REGISTERS for the whole kernel (thread t always multiplies the same
 //     k-chunks), optionally produced on the fly by a fused prologue:
 //       PRO_RMSNORM  x' = bf16(g * bf16(x * rstd))            (LlamaRMSNorm, modeling_llama.py:85-90)
 //       PRO_SWIGLU   x' = bf16(bf16(silu(gate)) * up), x = [gate | up]   (LlamaMLP, :240)
 //   general path (M <= 64): 8 activation rows per pass from L1/L2, several passes over the SAME shared-memory slot —
 //     the weights still cross HBM exactly once.
-constexpr int GV_CWARPS = 16;
+constexpr int GV_CWARPS = 8;
 constexpr int GV_CONSUMERS = GV_CWARPS * 32;
 constexpr int GV_THREADS = GV_CONSUMERS + 32;
 constexpr int GV_MAX_STAGES = 8;
-constexpr int GV_RING_BYTES = 192 * 1024;
+constexpr int GV_RING_BYTES = 100 * 1024;      // two CTAs (of consecutive launches, see PDL below) fit one SM
 enum { GV_PRO_NONE = 0, GV_PRO_RMSNORM = 1, GV_PRO_SWIGLU = 2 };
 
 struct GemvParams {
@@ -70,6 +77,9 @@ __device__ __forceinline__ void bulk_load_row(void* smem_dst, const void* gsrc, 
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// programmatic dependent launch: no-ops unless the launch carried the attribute / has a programmatic dependent
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void consumers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(GV_CONSUMERS) : "memory"); }
 __device__ __forceinline__ uint4 pack8f(const float* f) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
@@ -86,13 +96,14 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float acc)
 // MB: activation rows held per thread (fast path: M <= MB, registers) — or 8 in the general path (GEN = 1).
 // CPT: k-chunks (8 bf16) per consumer thread (fast path).  RPI: weight rows per ring slot.
 template <int MB, int CPT, int RPI, int PRO, int GEN>
-__global__ void __launch_bounds__(GV_THREADS, 1) gemv_ring_kernel(GemvParams p) {
+__global__ void __launch_bounds__(GV_THREADS, 2) gemv_ring_kernel(GemvParams p) {
   extern __shared__ uint8_t gv_smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gv_smem_raw) + 127) & ~uintptr_t(127));
   __shared__ uint64_t full_bar[GV_MAX_STAGES], empty_bar[GV_MAX_STAGES];
   __shared__ float partial[2][GV_CWARPS][RPI * MB];
   __shared__ float red_ss[GV_CWARPS][MB];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();       // the next kernel may become resident and prefetch ITS weights while we run
   const int chunks = p.K >> 3;
   const uint32_t row_bytes = uint32_t(p.K) * 2u;
   const uint32_t slot_bytes = p.pitch * RPI;
@@ -126,6 +137,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_ring_kernel(GemvParams p) 
   }
 
   // ===================== consumers =====================
+  pdl_wait();                    // activations / residual / output buffers belong to the kernels before us
   uint4 xr[GEN ? 1 : MB][GEN ? 1 : CPT];
   if (!GEN) {
     float ss[MB];
@@ -289,6 +301,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(
     const __nv_bfloat16* __restrict__ v, int64_t ldkv, __nv_bfloat16* __restrict__ o, int64_t ldo, int H, int Lq,
     int Lk, float scale) {
   constexpr int D = 32 * EPL;
+  pdl_launch_dependents();       // the output projection's gemv may start prefetching its weights
   __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];
   __shared__ float s_acc[DEC_WARPS][D];
   const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -416,6 +429,19 @@ __global__ void ddim_step_kernel(const float* __restrict__ x, const EpsT* __rest
 using namespace mla;
 #define S_(x) ((cudaStream_t)(x))
 
+static int g_gemv_pdl = -1;
+static bool gemv_pdl_enabled() {
+  if (g_gemv_pdl < 0) {
+    const char* e = getenv("MLA_DECODE_PDL");
+    g_gemv_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_gemv_pdl == 1;
+}
+extern "C" int mla_decode_set_pdl(int32_t on) {
+  g_gemv_pdl = on ? 1 : 0;
+  return MLA_OK;
+}
+
 template <int MB, int CPT, int RPI, int PRO, int GEN>
 static int launch_gemv(const GemvParams& p, int grid, size_t smem, cudaStream_t stream) {
   auto kern = gemv_ring_kernel<MB, CPT, RPI, PRO, GEN>;
@@ -425,21 +451,31 @@ static int launch_gemv(const GemvParams& p, int grid, size_t smem, cudaStream_t 
     if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "cudaFuncSetAttribute(gemv smem): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  kern<<<grid, GV_THREADS, smem, stream>>>(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GV_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = gemv_pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "gemv launch: %s", cudaGetErrorString(e));
   return MLA_OK;
 }
 
 template <int PRO>
 static int dispatch_gemv_fast(const GemvParams& p, int mb, bool small_k, int grid, size_t smem, cudaStream_t st) {
-  // small_k: K <= 4096 -> one k-chunk per thread, 4 weight rows per slot; else 3 chunks per thread, 2 rows per slot
+  // small_k: K <= 4096 -> two k-chunks per thread, 2 weight rows per slot; else up to 6 chunks per thread, 1 row per slot
   if (small_k) {
-    if (mb == 1) return launch_gemv<1, 1, 4, PRO, 0>(p, grid, smem, st);
-    if (mb == 2) return launch_gemv<2, 1, 4, PRO, 0>(p, grid, smem, st);
-    return launch_gemv<4, 1, 4, PRO, 0>(p, grid, smem, st);
+    if (mb == 1) return launch_gemv<1, 2, 2, PRO, 0>(p, grid, smem, st);
+    if (mb == 2) return launch_gemv<2, 2, 2, PRO, 0>(p, grid, smem, st);
+    return launch_gemv<4, 2, 2, PRO, 0>(p, grid, smem, st);
   }
-  if (mb == 1) return launch_gemv<1, 3, 2, PRO, 0>(p, grid, smem, st);
-  if (mb == 2) return launch_gemv<2, 3, 2, PRO, 0>(p, grid, smem, st);
-  return launch_gemv<4, 3, 2, PRO, 0>(p, grid, smem, st);
+  if (mb == 1) return launch_gemv<1, 6, 1, PRO, 0>(p, grid, smem, st);
+  return launch_gemv<2, 6, 1, PRO, 0>(p, grid, smem, st);
 }
 
 extern "C" int mla_gemv_fused(const mla_gemv_args* a, void* stream) {
@@ -451,20 +487,21 @@ extern "C" int mla_gemv_fused(const mla_gemv_args* a, void* stream) {
     return set_error(MLA_ERR_ARG, "gemv: k and the row pitches of x and w must be multiples of 8 (k=%d)", K);
   if ((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->w)) & 15)
     return set_error(MLA_ERR_ARG, "gemv: x and w must be 16-byte aligned");
-  if (M > 64) return set_error(MLA_ERR_ARG, "gemv: m=%d rows is a GEMM, use mla_gemm_bf16", M);
+  if (M > 16) return set_error(MLA_ERR_ARG, "gemv: m=%d rows is a GEMM, use mla_gemm_bf16", M);
   if (a->prologue < GV_PRO_NONE || a->prologue > GV_PRO_SWIGLU) return set_error(MLA_ERR_ARG, "gemv: unknown prologue");
   if (a->prologue == GV_PRO_RMSNORM && (!a->ln_weight || (reinterpret_cast<uintptr_t>(a->ln_weight) & 15)))
     return set_error(MLA_ERR_ARG, "gemv: the RMSNorm prologue needs a 16-byte aligned weight vector");
-  const bool small_k = K <= GV_CONSUMERS * 8;
-  const bool fast = M <= 4 && K <= GV_CONSUMERS * 8 * 3;
+  const bool small_k = K <= GV_CONSUMERS * 8 * 2;                       // 4096
+  const bool fast = (M <= 4 && small_k) || (M <= 2 && K <= GV_CONSUMERS * 8 * 6);   // activations fit the registers
   if (a->prologue != GV_PRO_NONE && !fast)
-    return set_error(MLA_ERR_ARG, "gemv: fused prologues need m <= 4 and k <= %d", GV_CONSUMERS * 8 * 3);
+    return set_error(MLA_ERR_ARG, "gemv: fused prologues need m <= 4 with k <= %d, or m <= 2 with k <= %d",
+                     GV_CONSUMERS * 8 * 2, GV_CONSUMERS * 8 * 6);
   GemvParams p;
   p.x = (const __nv_bfloat16*)a->x; p.w = (const __nv_bfloat16*)a->w; p.res = (const __nv_bfloat16*)a->residual;
   p.ln_w = (const __nv_bfloat16*)a->ln_weight; p.out = (__nv_bfloat16*)a->out;
   p.M = M; p.N = N; p.K = K; p.ldx = a->ldx; p.ldw = a->ldw; p.ldo = a->ldo; p.ldr = a->ldr; p.eps = a->eps;
   p.pitch = (uint32_t(K) * 2u + 127u) & ~127u;
-  const int rpi = small_k ? 4 : 2;
+  const int rpi = small_k ? 2 : 1;
   const size_t slot = size_t(p.pitch) * rpi;
   int stages = int(GV_RING_BYTES / slot);
   if (stages < 2) return set_error(MLA_ERR_ARG, "gemv: k=%d does not fit the shared-memory ring, use mla_gemm_bf16", K);
@@ -480,8 +517,8 @@ extern "C" int mla_gemv_fused(const mla_gemv_args* a, void* stream) {
     else if (a->prologue == GV_PRO_SWIGLU) rc = dispatch_gemv_fast<GV_PRO_SWIGLU>(p, mb, small_k, grid, smem, st);
     else rc = dispatch_gemv_fast<GV_PRO_NONE>(p, mb, small_k, grid, smem, st);
   } else {
-    rc = small_k ? launch_gemv<8, 1, 4, GV_PRO_NONE, 1>(p, grid, smem, st)
-                 : launch_gemv<8, 1, 2, GV_PRO_NONE, 1>(p, grid, smem, st);
+    rc = small_k ? launch_gemv<8, 1, 2, GV_PRO_NONE, 1>(p, grid, smem, st)
+                 : launch_gemv<8, 1, 1, GV_PRO_NONE, 1>(p, grid, smem, st);
   }
   if (rc) return rc;
   MLA_CHECK_LAUNCH("gemv_bf16");

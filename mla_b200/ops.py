@@ -559,22 +559,22 @@ def gemv(x: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = No
          out: Optional[torch.Tensor] = None, norm: Optional[tuple] = None, swiglu: bool = False) -> torch.Tensor:
     """Skinny nn.Linear for a handful of rows (HBM-bound weight streaming, csrc/decode.cu): x bf16 [m,k], w bf16 [n,k]
     -> bf16 [m,n] (+ residual).  Optional prologues on the activations, fused for m <= 4: norm = (ln_weight bf16 [k],
-    eps) applies LlamaRMSNorm first; swiglu=True takes x = [gate | up] bf16 [m, 2k].  Above 4 rows the prologue runs
-    as its own kernel; above 64 rows this is the tcgen05 GEMM."""
+    eps) applies LlamaRMSNorm first; swiglu=True takes x = [gate | up] bf16 [m, 2k].  Otherwise the prologue
+    runs as its own kernel; above 16 rows this is the tcgen05 GEMM."""
     _req(x, torch.bfloat16, "x")
     _req(w, torch.bfloat16, "w")
     m = x.shape[0]
     n, k = w.shape
     if x.shape[1] != (2 * k if swiglu else k):
         raise _lib.MlaError(f"gemv: contraction mismatch {x.shape[1]} vs {k}")
-    fused = m <= 4 and k <= 12288
+    fused = (m <= 4 and k <= 4096) or (m <= 2 and k <= 12288)      # activations fit the kernel's registers
     if not fused:
         if norm is not None:
             x, norm = rmsnorm_fwd(x, norm[0], norm[1]), None
         if swiglu:
             x, swiglu = swiglu_fwd(x.contiguous()), False
-    if m > 64:
-        return gemm(x, w, residual=residual, out=out)
+    if m > 16:          # SIMT dot products stop paying: the tensor-core GEMM streams the same weights
+        return gemm(x.contiguous(), w, residual=residual, out=out)
     if out is None:
         out = torch.empty((m, n), dtype=torch.bfloat16, device=x.device)
     a = _lib.GemvArgs()

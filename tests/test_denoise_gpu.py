@@ -19,7 +19,7 @@ def _bf(x):
     return x.to(torch.bfloat16)
 
 
-@pytest.mark.parametrize("m", [1, 2, 3, 4, 8, 17, 34])
+@pytest.mark.parametrize("m", [1, 2, 3, 4, 8, 16, 17, 34])
 @pytest.mark.parametrize("residual", [False, True])
 def test_gemv_kernel(cuda_lib, m, residual):
     from mla_b200 import ops
