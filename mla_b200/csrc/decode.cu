@@ -40,25 +40,26 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 //
 // Pure weight streaming, organised the way the DMA engine likes it: ONE producer thread per CTA issues a
 // cp.async.bulk (TMA, no tensor map) per weight row — 8-22 KB contiguous — into a multi-stage shared-memory ring
-// guarded by full/empty mbarriers; 8 consumer warps take the dot products from shared memory.  One persistent CTA per
-// SM owns a ~100 KB ring, 66-80 KB of it in flight.  A slot holds RPI consecutive weight rows; per slot the consumers
-// do one warp-shuffle + one named-barrier reduction.
-//   Launch overlap (programmatic dependent launch): a decode step is ~200 dependent kernels of 5-30 us, so launch gaps
-//   and ramp-up cost as much as the streaming itself.  The weights do not depend on the previous kernel — only the
-//   activations do — so every gemv is launched with programmaticStreamSerialization: its CTAs become resident next
-//   to the previous kernel's (the ring is sized for two CTAs per SM), the producer starts streaming immediately, and
-//   only the consumers execute griddepcontrol.wait before they touch the activations.
+// guarded by full/empty mbarriers; 16 consumer warps take the dot products from shared memory.  One persistent CTA per
+// SM owns ~190 KB of ring, so ~150 KB per SM is always in flight.  A slot holds RPI consecutive weight rows; per slot
+// the consumers do one warp-shuffle + one named-barrier reduction.
+//   Measured alternatives (profiles/r01_denoise_T0_v*.json, ms per decode step of 12.95 GB at Llama-2-7B size):
+//   warp-per-row direct loads 6.74; this ring with 16 consumer warps / 192 KB 4.33; 8 consumer warps / 100 KB ring
+//   (two CTAs of consecutive launches per SM) 5.72, and with programmatic dependent launch on top — the next kernel's
+//   producer prefetching its weights while this one drains, consumers behind griddepcontrol.wait — 6.65.  The
+//   consumer side (unpack + FMA from shared memory) is what limits, so the wide CTA stays and PDL is an off-by-default
+//   switch (MLA_DECODE_PDL=1).
 //   fast path (M <= 4): the activations live in REGISTERS for the whole kernel (thread t always multiplies the same
 //     k-chunks), optionally produced on the fly by a fused prologue:
 //       PRO_RMSNORM  x' = bf16(g * bf16(x * rstd))            (LlamaRMSNorm, modeling_llama.py:85-90)
 //       PRO_SWIGLU   x' = bf16(bf16(silu(gate)) * up), x = [gate | up]   (LlamaMLP, :240)
 //   general path (M <= 64): 8 activation rows per pass from L1/L2, several passes over the SAME shared-memory slot —
 //     the weights still cross HBM exactly once.
-constexpr int GV_CWARPS = 8;
+constexpr int GV_CWARPS = 16;
 constexpr int GV_CONSUMERS = GV_CWARPS * 32;
 constexpr int GV_THREADS = GV_CONSUMERS + 32;
 constexpr int GV_MAX_STAGES = 8;
-constexpr int GV_RING_BYTES = 100 * 1024;      // two CTAs (of consecutive launches, see PDL below) fit one SM
+constexpr int GV_RING_BYTES = 192 * 1024;
 enum { GV_PRO_NONE = 0, GV_PRO_RMSNORM = 1, GV_PRO_SWIGLU = 2 };
 
 struct GemvParams {
@@ -96,7 +97,7 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float acc)
 // MB: activation rows held per thread (fast path: M <= MB, registers) — or 8 in the general path (GEN = 1).
 // CPT: k-chunks (8 bf16) per consumer thread (fast path).  RPI: weight rows per ring slot.
 template <int MB, int CPT, int RPI, int PRO, int GEN>
-__global__ void __launch_bounds__(GV_THREADS, 2) gemv_ring_kernel(GemvParams p) {
+__global__ void __launch_bounds__(GV_THREADS, 1) gemv_ring_kernel(GemvParams p) {
   extern __shared__ uint8_t gv_smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gv_smem_raw) + 127) & ~uintptr_t(127));
   __shared__ uint64_t full_bar[GV_MAX_STAGES], empty_bar[GV_MAX_STAGES];
@@ -138,8 +139,9 @@ __global__ void __launch_bounds__(GV_THREADS, 2) gemv_ring_kernel(GemvParams p) 
 
   // ===================== consumers =====================
   pdl_wait();                    // activations / residual / output buffers belong to the kernels before us
-  uint4 xr[GEN ? 1 : MB][GEN ? 1 : CPT];
+  float xf[GEN ? 1 : MB][GEN ? 1 : CPT][8];      // activations, unpacked once: thread t always meets the same k-chunks
   if (!GEN) {
+    uint4 xr[MB][CPT];
     float ss[MB];
 #pragma unroll
     for (int r = 0; r < MB; ++r) ss[r] = 0.f;
@@ -197,6 +199,10 @@ __global__ void __launch_bounds__(GV_THREADS, 2) gemv_ring_kernel(GemvParams p) 
         }
       }
     }
+#pragma unroll
+    for (int r = 0; r < MB; ++r)
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) unpack8(xr[r][j], xf[r][j]);
   }
 
   int it = 0, pb = 0;
@@ -221,9 +227,12 @@ __global__ void __launch_bounds__(GV_THREADS, 2) gemv_ring_kernel(GemvParams p) 
           if (c < chunks) {
 #pragma unroll
             for (int rr = 0; rr < RPI; ++rr) {
-              const uint4 wv = *reinterpret_cast<const uint4*>(slot + size_t(rr) * p.pitch + 16 * c);
+              float wf[8];
+              unpack8(*reinterpret_cast<const uint4*>(slot + size_t(rr) * p.pitch + 16 * c), wf);
 #pragma unroll
-              for (int r = 0; r < MB; ++r) acc[rr][r] = dot8(wv, xr[r][j], acc[rr][r]);
+              for (int r = 0; r < MB; ++r)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[rr][r] = fmaf(wf[e], xf[r][j][e], acc[rr][r]);
             }
           }
         }
@@ -433,7 +442,7 @@ static int g_gemv_pdl = -1;
 static bool gemv_pdl_enabled() {
   if (g_gemv_pdl < 0) {
     const char* e = getenv("MLA_DECODE_PDL");
-    g_gemv_pdl = (e && e[0] == '0') ? 0 : 1;
+    g_gemv_pdl = (e && e[0] == '1') ? 1 : 0;
   }
   return g_gemv_pdl == 1;
 }
@@ -468,14 +477,14 @@ static int launch_gemv(const GemvParams& p, int grid, size_t smem, cudaStream_t 
 
 template <int PRO>
 static int dispatch_gemv_fast(const GemvParams& p, int mb, bool small_k, int grid, size_t smem, cudaStream_t st) {
-  // small_k: K <= 4096 -> two k-chunks per thread, 2 weight rows per slot; else up to 6 chunks per thread, 1 row per slot
+  // small_k: K <= 4096 -> one k-chunk per thread, 4 weight rows per slot; else up to 3 chunks per thread, 2 rows per slot
   if (small_k) {
-    if (mb == 1) return launch_gemv<1, 2, 2, PRO, 0>(p, grid, smem, st);
-    if (mb == 2) return launch_gemv<2, 2, 2, PRO, 0>(p, grid, smem, st);
-    return launch_gemv<4, 2, 2, PRO, 0>(p, grid, smem, st);
+    if (mb == 1) return launch_gemv<1, 1, 4, PRO, 0>(p, grid, smem, st);
+    if (mb == 2) return launch_gemv<2, 1, 4, PRO, 0>(p, grid, smem, st);
+    return launch_gemv<4, 1, 4, PRO, 0>(p, grid, smem, st);
   }
-  if (mb == 1) return launch_gemv<1, 6, 1, PRO, 0>(p, grid, smem, st);
-  return launch_gemv<2, 6, 1, PRO, 0>(p, grid, smem, st);
+  if (mb == 1) return launch_gemv<1, 3, 2, PRO, 0>(p, grid, smem, st);
+  return launch_gemv<2, 3, 2, PRO, 0>(p, grid, smem, st);
 }
 
 extern "C" int mla_gemv_fused(const mla_gemv_args* a, void* stream) {
@@ -491,17 +500,17 @@ extern "C" int mla_gemv_fused(const mla_gemv_args* a, void* stream) {
   if (a->prologue < GV_PRO_NONE || a->prologue > GV_PRO_SWIGLU) return set_error(MLA_ERR_ARG, "gemv: unknown prologue");
   if (a->prologue == GV_PRO_RMSNORM && (!a->ln_weight || (reinterpret_cast<uintptr_t>(a->ln_weight) & 15)))
     return set_error(MLA_ERR_ARG, "gemv: the RMSNorm prologue needs a 16-byte aligned weight vector");
-  const bool small_k = K <= GV_CONSUMERS * 8 * 2;                       // 4096
-  const bool fast = (M <= 4 && small_k) || (M <= 2 && K <= GV_CONSUMERS * 8 * 6);   // activations fit the registers
+  const bool small_k = K <= GV_CONSUMERS * 8;                           // 4096
+  const bool fast = (M <= 4 && small_k) || (M <= 2 && K <= GV_CONSUMERS * 8 * 3);   // activations fit the registers
   if (a->prologue != GV_PRO_NONE && !fast)
     return set_error(MLA_ERR_ARG, "gemv: fused prologues need m <= 4 with k <= %d, or m <= 2 with k <= %d",
-                     GV_CONSUMERS * 8 * 2, GV_CONSUMERS * 8 * 6);
+                     GV_CONSUMERS * 8, GV_CONSUMERS * 8 * 3);
   GemvParams p;
   p.x = (const __nv_bfloat16*)a->x; p.w = (const __nv_bfloat16*)a->w; p.res = (const __nv_bfloat16*)a->residual;
   p.ln_w = (const __nv_bfloat16*)a->ln_weight; p.out = (__nv_bfloat16*)a->out;
   p.M = M; p.N = N; p.K = K; p.ldx = a->ldx; p.ldw = a->ldw; p.ldo = a->ldo; p.ldr = a->ldr; p.eps = a->eps;
   p.pitch = (uint32_t(K) * 2u + 127u) & ~127u;
-  const int rpi = small_k ? 2 : 1;
+  const int rpi = small_k ? 4 : 2;
   const size_t slot = size_t(p.pitch) * rpi;
   int stages = int(GV_RING_BYTES / slot);
   if (stages < 2) return set_error(MLA_ERR_ARG, "gemv: k=%d does not fit the shared-memory ring, use mla_gemm_bf16", K);
@@ -517,8 +526,8 @@ extern "C" int mla_gemv_fused(const mla_gemv_args* a, void* stream) {
     else if (a->prologue == GV_PRO_SWIGLU) rc = dispatch_gemv_fast<GV_PRO_SWIGLU>(p, mb, small_k, grid, smem, st);
     else rc = dispatch_gemv_fast<GV_PRO_NONE>(p, mb, small_k, grid, smem, st);
   } else {
-    rc = small_k ? launch_gemv<8, 1, 2, GV_PRO_NONE, 1>(p, grid, smem, st)
-                 : launch_gemv<8, 1, 1, GV_PRO_NONE, 1>(p, grid, smem, st);
+    rc = small_k ? launch_gemv<8, 1, 4, GV_PRO_NONE, 1>(p, grid, smem, st)
+                 : launch_gemv<8, 1, 2, GV_PRO_NONE, 1>(p, grid, smem, st);
   }
   if (rc) return rc;
   MLA_CHECK_LAUNCH("gemv_bf16");
