@@ -96,7 +96,7 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float acc)
 
 // MB: activation rows held per thread (fast path: M <= MB, registers) — or 8 in the general path (GEN = 1).
 // CPT: k-chunks (8 bf16) per consumer thread (fast path).  RPI: weight rows per ring slot.
-template <int MB, int CPT, int RPI, int PRO, int GEN>
+template <int MB, int CPT, int RPI, int PRO, int GEN, int XF>
 __global__ void __launch_bounds__(GV_THREADS, 1) gemv_ring_kernel(GemvParams p) {
   extern __shared__ uint8_t gv_smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gv_smem_raw) + 127) & ~uintptr_t(127));
@@ -139,9 +139,11 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_ring_kernel(GemvParams p) 
 
   // ===================== consumers =====================
   pdl_wait();                    // activations / residual / output buffers belong to the kernels before us
-  float xf[GEN ? 1 : MB][GEN ? 1 : CPT][8];      // activations, unpacked once: thread t always meets the same k-chunks
+  // activations: thread t always meets the same k-chunks, so they stay in registers — packed bf16 (XF = 0, unpacked
+  // at every use) or unpacked once to fp32 (XF = 1)
+  float xf[(GEN || !XF) ? 1 : MB][(GEN || !XF) ? 1 : CPT][8];
+  uint4 xr[GEN ? 1 : MB][GEN ? 1 : CPT];
   if (!GEN) {
-    uint4 xr[MB][CPT];
     float ss[MB];
 #pragma unroll
     for (int r = 0; r < MB; ++r) ss[r] = 0.f;
@@ -199,10 +201,12 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_ring_kernel(GemvParams p) 
         }
       }
     }
+    if (XF) {
 #pragma unroll
-    for (int r = 0; r < MB; ++r)
+      for (int r = 0; r < MB; ++r)
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) unpack8(xr[r][j], xf[r][j]);
+        for (int j = 0; j < CPT; ++j) unpack8(xr[r][j], xf[XF ? r : 0][XF ? j : 0]);
+    }
   }
 
   int it = 0, pb = 0;
@@ -227,12 +231,18 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_ring_kernel(GemvParams p) 
           if (c < chunks) {
 #pragma unroll
             for (int rr = 0; rr < RPI; ++rr) {
-              float wf[8];
-              unpack8(*reinterpret_cast<const uint4*>(slot + size_t(rr) * p.pitch + 16 * c), wf);
+              const uint4 wv = *reinterpret_cast<const uint4*>(slot + size_t(rr) * p.pitch + 16 * c);
+              if (XF) {
+                float wf[8];
+                unpack8(wv, wf);
 #pragma unroll
-              for (int r = 0; r < MB; ++r)
+                for (int r = 0; r < MB; ++r)
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[rr][r] = fmaf(wf[e], xf[r][j][e], acc[rr][r]);
+                  for (int e = 0; e < 8; ++e) acc[rr][r] = fmaf(wf[e], xf[XF ? r : 0][XF ? j : 0][e], acc[rr][r]);
+              } else {
+#pragma unroll
+                for (int r = 0; r < MB; ++r) acc[rr][r] = dot8(wv, xr[r][j], acc[rr][r]);
+              }
             }
           }
         }
@@ -451,9 +461,9 @@ extern "C" int mla_decode_set_pdl(int32_t on) {
   return MLA_OK;
 }
 
-template <int MB, int CPT, int RPI, int PRO, int GEN>
-static int launch_gemv(const GemvParams& p, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = gemv_ring_kernel<MB, CPT, RPI, PRO, GEN>;
+template <int MB, int CPT, int RPI, int PRO, int GEN, int XF>
+static int launch_gemv_x(const GemvParams& p, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = gemv_ring_kernel<MB, CPT, RPI, PRO, GEN, XF>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GV_RING_BYTES + 128);
@@ -473,6 +483,17 @@ static int launch_gemv(const GemvParams& p, int grid, size_t smem, cudaStream_t 
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "gemv launch: %s", cudaGetErrorString(e));
   return MLA_OK;
+}
+
+static int g_gemv_xf32 = -1;
+template <int MB, int CPT, int RPI, int PRO, int GEN>
+static int launch_gemv(const GemvParams& p, int grid, size_t smem, cudaStream_t stream) {
+  if (g_gemv_xf32 < 0) {
+    const char* e = getenv("MLA_GEMV_XF32");
+    g_gemv_xf32 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!GEN && g_gemv_xf32) return launch_gemv_x<MB, CPT, RPI, PRO, GEN, 1>(p, grid, smem, stream);
+  return launch_gemv_x<MB, CPT, RPI, PRO, GEN, 0>(p, grid, smem, stream);
 }
 
 template <int PRO>

@@ -1,6 +1,6 @@
 """One decoder layer of the K/V-cached denoise step at Llama-2-7B size (2 suffix rows, 546-token prefix) inside a
 profiler range, for
-    ncu --set full --profile-from-start off --clock-control none -k regex:"gemv|decode_attn" python tools/ncu_decode.py
+    ncu --set full --profile-from-start off --clock-control none -k regex:"gemv|decode_attn|rope_cache" python tools/ncu_decode.py
 Eight distinct weight sets rotate so that no launch finds its weights in the 126 MB L2 (one layer = 405 MB)."""
 import os
 import sys
@@ -20,12 +20,20 @@ x = torch.randn(N, H, device=dev).to(bf)
 cache = torch.randn(P + N, 2 * H, device=dev).to(bf)
 
 
+lnw = torch.ones(H, device=dev).to(bf)
+inv = 1.0 / (10000 ** (torch.arange(0, H // HEADS, 2, device=dev).float() / (H // HEADS)))
+fr = torch.arange(P, P + N, device=dev).float()[:, None] * inv[None]
+cos, sin = fr.cos().to(bf).contiguous(), fr.sin().to(bf).contiguous()
+
+
 def layer(w):
-    qkv = ops.gemv(x, w["qkv"])
+    """Same launch sequence as LlamaDecoderLayer.decode (mla_b200/llama.py)."""
+    qkv = ops.gemv(x, w["qkv"], norm=(lnw, 1e-5))
+    ops.rope_cache(qkv, cache, cos, sin, 1, N, P, HEADS, H // HEADS)
     ctx = ops.decode_attn(qkv, cache, 1, HEADS, N, P + N, H // HEADS)
     mid = ops.gemv(ctx, w["o"], residual=x)
-    act = ops.swiglu_fwd(ops.gemv(mid, w["gu"]))
-    return ops.gemv(act, w["d"], residual=mid)
+    gu = ops.gemv(mid, w["gu"], norm=(lnw, 1e-5))
+    return ops.gemv(gu, w["d"], residual=mid, swiglu=True)
 
 
 for w in W:
