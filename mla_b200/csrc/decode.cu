@@ -94,6 +94,33 @@ __device__ __forceinline__ float dot8(const uint4& a, const uint4& b, float acc)
   return acc;
 }
 
+// Sum V per-lane values across the warp with V - 1 + (5 - log2 V) shuffles instead of 5 V: while more than one value
+// is left, the two halves of the warp exchange the half of the values the other one keeps.  On return lane l holds in
+// v[0] the total of value (l * V) >> 5 (for V >= 32: value l).
+template <int V>
+__device__ __forceinline__ void warp_reduce_many(float (&v)[V], int lane) {
+  static_assert(V >= 1 && V <= 32 && (V & (V - 1)) == 0, "V must be a power of two <= 32");
+  int cur = V;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    if (cur > 1) {
+      const int half = cur >> 1;
+      const bool hi = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < V / 2; ++i) {
+        if (i < half) {
+          const float send = hi ? v[i] : v[i + half];
+          const float keep = hi ? v[i + half] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      cur = half;
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+    }
+  }
+}
+
 // MB: activation rows held per thread (fast path: M <= MB, registers) — or 8 in the general path (GEN = 1).
 // CPT: k-chunks (8 bf16) per consumer thread (fast path).  RPI: weight rows per ring slot.
 template <int MB, int CPT, int RPI, int PRO, int GEN, int XF>
@@ -265,13 +292,17 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_ring_kernel(GemvParams p) 
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
       }
+      {
+        constexpr int V = RPI * MB;
+        float flat[V];
 #pragma unroll
-      for (int rr = 0; rr < RPI; ++rr)
+        for (int rr = 0; rr < RPI; ++rr)
 #pragma unroll
-        for (int r = 0; r < MB; ++r) {
-          const float t = d_wsum(acc[rr][r]);
-          if (lane == 0) partial[pb][warp][rr * MB + r] = t;
-        }
+          for (int r = 0; r < MB; ++r) flat[rr * MB + r] = acc[rr][r];
+        warp_reduce_many<V>(flat, lane);
+        constexpr int LPV = 32 / V;                       // lanes that end up holding the same value
+        if (lane % LPV == 0) partial[pb][warp][lane / LPV] = flat[0];
+      }
       consumers_sync();
       if (tid < RPI * MB) {
         const int rr = tid / MB, r = tid % MB;
@@ -312,8 +343,9 @@ __device__ __forceinline__ void ld_epl(const __nv_bfloat16* p, float* f) {
 // ---------------------------------------------------------------------------------------------- decode attention
 // q rows (b, i), i < Lq, are the LAST Lq positions of a length-Lk sequence whose K/V rows live at
 // k/v + (b*Lk + j)*ldkv + h*D.  Query i sees keys j <= Lk - Lq + i.  One CTA per (i, h, b); warp w takes keys
-// w, w+NW, ...; partial (max, sum, acc[D]) are merged through shared memory.  D = 32 * EPL.
-constexpr int DEC_WARPS = 8;
+// w, w+NW, ... (16 warps x 8 keys per pass cover 128 keys at once); partial (max, sum, acc[D]) are merged through
+// shared memory.  D = 32 * EPL.
+constexpr int DEC_WARPS = 16;
 template <int EPL>
 __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(
     const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k,
@@ -332,7 +364,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(
   for (int e = 0; e < EPL; ++e) { qf[e] = __bfloat162float(qr[e]) * scale; acc[e] = 0.f; }   // scale folded into q
   float m = -INFINITY, l = 0.f;
   const int64_t base = int64_t(b) * Lk * ldkv + int64_t(h) * D + lane * EPL;
-  constexpr int UN = 4;
+  constexpr int UN = 8;          // 16 independent loads per lane in flight: the kernel is DRAM-latency bound
   for (int j0 = warp; j0 < nkeys; j0 += DEC_WARPS * UN) {
     float s[UN], vf[UN][EPL];
 #pragma unroll
