@@ -332,6 +332,13 @@ int mla_rope_cache(void* qkv, void* cache, const void* cos_t, const void* sin_t,
 int mla_decode_attn(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* o, int64_t ldo,
                     int32_t batch, int32_t heads, int32_t len_q, int32_t len_k, int32_t head_dim, float scale,
                     void* stream);
+/* decode_attn_rope: the same attention reading q and the len_q NEW key/value rows un-rotated from the packed projection
+ * qkv bf16 [batch*len_q, 3*heads*head_dim] (q | k | v) and applying RoPE on the fly (cos/sin bf16 [len_q, head_dim/2]
+ * = table rows of positions len_k-len_q..len_k-1); the cache holds the rotated prefix rows j < len_k - len_q at rows
+ * b*len_k + j.  Nothing is written back to the cache. */
+int mla_decode_attn_rope(const void* qkv, int64_t ldqkv, const void* k_cache, const void* v_cache, int64_t ldkv,
+                         const void* cos_t, const void* sin_t, void* o, int64_t ldo, int32_t batch, int32_t heads,
+                         int32_t len_q, int32_t len_k, int32_t head_dim, float scale, void* stream);
 int mla_ddim_step(const void* x, const void* eps, int32_t eps_is_f32, const void* coef, void* out, int64_t n,
                   void* stream);
 

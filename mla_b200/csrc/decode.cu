@@ -346,51 +346,122 @@ __device__ __forceinline__ void ld_epl(const __nv_bfloat16* p, float* f) {
 // w, w+NW, ... (16 warps x 8 keys per pass cover 128 keys at once); partial (max, sum, acc[D]) are merged through
 // shared memory.  D = 32 * EPL.
 constexpr int DEC_WARPS = 16;
+
+// raw (packed bf16) loads first, conversion later: the loads of all UN keys are in flight before the first use
+template <int EPL> struct RawEpl { uint32_t w[(EPL + 1) / 2]; };
 template <int EPL>
+__device__ __forceinline__ RawEpl<EPL> ld_raw(const __nv_bfloat16* p) {
+  RawEpl<EPL> r;
+  if constexpr (EPL == 8) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    r.w[0] = u.x; r.w[1] = u.y; r.w[2] = u.z; r.w[3] = u.w;
+  } else if constexpr (EPL == 4) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    r.w[0] = u.x; r.w[1] = u.y;
+  } else if constexpr (EPL == 2) {
+    r.w[0] = __ldg(reinterpret_cast<const uint32_t*>(p));
+  } else {
+    r.w[0] = uint32_t(__ldg(reinterpret_cast<const unsigned short*>(p)));
+  }
+  return r;
+}
+template <int EPL>
+__device__ __forceinline__ void cvt_raw(const RawEpl<EPL>& r, float* f) {
+  if constexpr (EPL == 1) {
+    f[0] = __uint_as_float(r.w[0] << 16);
+  } else {
+#pragma unroll
+    for (int i = 0; i < EPL / 2; ++i) {
+      f[2 * i] = __uint_as_float(r.w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(r.w[i] & 0xffff0000u);
+    }
+  }
+}
+// RoPE of one head row spread over the warp (lane holds dims [lane*EPL, lane*EPL+EPL); lanes 0-15 hold the first half,
+// their partners lane^16 the second): o1 = bf16(x1 c) + bf16(-x2 s), o2 = bf16(x2 c) + bf16(x1 s), rounded to bf16 —
+// the arithmetic of rope_kernel (norm_rope_act.cu; modeling_llama.py:184-208).  cs/sn: table row of this position.
+template <int EPL>
+__device__ __forceinline__ void rope_lanes(float* x, const __nv_bfloat16* __restrict__ cs,
+                                           const __nv_bfloat16* __restrict__ sn, int lane) {
+  const int col = (lane & 15) * EPL;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const float other = __shfl_xor_sync(0xffffffffu, x[e], 16);
+    const float c = __bfloat162float(cs[col + e]), sgn = __bfloat162float(sn[col + e]);
+    const float t = lane < 16 ? bf16_round(x[e] * c) + bf16_round(-other * sgn) : bf16_round(x[e] * c) + bf16_round(other * sgn);
+    x[e] = bf16_round(t);
+  }
+}
+
+// ROPE = 0: q rows are already rotated and every key/value row (b, j), j < Lk, lives in the cache.
+// ROPE = 1: q and the last Lq key rows come un-rotated from the packed projection `qkv` (row b*Lq + i: q | k | v at
+//           column offsets 0 / hdim / 2*hdim) and are rotated on the fly with the table rows cs/sn [Lq, D/2] of
+//           positions Lk-Lq..Lk-1; the cache holds the rotated prefix rows j < Lk - Lq (rows b*Lk + j).  The new K/V
+//           are never written back: within the DDIM loop the next step recomputes them from the next x_t.
+template <int EPL, int ROPE>
 __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(
     const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k,
     const __nv_bfloat16* __restrict__ v, int64_t ldkv, __nv_bfloat16* __restrict__ o, int64_t ldo, int H, int Lq,
-    int Lk, float scale) {
+    int Lk, float scale, const __nv_bfloat16* __restrict__ cs, const __nv_bfloat16* __restrict__ sn) {
   constexpr int D = 32 * EPL;
   pdl_launch_dependents();       // the output projection's gemv may start prefetching its weights
   __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];
   __shared__ float s_acc[DEC_WARPS][D];
   const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkeys = Lk - Lq + i + 1;
+  const int P = Lk - Lq;
+  const int nkeys = P + i + 1;
+  const int hdim = H * D;
   float qf[EPL], acc[EPL];
-  const __nv_bfloat16* qr = q + (int64_t(b) * Lq + i) * ldq + int64_t(h) * D + lane * EPL;
+  cvt_raw<EPL>(ld_raw<EPL>(q + (int64_t(b) * Lq + i) * ldq + int64_t(h) * D + lane * EPL), qf);
+  if (ROPE) rope_lanes<EPL>(qf, cs + int64_t(i) * (D / 2), sn + int64_t(i) * (D / 2), lane);
 #pragma unroll
-  for (int e = 0; e < EPL; ++e) { qf[e] = __bfloat162float(qr[e]) * scale; acc[e] = 0.f; }   // scale folded into q
+  for (int e = 0; e < EPL; ++e) { qf[e] *= scale; acc[e] = 0.f; }   // scale folded into q
   float m = -INFINITY, l = 0.f;
   const int64_t base = int64_t(b) * Lk * ldkv + int64_t(h) * D + lane * EPL;
   constexpr int UN = 8;          // 16 independent loads per lane in flight: the kernel is DRAM-latency bound
   for (int j0 = warp; j0 < nkeys; j0 += DEC_WARPS * UN) {
-    float s[UN], vf[UN][EPL];
+    RawEpl<EPL> kr[UN], vr[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const int j = j0 + u * DEC_WARPS;
+#pragma unroll
+      for (int w2 = 0; w2 < (EPL + 1) / 2; ++w2) { kr[u].w[w2] = 0u; vr[u].w[w2] = 0u; }
+      if (j < nkeys) {
+        if (ROPE && j >= P) {
+          const __nv_bfloat16* row = q + (int64_t(b) * Lq + (j - P)) * ldq + int64_t(h) * D + lane * EPL;
+          kr[u] = ld_raw<EPL>(row + hdim);
+          vr[u] = ld_raw<EPL>(row + 2 * hdim);
+        } else {
+          kr[u] = ld_raw<EPL>(k + base + int64_t(j) * ldkv);
+          vr[u] = ld_raw<EPL>(v + base + int64_t(j) * ldkv);
+        }
+      }
+    }
+    float s[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int j = j0 + u * DEC_WARPS;
+      float kf[EPL];
+      cvt_raw<EPL>(kr[u], kf);
+      if (ROPE && j >= P && j < nkeys)       // warp-uniform: j depends on the warp index only
+        rope_lanes<EPL>(kf, cs + int64_t(j - P) * (D / 2), sn + int64_t(j - P) * (D / 2), lane);
       s[u] = 0.f;
 #pragma unroll
-      for (int e = 0; e < EPL; ++e) vf[u][e] = 0.f;
-      if (j < nkeys) {
-        float kf[EPL];
-        ld_epl<EPL>(k + base + int64_t(j) * ldkv, kf);
-        ld_epl<EPL>(v + base + int64_t(j) * ldkv, vf[u]);
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) s[u] = fmaf(qf[e], kf[e], s[u]);
-      }
+      for (int e = 0; e < EPL; ++e) s[u] = fmaf(qf[e], kf[e], s[u]);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) s[u] = d_wsum(s[u]);
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       if (j0 + u * DEC_WARPS < nkeys) {
+        float vf[EPL];
+        cvt_raw<EPL>(vr[u], vf);
         const float mn = fmaxf(m, s[u]);
-        const float corr = __expf(m - mn), p = __expf(s[u] - mn);
-        l = l * corr + p;
+        const float corr = __expf(m - mn), pj = __expf(s[u] - mn);
+        l = l * corr + pj;
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) acc[e] = acc[e] * corr + p * vf[u][e];
+        for (int e = 0; e < EPL; ++e) acc[e] = acc[e] * corr + pj * vf[e];
         m = mn;
       }
     }
@@ -522,7 +593,7 @@ template <int MB, int CPT, int RPI, int PRO, int GEN>
 static int launch_gemv(const GemvParams& p, int grid, size_t smem, cudaStream_t stream) {
   if (g_gemv_xf32 < 0) {
     const char* e = getenv("MLA_GEMV_XF32");
-    g_gemv_xf32 = (e && e[0] == '1') ? 1 : 0;
+    g_gemv_xf32 = (e && e[0] == '0') ? 0 : 1;       // fp32 activations in registers by default
   }
   if (!GEN && g_gemv_xf32) return launch_gemv_x<MB, CPT, RPI, PRO, GEN, 1>(p, grid, smem, stream);
   return launch_gemv_x<MB, CPT, RPI, PRO, GEN, 0>(p, grid, smem, stream);
@@ -596,19 +667,29 @@ extern "C" int mla_gemv_bf16(const void* x, const void* w, void* out, const void
   return mla_gemv_fused(&a, stream);
 }
 
-extern "C" int mla_decode_attn(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* o,
-                               int64_t ldo, int32_t batch, int32_t heads, int32_t len_q, int32_t len_k,
-                               int32_t head_dim, float scale, void* stream) {
+static int decode_attn_launch(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* o,
+                              int64_t ldo, int32_t batch, int32_t heads, int32_t len_q, int32_t len_k, int32_t head_dim,
+                              float scale, const void* cs, const void* sn, void* stream) {
   if (int rc = device_check()) return rc;
   if (batch <= 0 || heads <= 0 || len_q <= 0) return MLA_OK;
   if (len_k < len_q) return set_error(MLA_ERR_ARG, "decode_attn: len_k=%d < len_q=%d", len_k, len_q);
   if ((ldkv & 7) || ((reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15))
     return set_error(MLA_ERR_ARG, "decode_attn: K/V must be 16-byte aligned with a row pitch that is a multiple of 8");
+  if ((ldq & 7) || (reinterpret_cast<uintptr_t>(q) & 15))
+    return set_error(MLA_ERR_ARG, "decode_attn: q must be 16-byte aligned with a row pitch that is a multiple of 8");
   dim3 grid(len_q, heads, batch);
-#define MLA_DEC(EPL)                                                                                            \
-  decode_attn_kernel<EPL><<<grid, DEC_WARPS * 32, 0, S_(stream)>>>(                                             \
-      (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, (__nv_bfloat16*)o, ldo, \
-      heads, len_q, len_k, scale)
+  const bool rope = cs != nullptr;
+#define MLA_DEC(EPL)                                                                                             \
+  do {                                                                                                           \
+    if (rope)                                                                                                    \
+      decode_attn_kernel<EPL, 1><<<grid, DEC_WARPS * 32, 0, S_(stream)>>>(                                       \
+          (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, (__nv_bfloat16*)o, \
+          ldo, heads, len_q, len_k, scale, (const __nv_bfloat16*)cs, (const __nv_bfloat16*)sn);                  \
+    else                                                                                                         \
+      decode_attn_kernel<EPL, 0><<<grid, DEC_WARPS * 32, 0, S_(stream)>>>(                                       \
+          (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, (__nv_bfloat16*)o, \
+          ldo, heads, len_q, len_k, scale, nullptr, nullptr);                                                    \
+  } while (0)
   switch (head_dim) {
     case 32: MLA_DEC(1); break;
     case 64: MLA_DEC(2); break;
@@ -619,6 +700,22 @@ extern "C" int mla_decode_attn(const void* q, int64_t ldq, const void* k, const 
 #undef MLA_DEC
   MLA_CHECK_LAUNCH("decode_attn");
   return MLA_OK;
+}
+
+extern "C" int mla_decode_attn(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* o,
+                               int64_t ldo, int32_t batch, int32_t heads, int32_t len_q, int32_t len_k,
+                               int32_t head_dim, float scale, void* stream) {
+  return decode_attn_launch(q, ldq, k, v, ldkv, o, ldo, batch, heads, len_q, len_k, head_dim, scale, nullptr, nullptr,
+                            stream);
+}
+
+extern "C" int mla_decode_attn_rope(const void* qkv, int64_t ldqkv, const void* k_cache, const void* v_cache,
+                                    int64_t ldkv, const void* cos_t, const void* sin_t, void* o, int64_t ldo,
+                                    int32_t batch, int32_t heads, int32_t len_q, int32_t len_k, int32_t head_dim,
+                                    float scale, void* stream) {
+  if (!cos_t || !sin_t) return set_error(MLA_ERR_ARG, "decode_attn_rope: RoPE tables are required");
+  return decode_attn_launch(qkv, ldqkv, k_cache, v_cache, ldkv, o, ldo, batch, heads, len_q, len_k, head_dim, scale,
+                            cos_t, sin_t, stream);
 }
 
 extern "C" int mla_ddim_step(const void* x, const void* eps, int32_t eps_is_f32, const void* coef, void* out, int64_t n,

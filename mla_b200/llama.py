@@ -293,11 +293,11 @@ class LlamaDecoderLayer(nn.Module):
         wqkv, wo, wgu, wd, l1, l2 = self.compute_weights()
         h, H = self.hidden_size, self.heads
         D = h // H
-        # 6 launches: RMSNorm and SwiGLU ride in the prologues of the skinny GEMMs (ops.gemv), RoPE + cache append
-        # are one kernel
+        # 5 launches: RMSNorm and SwiGLU ride in the prologues of the skinny GEMMs (ops.gemv); RoPE of q and of the
+        # new keys happens inside the attention kernel, which reads them straight from the projection — the suffix
+        # K/V are never appended to the cache (the next DDIM step recomputes them from the next x_t)
         qkv = ops.gemv(x, wqkv, norm=(l1, self.eps))
-        ops.rope_cache(qkv, cache, cos, sin, B, n, P, H, D)
-        ctx = ops.decode_attn(qkv, cache, B, H, n, P + n, D)
+        ctx = ops.decode_attn_rope(qkv, cache, cos, sin, B, H, n, P + n, D)
         x_mid = ops.gemv(ctx, wo, residual=x)
         gu = ops.gemv(x_mid, wgu, norm=(l2, self.eps))
         return ops.gemv(gu, wd, residual=x_mid, swiglu=True)

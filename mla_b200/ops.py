@@ -626,6 +626,27 @@ def decode_attn(q: torch.Tensor, kv: torch.Tensor, B: int, H: int, Lq: int, Lk: 
     return ctx
 
 
+def decode_attn_rope(qkv: torch.Tensor, kv: torch.Tensor, cos_t: torch.Tensor, sin_t: torch.Tensor, B: int, H: int,
+                     Lq: int, Lk: int, D: int) -> torch.Tensor:
+    """decode_attn on the un-rotated packed projection qkv bf16 [B*Lq, 3*H*D]: RoPE of q and of the Lq new keys happens
+    inside the kernel (cos/sin = table rows Lk-Lq..Lk-1), the prefix keys/values come from the cache kv [B*Lk, 2*H*D]
+    (rows b*Lk + j, j < Lk-Lq).  Returns ctx bf16 [B*Lq, H*D]."""
+    _req(qkv, torch.bfloat16, "qkv")
+    _req(kv, torch.bfloat16, "kv")
+    if tuple(qkv.shape) != (B * Lq, 3 * H * D) or not qkv.is_contiguous():
+        raise _lib.MlaError(f"decode_attn_rope: qkv must be contiguous [{B * Lq}, {3 * H * D}]")
+    if tuple(kv.shape) != (B * Lk, 2 * H * D) or not kv.is_contiguous():
+        raise _lib.MlaError(f"decode_attn_rope: kv cache must be contiguous [{B * Lk}, {2 * H * D}]")
+    if tuple(cos_t.shape) != (Lq, D // 2) or not (cos_t.is_contiguous() and sin_t.is_contiguous()):
+        raise _lib.MlaError("decode_attn_rope: cos/sin must be contiguous [Lq, D/2]")
+    ctx = torch.empty((B * Lq, H * D), dtype=torch.bfloat16, device=qkv.device)
+    check(_lib.lib().mla_decode_attn_rope(_p(qkv), C.c_int64(qkv.stride(0)), _p(kv), C.c_void_p(kv.data_ptr() + 2 * H * D),
+                                          C.c_int64(kv.stride(0)), _p(cos_t), _p(sin_t), _p(ctx),
+                                          C.c_int64(ctx.stride(0)), C.c_int32(B), C.c_int32(H), C.c_int32(Lq),
+                                          C.c_int32(Lk), C.c_int32(D), C.c_float(D ** -0.5), _stream()))
+    return ctx
+
+
 def ddim_step(x: torch.Tensor, eps: torch.Tensor, coef: torch.Tensor) -> torch.Tensor:
     """x_{t-1} = ddim_sample(x_t, eps) with eta = 0 (see mla_ddim_step); x f32, eps bf16/f32, coef f32 [4] on device."""
     _req(x, torch.float32, "x")

@@ -84,6 +84,28 @@ def test_rope_cache_kernel(cuda_lib):
         assert torch.equal(cache, c2)                        # k rotated into the cache, v copied, prefix untouched
 
 
+@pytest.mark.parametrize("D,H", [(32, 4), (128, 8)])
+def test_decode_attn_with_fused_rope(cuda_lib, D, H):
+    """RoPE of q and of the new keys inside the attention kernel (they are read un-rotated from the projection and
+    never appended to the cache) == rope_cache followed by decode_attn on the appended cache."""
+    from mla_b200 import ops
+    torch.manual_seed(D)
+    B, n, P = 2, 3, 77
+    h = H * D
+    qkv = _bf(torch.randn(B * n, 3 * h, device="cuda"))
+    cache = _bf(torch.randn(B * (P + n), 2 * h, device="cuda"))
+    pos = torch.arange(P + n, device="cuda").float()
+    inv = 1.0 / (10000 ** (torch.arange(0, D, 2, device="cuda").float() / D))
+    fr = pos[:, None] * inv[None]
+    cos, sin = _bf(fr.cos())[P:].contiguous(), _bf(fr.sin())[P:].contiguous()
+    got = ops.decode_attn_rope(qkv, cache, cos, sin, B, H, n, P + n, D)
+    q2, c2 = qkv.clone(), cache.clone()
+    ops.rope_cache(q2, c2, cos, sin, B, n, P, H, D)
+    want = ops.decode_attn(q2, c2, B, H, n, P + n, D)
+    assert rel_err(got, want) < 1e-6, rel_err(got, want)
+    assert torch.equal(cache.view(B, P + n, 2 * h)[:, :P], c2.view(B, P + n, 2 * h)[:, :P])      # cache untouched
+
+
 @pytest.mark.parametrize("D", [32, 128])
 def test_decode_attn_kernel(cuda_lib, D):
     """Suffix queries against the cache with flash-attn's bottom-right aligned causal mask."""

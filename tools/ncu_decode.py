@@ -29,8 +29,7 @@ cos, sin = fr.cos().to(bf).contiguous(), fr.sin().to(bf).contiguous()
 def layer(w):
     """Same launch sequence as LlamaDecoderLayer.decode (mla_b200/llama.py)."""
     qkv = ops.gemv(x, w["qkv"], norm=(lnw, 1e-5))
-    ops.rope_cache(qkv, cache, cos, sin, 1, N, P, HEADS, H // HEADS)
-    ctx = ops.decode_attn(qkv, cache, 1, HEADS, N, P + N, H // HEADS)
+    ctx = ops.decode_attn_rope(qkv, cache, cos, sin, 1, HEADS, N, P + N, H // HEADS)
     mid = ops.gemv(ctx, w["o"], residual=x)
     gu = ops.gemv(mid, w["gu"], norm=(lnw, 1e-5))
     return ops.gemv(gu, w["d"], residual=mid, swiglu=True)
