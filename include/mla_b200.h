@@ -334,11 +334,13 @@ int mla_decode_attn(const void* q, int64_t ldq, const void* k, const void* v, in
                     void* stream);
 /* decode_attn_rope: the same attention reading q and the len_q NEW key/value rows un-rotated from the packed projection
  * qkv bf16 [batch*len_q, 3*heads*head_dim] (q | k | v) and applying RoPE on the fly (cos/sin bf16 [len_q, head_dim/2]
- * = table rows of positions len_k-len_q..len_k-1); the cache holds the rotated prefix rows j < len_k - len_q at rows
- * b*len_k + j.  Nothing is written back to the cache. */
-int mla_decode_attn_rope(const void* qkv, int64_t ldqkv, const void* k_cache, const void* v_cache, int64_t ldkv,
-                         const void* cos_t, const void* sin_t, void* o, int64_t ldo, int32_t batch, int32_t heads,
-                         int32_t len_q, int32_t len_k, int32_t head_dim, float scale, void* stream);
+ * = table rows of positions len_k-len_q..len_k-1).  The cache holds the rotated prefix rows only, row (b, h, j),
+ * j < len_k - len_q, at k|v_cache + b*kv_stride_b + h*kv_stride_h + j*kv_stride_j (elements; a head-major cache,
+ * kv_stride_j = head_dim, streams contiguously).  Nothing is written back to the cache. */
+int mla_decode_attn_rope(const void* qkv, int64_t ldqkv, const void* k_cache, const void* v_cache, int64_t kv_stride_b,
+                         int64_t kv_stride_h, int64_t kv_stride_j, const void* cos_t, const void* sin_t, void* o,
+                         int64_t ldo, int32_t batch, int32_t heads, int32_t len_q, int32_t len_k, int32_t head_dim,
+                         float scale, void* stream);
 int mla_ddim_step(const void* x, const void* eps, int32_t eps_is_f32, const void* coef, void* out, int64_t n,
                   void* stream);
 

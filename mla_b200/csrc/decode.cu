@@ -401,8 +401,12 @@ __device__ __forceinline__ void rope_lanes(float* x, const __nv_bfloat16* __rest
 template <int EPL, int ROPE>
 __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(
     const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k,
-    const __nv_bfloat16* __restrict__ v, int64_t ldkv, __nv_bfloat16* __restrict__ o, int64_t ldo, int H, int Lq,
-    int Lk, float scale, const __nv_bfloat16* __restrict__ cs, const __nv_bfloat16* __restrict__ sn) {
+    const __nv_bfloat16* __restrict__ v, int64_t kv_sb, int64_t kv_sh, int64_t kv_sj, __nv_bfloat16* __restrict__ o,
+    int64_t ldo, int H, int Lq, int Lk, float scale, const __nv_bfloat16* __restrict__ cs,
+    const __nv_bfloat16* __restrict__ sn) {
+  // cached key/value row (b, h, j) at k|v + b*kv_sb + h*kv_sh + j*kv_sj.  Token-major caches ([token][head][d]:
+  // kv_sj = row pitch, kv_sh = D) make every head's stream a 256-byte gather at a 16 KB stride; the head-major layout
+  // the denoise loop uses ([head][token][d]: kv_sj = D) lets the 16 warps of a CTA sweep 32 KB contiguous per pass.
   constexpr int D = 32 * EPL;
   pdl_launch_dependents();       // the output projection's gemv may start prefetching its weights
   __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(
 #pragma unroll
   for (int e = 0; e < EPL; ++e) { qf[e] *= scale; acc[e] = 0.f; }   // scale folded into q
   float m = -INFINITY, l = 0.f;
-  const int64_t base = int64_t(b) * Lk * ldkv + int64_t(h) * D + lane * EPL;
+  const int64_t base = int64_t(b) * kv_sb + int64_t(h) * kv_sh + lane * EPL;
   constexpr int UN = 8;          // 16 independent loads per lane in flight: the kernel is DRAM-latency bound
   for (int j0 = warp; j0 < nkeys; j0 += DEC_WARPS * UN) {
     RawEpl<EPL> kr[UN], vr[UN];
@@ -433,8 +437,8 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(
           kr[u] = ld_raw<EPL>(row + hdim);
           vr[u] = ld_raw<EPL>(row + 2 * hdim);
         } else {
-          kr[u] = ld_raw<EPL>(k + base + int64_t(j) * ldkv);
-          vr[u] = ld_raw<EPL>(v + base + int64_t(j) * ldkv);
+          kr[u] = ld_raw<EPL>(k + base + int64_t(j) * kv_sj);
+          vr[u] = ld_raw<EPL>(v + base + int64_t(j) * kv_sj);
         }
       }
     }
@@ -667,14 +671,15 @@ extern "C" int mla_gemv_bf16(const void* x, const void* w, void* out, const void
   return mla_gemv_fused(&a, stream);
 }
 
-static int decode_attn_launch(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* o,
-                              int64_t ldo, int32_t batch, int32_t heads, int32_t len_q, int32_t len_k, int32_t head_dim,
-                              float scale, const void* cs, const void* sn, void* stream) {
+static int decode_attn_launch(const void* q, int64_t ldq, const void* k, const void* v, int64_t kv_sb, int64_t kv_sh,
+                              int64_t kv_sj, void* o, int64_t ldo, int32_t batch, int32_t heads, int32_t len_q,
+                              int32_t len_k, int32_t head_dim, float scale, const void* cs, const void* sn,
+                              void* stream) {
   if (int rc = device_check()) return rc;
   if (batch <= 0 || heads <= 0 || len_q <= 0) return MLA_OK;
   if (len_k < len_q) return set_error(MLA_ERR_ARG, "decode_attn: len_k=%d < len_q=%d", len_k, len_q);
-  if ((ldkv & 7) || ((reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15))
-    return set_error(MLA_ERR_ARG, "decode_attn: K/V must be 16-byte aligned with a row pitch that is a multiple of 8");
+  if (((kv_sb | kv_sh | kv_sj) & 7) || ((reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v)) & 15))
+    return set_error(MLA_ERR_ARG, "decode_attn: K/V must be 16-byte aligned with strides that are multiples of 8");
   if ((ldq & 7) || (reinterpret_cast<uintptr_t>(q) & 15))
     return set_error(MLA_ERR_ARG, "decode_attn: q must be 16-byte aligned with a row pitch that is a multiple of 8");
   dim3 grid(len_q, heads, batch);
@@ -683,12 +688,12 @@ static int decode_attn_launch(const void* q, int64_t ldq, const void* k, const v
   do {                                                                                                           \
     if (rope)                                                                                                    \
       decode_attn_kernel<EPL, 1><<<grid, DEC_WARPS * 32, 0, S_(stream)>>>(                                       \
-          (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, (__nv_bfloat16*)o, \
-          ldo, heads, len_q, len_k, scale, (const __nv_bfloat16*)cs, (const __nv_bfloat16*)sn);                  \
+          (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, kv_sb, kv_sh, kv_sj,    \
+          (__nv_bfloat16*)o, ldo, heads, len_q, len_k, scale, (const __nv_bfloat16*)cs, (const __nv_bfloat16*)sn); \
     else                                                                                                         \
       decode_attn_kernel<EPL, 0><<<grid, DEC_WARPS * 32, 0, S_(stream)>>>(                                       \
-          (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, ldkv, (__nv_bfloat16*)o, \
-          ldo, heads, len_q, len_k, scale, nullptr, nullptr);                                                    \
+          (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, kv_sb, kv_sh, kv_sj,    \
+          (__nv_bfloat16*)o, ldo, heads, len_q, len_k, scale, nullptr, nullptr);                                 \
   } while (0)
   switch (head_dim) {
     case 32: MLA_DEC(1); break;
@@ -705,17 +710,17 @@ static int decode_attn_launch(const void* q, int64_t ldq, const void* k, const v
 extern "C" int mla_decode_attn(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv, void* o,
                                int64_t ldo, int32_t batch, int32_t heads, int32_t len_q, int32_t len_k,
                                int32_t head_dim, float scale, void* stream) {
-  return decode_attn_launch(q, ldq, k, v, ldkv, o, ldo, batch, heads, len_q, len_k, head_dim, scale, nullptr, nullptr,
-                            stream);
+  return decode_attn_launch(q, ldq, k, v, int64_t(len_k) * ldkv, head_dim, ldkv, o, ldo, batch, heads, len_q, len_k,
+                            head_dim, scale, nullptr, nullptr, stream);
 }
 
 extern "C" int mla_decode_attn_rope(const void* qkv, int64_t ldqkv, const void* k_cache, const void* v_cache,
-                                    int64_t ldkv, const void* cos_t, const void* sin_t, void* o, int64_t ldo,
-                                    int32_t batch, int32_t heads, int32_t len_q, int32_t len_k, int32_t head_dim,
-                                    float scale, void* stream) {
+                                    int64_t kv_stride_b, int64_t kv_stride_h, int64_t kv_stride_j, const void* cos_t,
+                                    const void* sin_t, void* o, int64_t ldo, int32_t batch, int32_t heads,
+                                    int32_t len_q, int32_t len_k, int32_t head_dim, float scale, void* stream) {
   if (!cos_t || !sin_t) return set_error(MLA_ERR_ARG, "decode_attn_rope: RoPE tables are required");
-  return decode_attn_launch(qkv, ldqkv, k_cache, v_cache, ldkv, o, ldo, batch, heads, len_q, len_k, head_dim, scale,
-                            cos_t, sin_t, stream);
+  return decode_attn_launch(qkv, ldqkv, k_cache, v_cache, kv_stride_b, kv_stride_h, kv_stride_j, o, ldo, batch, heads,
+                            len_q, len_k, head_dim, scale, cos_t, sin_t, stream);
 }
 
 extern "C" int mla_ddim_step(const void* x, const void* eps, int32_t eps_is_f32, const void* coef, void* out, int64_t n,

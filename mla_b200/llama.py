@@ -277,12 +277,12 @@ class LlamaDecoderLayer(nn.Module):
         return dx
 
     # ------------------------------------------------------------------ inference: prefix once, suffix per DDIM step
-    def prefill(self, x: torch.Tensor, sh: LayerShape, cache: torch.Tensor, total: int) -> torch.Tensor:
-        """Training-path forward of the prefix rows x [B*P, h] (no autograd); the post-RoPE k | v of every prefix
-        position are copied into cache [B*total, 2h] (rows b*total + j, j < P)."""
+    def prefill(self, x: torch.Tensor, sh: LayerShape, cache: torch.Tensor) -> torch.Tensor:
+        """Training-path forward of the prefix rows x [B*P, h] (no autograd); the post-RoPE keys | values of every
+        prefix position go to the head-major cache [B, 2, H, P, D] (each head's rows contiguous: the decode attention
+        streams them instead of gathering 256-byte pieces at a 16 KB stride)."""
         _, qkv, _, _, x_mid = self._attn_half(x, sh, False)
-        h = self.hidden_size
-        cache.view(sh.B, total, 2 * h)[:, :sh.S].copy_(qkv.view(sh.B, sh.S, 3 * h)[:, :, h:])
+        cache.copy_(qkv.view(sh.B, sh.S, 3, sh.H, sh.D)[:, :, 1:].permute(0, 2, 3, 1, 4))
         del qkv
         return self._mlp_half(x_mid)[3]
 
@@ -297,7 +297,7 @@ class LlamaDecoderLayer(nn.Module):
         # new keys happens inside the attention kernel, which reads them straight from the projection — the suffix
         # K/V are never appended to the cache (the next DDIM step recomputes them from the next x_t)
         qkv = ops.gemv(x, wqkv, norm=(l1, self.eps))
-        ctx = ops.decode_attn_rope(qkv, cache, cos, sin, B, H, n, P + n, D)
+        ctx = ops.decode_attn_rope(qkv, cache, cos, sin, B, H, n, P, D)
         x_mid = ops.gemv(ctx, wo, residual=x)
         gu = ops.gemv(x_mid, wgu, norm=(l2, self.eps))
         return ops.gemv(gu, wd, residual=x_mid, swiglu=True)
@@ -383,16 +383,15 @@ class LlamaModel(nn.Module):
     def prefill(self, x: torch.Tensor, B: int, P: int, extra: int,
                 caches: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
         """Run the P prefix rows per sample (x bf16 [B*P, h], no padding) through every layer once.  Returns one
-        k | v cache per layer, bf16 [B*(P+extra), 2h], with room for `extra` suffix positions (written into `caches`
-        when given: static buffers of a CUDA-graph session)."""
+        key | value cache per layer, bf16 [B, 2, H, P, D] (written into `caches` when given: static buffers of a
+        CUDA-graph session); `extra` = the number of suffix positions that will follow (sizes the RoPE table)."""
         D = self.hidden_size // self.heads
         cos, sin = self.rope_tables(P + extra, x.device)
         sh = LayerShape(B, P, self.heads, D, None, cos[:P].contiguous(), sin[:P].contiguous())
         if caches is None:
-            caches = [torch.empty((B * (P + extra), 2 * self.hidden_size), dtype=torch.bfloat16, device=x.device)
-                      for _ in self.layers]
+            caches = [torch.empty((B, 2, self.heads, P, D), dtype=torch.bfloat16, device=x.device) for _ in self.layers]
         for layer, cache in zip(self.layers, caches):
-            x = layer.prefill(x, sh, cache, P + extra)
+            x = layer.prefill(x, sh, cache)
         return caches
 
     @torch.no_grad()

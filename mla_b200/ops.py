@@ -627,23 +627,24 @@ def decode_attn(q: torch.Tensor, kv: torch.Tensor, B: int, H: int, Lq: int, Lk: 
 
 
 def decode_attn_rope(qkv: torch.Tensor, kv: torch.Tensor, cos_t: torch.Tensor, sin_t: torch.Tensor, B: int, H: int,
-                     Lq: int, Lk: int, D: int) -> torch.Tensor:
-    """decode_attn on the un-rotated packed projection qkv bf16 [B*Lq, 3*H*D]: RoPE of q and of the Lq new keys happens
-    inside the kernel (cos/sin = table rows Lk-Lq..Lk-1), the prefix keys/values come from the cache kv [B*Lk, 2*H*D]
-    (rows b*Lk + j, j < Lk-Lq).  Returns ctx bf16 [B*Lq, H*D]."""
+                     Lq: int, P: int, D: int) -> torch.Tensor:
+    """Attention of the Lq new rows per sample against a head-major prefix cache + themselves: qkv bf16 [B*Lq, 3*H*D]
+    un-rotated (RoPE of q and of the new keys happens in the kernel; cos/sin = table rows P..P+Lq-1); kv bf16
+    [B, 2, H, P, D] = the rotated prefix keys | values.  Returns ctx bf16 [B*Lq, H*D]."""
     _req(qkv, torch.bfloat16, "qkv")
     _req(kv, torch.bfloat16, "kv")
     if tuple(qkv.shape) != (B * Lq, 3 * H * D) or not qkv.is_contiguous():
         raise _lib.MlaError(f"decode_attn_rope: qkv must be contiguous [{B * Lq}, {3 * H * D}]")
-    if tuple(kv.shape) != (B * Lk, 2 * H * D) or not kv.is_contiguous():
-        raise _lib.MlaError(f"decode_attn_rope: kv cache must be contiguous [{B * Lk}, {2 * H * D}]")
+    if tuple(kv.shape) != (B, 2, H, P, D) or not kv.is_contiguous():
+        raise _lib.MlaError(f"decode_attn_rope: kv cache must be contiguous [{B}, 2, {H}, {P}, {D}], got {tuple(kv.shape)}")
     if tuple(cos_t.shape) != (Lq, D // 2) or not (cos_t.is_contiguous() and sin_t.is_contiguous()):
         raise _lib.MlaError("decode_attn_rope: cos/sin must be contiguous [Lq, D/2]")
     ctx = torch.empty((B * Lq, H * D), dtype=torch.bfloat16, device=qkv.device)
-    check(_lib.lib().mla_decode_attn_rope(_p(qkv), C.c_int64(qkv.stride(0)), _p(kv), C.c_void_p(kv.data_ptr() + 2 * H * D),
-                                          C.c_int64(kv.stride(0)), _p(cos_t), _p(sin_t), _p(ctx),
+    check(_lib.lib().mla_decode_attn_rope(_p(qkv), C.c_int64(qkv.stride(0)), _p(kv),
+                                          C.c_void_p(kv.data_ptr() + 2 * H * P * D), C.c_int64(2 * H * P * D),
+                                          C.c_int64(P * D), C.c_int64(D), _p(cos_t), _p(sin_t), _p(ctx),
                                           C.c_int64(ctx.stride(0)), C.c_int32(B), C.c_int32(H), C.c_int32(Lq),
-                                          C.c_int32(Lk), C.c_int32(D), C.c_float(D ** -0.5), _stream()))
+                                          C.c_int32(P + Lq), C.c_int32(D), C.c_float(D ** -0.5), _stream()))
     return ctx
 
 

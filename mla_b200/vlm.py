@@ -438,8 +438,9 @@ class PrismaticVLM(nn.Module):
         if sess is None:
             sess = SimpleNamespace(prefix=torch.zeros((B * P, h), dtype=torch.bfloat16, device=dev),
                                    noise=torch.zeros((B, n_x, self.action_dim), dtype=torch.float32, device=dev),
-                                   caches=[torch.empty((B * (P + 1 + n_x), 2 * h), dtype=torch.bfloat16, device=dev)
-                                           for _ in model.layers], g_prefill=None, g_loop=None, out=None, fp=None)
+                                   caches=[torch.empty((B, 2, model.heads, P, h // model.heads), dtype=torch.bfloat16,
+                                                       device=dev) for _ in model.layers],
+                                   g_prefill=None, g_loop=None, out=None, fp=None)
         st = SimpleNamespace(caches=sess.caches, B=B, P=P, n_x=n_x, h=h, dev=dev)
 
         def run_prefill():

@@ -98,12 +98,15 @@ def test_decode_attn_with_fused_rope(cuda_lib, D, H):
     inv = 1.0 / (10000 ** (torch.arange(0, D, 2, device="cuda").float() / D))
     fr = pos[:, None] * inv[None]
     cos, sin = _bf(fr.cos())[P:].contiguous(), _bf(fr.sin())[P:].contiguous()
-    got = ops.decode_attn_rope(qkv, cache, cos, sin, B, H, n, P + n, D)
+    # the denoise loop keeps the prefix head-major: [B, 2, H, P, D]
+    hm = cache.view(B, P + n, 2, H, D)[:, :P].permute(0, 2, 3, 1, 4).contiguous()
+    hm0 = hm.clone()
+    got = ops.decode_attn_rope(qkv, hm, cos, sin, B, H, n, P, D)
     q2, c2 = qkv.clone(), cache.clone()
     ops.rope_cache(q2, c2, cos, sin, B, n, P, H, D)
     want = ops.decode_attn(q2, c2, B, H, n, P + n, D)
     assert rel_err(got, want) < 1e-6, rel_err(got, want)
-    assert torch.equal(cache.view(B, P + n, 2 * h)[:, :P], c2.view(B, P + n, 2 * h)[:, :P])      # cache untouched
+    assert torch.equal(hm, hm0)                                                             # cache untouched
 
 
 @pytest.mark.parametrize("D", [32, 128])

@@ -17,7 +17,7 @@ W = [dict(qkv=torch.randn(3 * H, H, device=dev).to(bf) * 0.02, o=torch.randn(H, 
           gu=torch.randn(2 * F, H, device=dev).to(bf) * 0.02, d=torch.randn(H, F, device=dev).to(bf) * 0.02)
      for _ in range(R)]
 x = torch.randn(N, H, device=dev).to(bf)
-cache = torch.randn(P + N, 2 * H, device=dev).to(bf)
+cache = torch.randn(1, 2, HEADS, P, H // HEADS, device=dev).to(bf)       # head-major prefix K | V
 
 
 lnw = torch.ones(H, device=dev).to(bf)
@@ -29,7 +29,7 @@ cos, sin = fr.cos().to(bf).contiguous(), fr.sin().to(bf).contiguous()
 def layer(w):
     """Same launch sequence as LlamaDecoderLayer.decode (mla_b200/llama.py)."""
     qkv = ops.gemv(x, w["qkv"], norm=(lnw, 1e-5))
-    ctx = ops.decode_attn_rope(qkv, cache, cos, sin, 1, HEADS, N, P + N, H // HEADS)
+    ctx = ops.decode_attn_rope(qkv, cache, cos, sin, 1, HEADS, N, P, H // HEADS)
     mid = ops.gemv(ctx, w["o"], residual=x)
     gu = ops.gemv(mid, w["gu"], norm=(lnw, 1e-5))
     return ops.gemv(gu, w["d"], residual=mid, swiglu=True)
