@@ -320,9 +320,9 @@ typedef struct mla_gemv_args {
   float eps;
 } mla_gemv_args;
 int mla_gemv_fused(const mla_gemv_args* a, void* stream);
-/* Optional: launch the gemv kernels with programmaticStreamSerialization (the weight prefetch of the next kernel then
- * overlaps the previous kernel's tail; consumers griddepcontrol.wait before touching activations).  Measured slower on
- * B200 for this kernel shape, so it is off unless switched on here or with env MLA_DECODE_PDL=1. */
+/* The gemv kernels are launched with programmaticStreamSerialization (the weight prefetch of the next kernel overlaps
+ * the previous kernel's tail; consumers griddepcontrol.wait before touching activations).  0 turns it off (env
+ * MLA_DECODE_PDL=0 does the same). */
 int mla_decode_set_pdl(int32_t on);
 /* rope_cache: the n new rows per sample of a packed q|k|v projection bf16 [batch*n, 3*heads*head_dim] at positions
  * prefix..prefix+n-1: RoPE (modeling_llama.py:184-208) on q in place and on k into cache row (b*(prefix+n) + prefix + i),

@@ -36,25 +36,21 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 }
 
 // ---------------------------------------------------------------------------------------------- skinny GEMM
-// out[m, n] = bf16( bf16(sum_k x'[m,k] w[n,k]) + residual[m,n] ),  w [N,K] row-major (nn.Linear layout), m < M <= 64.
+// out[m, n] = bf16( bf16(sum_k x'[m,k] w[n,k]) + residual[m,n] ),  w [N,K] row-major (nn.Linear layout), m < M <= 16.
 //
 // Pure weight streaming, organised the way the DMA engine likes it: ONE producer thread per CTA issues a
 // cp.async.bulk (TMA, no tensor map) per weight row — 8-22 KB contiguous — into a multi-stage shared-memory ring
 // guarded by full/empty mbarriers; 16 consumer warps take the dot products from shared memory.  One persistent CTA per
 // SM owns ~190 KB of ring, so ~150 KB per SM is always in flight.  A slot holds RPI consecutive weight rows; per slot
 // the consumers do one warp-shuffle + one named-barrier reduction.
-//   Measured alternatives (profiles/r01_denoise_T0_v*.json, ms per decode step of 12.95 GB at Llama-2-7B size):
-//   warp-per-row direct loads 6.74; this ring with 16 consumer warps / 192 KB 4.33; 8 consumer warps / 100 KB ring
-//   (two CTAs of consecutive launches per SM) 5.72, and with programmatic dependent launch on top — the next kernel's
-//   producer prefetching its weights while this one drains, consumers behind griddepcontrol.wait — 6.65.  The
-//   consumer side (unpack + FMA from shared memory) is what limits, so the wide CTA stays and PDL is an off-by-default
-//   switch (MLA_DECODE_PDL=1).
-//   fast path (M <= 4): the activations live in REGISTERS for the whole kernel (thread t always multiplies the same
-//     k-chunks), optionally produced on the fly by a fused prologue:
-//       PRO_RMSNORM  x' = bf16(g * bf16(x * rstd))            (LlamaRMSNorm, modeling_llama.py:85-90)
-//       PRO_SWIGLU   x' = bf16(bf16(silu(gate)) * up), x = [gate | up]   (LlamaMLP, :240)
-//   general path (M <= 64): 8 activation rows per pass from L1/L2, several passes over the SAME shared-memory slot —
-//     the weights still cross HBM exactly once.
+//   Launch overlap (programmatic dependent launch): the weights do not depend on the previous kernel — only the
+//   activations do — so every gemv is launched with programmaticStreamSerialization: the producer starts streaming as
+//   soon as the previous kernel lets dependents launch, and only the consumers execute griddepcontrol.wait before they
+//   touch activations / residual / output.  (MLA_DECODE_PDL=0 turns it off.)
+//   Measured on B200 (profiles/r01_denoise_T0_v*.json, ms per decode step = 12.95 GB of weights at Llama-2-7B size):
+//   warp-per-row direct loads 6.74 -> this ring, 16 consumer warps / 192 KB 4.33 -> 9-shuffle multi-value reduction +
+//   latency-tolerant attention 3.76 -> RoPE fused into the attention (5 launches per layer) 3.64 -> PDL 3.50.  A
+//   narrower CTA (8 consumer warps, 100 KB ring, two CTAs of consecutive launches per SM) was slower (5.72).
 constexpr int GV_CWARPS = 16;
 constexpr int GV_CONSUMERS = GV_CWARPS * 32;
 constexpr int GV_THREADS = GV_CONSUMERS + 32;
@@ -559,7 +555,7 @@ static int g_gemv_pdl = -1;
 static bool gemv_pdl_enabled() {
   if (g_gemv_pdl < 0) {
     const char* e = getenv("MLA_DECODE_PDL");
-    g_gemv_pdl = (e && e[0] == '1') ? 1 : 0;
+    g_gemv_pdl = (e && e[0] == '0') ? 0 : 1;
   }
   return g_gemv_pdl == 1;
 }
