@@ -340,7 +340,11 @@ int mla_decode_attn(const void* q, int64_t ldq, const void* k, const void* v, in
 int mla_decode_attn_rope(const void* qkv, int64_t ldqkv, const void* k_cache, const void* v_cache, int64_t kv_stride_b,
                          int64_t kv_stride_h, int64_t kv_stride_j, const void* cos_t, const void* sin_t, void* o,
                          int64_t ldo, int32_t batch, int32_t heads, int32_t len_q, int32_t len_k, int32_t head_dim,
-                         float scale, void* stream);
+                         float scale, void* workspace, void* counters, void* stream);
+/* Split-K scratch of decode_attn_rope: with workspace (mla_decode_attn_workspace bytes, f32) and counters (int32
+ * [batch*heads*len_q], zero before the first use; the kernel re-arms them) the keys are split over ceil(len_k/128) CTAs
+ * per (sample, head, query) — one DRAM round trip each — and the last CTA to arrive merges.  NULL = one CTA per query. */
+size_t mla_decode_attn_workspace(int32_t batch, int32_t heads, int32_t len_q, int32_t len_k, int32_t head_dim);
 int mla_ddim_step(const void* x, const void* eps, int32_t eps_is_f32, const void* coef, void* out, int64_t n,
                   void* stream);
 

@@ -399,7 +399,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(
     const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k,
     const __nv_bfloat16* __restrict__ v, int64_t kv_sb, int64_t kv_sh, int64_t kv_sj, __nv_bfloat16* __restrict__ o,
     int64_t ldo, int H, int Lq, int Lk, float scale, const __nv_bfloat16* __restrict__ cs,
-    const __nv_bfloat16* __restrict__ sn) {
+    const __nv_bfloat16* __restrict__ sn, float* __restrict__ ws, int* __restrict__ counters, int S) {
+  // Split-K: with S > 1 splits, CTA (i, sp) covers keys [sp*128, sp*128+128) — ONE pass of 16 warps x 8 keys, i.e. a
+  // single DRAM round trip instead of ceil(keys/128) dependent ones — and leaves its un-normalised partial
+  // (max, sum, acc[D]) in ws; the last CTA of a (b, h, i) to arrive (atomic counter, self-resetting) merges them.
   // cached key/value row (b, h, j) at k|v + b*kv_sb + h*kv_sh + j*kv_sj.  Token-major caches ([token][head][d]:
   // kv_sj = row pitch, kv_sh = D) make every head's stream a 256-byte gather at a 16 KB stride; the head-major layout
   // the denoise loop uses ([head][token][d]: kv_sj = D) lets the 16 warps of a CTA sweep 32 KB contiguous per pass.
@@ -407,10 +410,10 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(
   pdl_launch_dependents();       // the output projection's gemv may start prefetching its weights
   __shared__ float s_m[DEC_WARPS], s_l[DEC_WARPS];
   __shared__ float s_acc[DEC_WARPS][D];
-  const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int i = blockIdx.x / S, sp = blockIdx.x % S, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = Lk - Lq;
-  const int nkeys = P + i + 1;
+  const int nall = P + i + 1;                              // keys visible to query i
   const int hdim = H * D;
   float qf[EPL], acc[EPL];
   cvt_raw<EPL>(ld_raw<EPL>(q + (int64_t(b) * Lq + i) * ldq + int64_t(h) * D + lane * EPL), qf);
@@ -420,7 +423,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(
   float m = -INFINITY, l = 0.f;
   const int64_t base = int64_t(b) * kv_sb + int64_t(h) * kv_sh + lane * EPL;
   constexpr int UN = 8;          // 16 independent loads per lane in flight: the kernel is DRAM-latency bound
-  for (int j0 = warp; j0 < nkeys; j0 += DEC_WARPS * UN) {
+  const int jbeg = S > 1 ? sp * (DEC_WARPS * UN) : 0;
+  const int nkeys = S > 1 ? (nall < jbeg + DEC_WARPS * UN ? nall : jbeg + DEC_WARPS * UN) : nall;
+  for (int j0 = jbeg + warp; j0 < nkeys; j0 += DEC_WARPS * UN) {
     RawEpl<EPL> kr[UN], vr[UN];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
@@ -470,6 +475,9 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(
 #pragma unroll
   for (int e = 0; e < EPL; ++e) s_acc[warp][lane * EPL + e] = acc[e];
   __syncthreads();
+  __nv_bfloat16* orow = o + (int64_t(b) * Lq + i) * ldo + int64_t(h) * D;
+  const int64_t unit = (int64_t(b) * H + h) * Lq + i;
+  float* part = ws ? ws + (unit * S + sp) * (D + 2) : nullptr;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float mx = -INFINITY;
 #pragma unroll
@@ -481,8 +489,35 @@ __global__ void __launch_bounds__(DEC_WARPS * 32) decode_attn_kernel(
       L += s_l[w2] * c;
       a += s_acc[w2][d] * c;
     }
-    o[(int64_t(b) * Lq + i) * ldo + int64_t(h) * D + d] = __float2bfloat16_rn(L > 0.f ? a / L : 0.f);
+    if (S == 1) {
+      orow[d] = __float2bfloat16_rn(L > 0.f ? a / L : 0.f);
+    } else {
+      part[2 + d] = a;
+      if (d == 0) { part[0] = mx; part[1] = L; }
+    }
   }
+  if (S == 1) return;
+  __shared__ int s_last;
+  __threadfence();                       // this CTA's partial is visible before its arrival is counted
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counters + unit, 1) == S - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* all = ws + unit * S * (D + 2);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float mx = -INFINITY;
+    for (int s2 = 0; s2 < S; ++s2) mx = fmaxf(mx, __ldcg(all + s2 * (D + 2)));
+    float L = 0.f, a = 0.f;
+    for (int s2 = 0; s2 < S; ++s2) {
+      const float ms = __ldcg(all + s2 * (D + 2));
+      const float c = ms == -INFINITY ? 0.f : __expf(ms - mx);
+      L += __ldcg(all + s2 * (D + 2) + 1) * c;
+      a += __ldcg(all + s2 * (D + 2) + 2 + d) * c;
+    }
+    orow[d] = __float2bfloat16_rn(L > 0.f ? a / L : 0.f);
+  }
+  if (threadIdx.x == 0) counters[unit] = 0;          // re-armed for the next launch
 }
 
 // ---------------------------------------------------------------------------------------------- RoPE + cache append
@@ -670,7 +705,7 @@ extern "C" int mla_gemv_bf16(const void* x, const void* w, void* out, const void
 static int decode_attn_launch(const void* q, int64_t ldq, const void* k, const void* v, int64_t kv_sb, int64_t kv_sh,
                               int64_t kv_sj, void* o, int64_t ldo, int32_t batch, int32_t heads, int32_t len_q,
                               int32_t len_k, int32_t head_dim, float scale, const void* cs, const void* sn,
-                              void* stream) {
+                              void* ws, void* counters, void* stream) {
   if (int rc = device_check()) return rc;
   if (batch <= 0 || heads <= 0 || len_q <= 0) return MLA_OK;
   if (len_k < len_q) return set_error(MLA_ERR_ARG, "decode_attn: len_k=%d < len_q=%d", len_k, len_q);
@@ -678,18 +713,22 @@ static int decode_attn_launch(const void* q, int64_t ldq, const void* k, const v
     return set_error(MLA_ERR_ARG, "decode_attn: K/V must be 16-byte aligned with strides that are multiples of 8");
   if ((ldq & 7) || (reinterpret_cast<uintptr_t>(q) & 15))
     return set_error(MLA_ERR_ARG, "decode_attn: q must be 16-byte aligned with a row pitch that is a multiple of 8");
-  dim3 grid(len_q, heads, batch);
+  const int splits = (ws && counters) ? (len_k + DEC_WARPS * 8 - 1) / (DEC_WARPS * 8) : 1;
+  dim3 grid(len_q * splits, heads, batch);
   const bool rope = cs != nullptr;
+  float* wsp = splits > 1 ? (float*)ws : nullptr;
+  int* cnt = splits > 1 ? (int*)counters : nullptr;
 #define MLA_DEC(EPL)                                                                                             \
   do {                                                                                                           \
     if (rope)                                                                                                    \
       decode_attn_kernel<EPL, 1><<<grid, DEC_WARPS * 32, 0, S_(stream)>>>(                                       \
           (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, kv_sb, kv_sh, kv_sj,    \
-          (__nv_bfloat16*)o, ldo, heads, len_q, len_k, scale, (const __nv_bfloat16*)cs, (const __nv_bfloat16*)sn); \
+          (__nv_bfloat16*)o, ldo, heads, len_q, len_k, scale, (const __nv_bfloat16*)cs, (const __nv_bfloat16*)sn, \
+          wsp, cnt, splits);                                                                                     \
     else                                                                                                         \
       decode_attn_kernel<EPL, 0><<<grid, DEC_WARPS * 32, 0, S_(stream)>>>(                                       \
           (const __nv_bfloat16*)q, ldq, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, kv_sb, kv_sh, kv_sj,    \
-          (__nv_bfloat16*)o, ldo, heads, len_q, len_k, scale, nullptr, nullptr);                                 \
+          (__nv_bfloat16*)o, ldo, heads, len_q, len_k, scale, nullptr, nullptr, wsp, cnt, splits);               \
   } while (0)
   switch (head_dim) {
     case 32: MLA_DEC(1); break;
@@ -707,16 +746,23 @@ extern "C" int mla_decode_attn(const void* q, int64_t ldq, const void* k, const 
                                int64_t ldo, int32_t batch, int32_t heads, int32_t len_q, int32_t len_k,
                                int32_t head_dim, float scale, void* stream) {
   return decode_attn_launch(q, ldq, k, v, int64_t(len_k) * ldkv, head_dim, ldkv, o, ldo, batch, heads, len_q, len_k,
-                            head_dim, scale, nullptr, nullptr, stream);
+                            head_dim, scale, nullptr, nullptr, nullptr, nullptr, stream);
 }
 
 extern "C" int mla_decode_attn_rope(const void* qkv, int64_t ldqkv, const void* k_cache, const void* v_cache,
                                     int64_t kv_stride_b, int64_t kv_stride_h, int64_t kv_stride_j, const void* cos_t,
                                     const void* sin_t, void* o, int64_t ldo, int32_t batch, int32_t heads,
-                                    int32_t len_q, int32_t len_k, int32_t head_dim, float scale, void* stream) {
+                                    int32_t len_q, int32_t len_k, int32_t head_dim, float scale, void* workspace,
+                                    void* counters, void* stream) {
   if (!cos_t || !sin_t) return set_error(MLA_ERR_ARG, "decode_attn_rope: RoPE tables are required");
   return decode_attn_launch(qkv, ldqkv, k_cache, v_cache, kv_stride_b, kv_stride_h, kv_stride_j, o, ldo, batch, heads,
-                            len_q, len_k, head_dim, scale, cos_t, sin_t, stream);
+                            len_q, len_k, head_dim, scale, cos_t, sin_t, workspace, counters, stream);
+}
+
+extern "C" size_t mla_decode_attn_workspace(int32_t batch, int32_t heads, int32_t len_q, int32_t len_k,
+                                            int32_t head_dim) {
+  const size_t splits = size_t((len_k + DEC_WARPS * 8 - 1) / (DEC_WARPS * 8));
+  return size_t(batch) * heads * len_q * splits * (head_dim + 2) * sizeof(float);
 }
 
 extern "C" int mla_ddim_step(const void* x, const void* eps, int32_t eps_is_f32, const void* coef, void* out, int64_t n,

@@ -627,7 +627,7 @@ def decode_attn(q: torch.Tensor, kv: torch.Tensor, B: int, H: int, Lq: int, Lk: 
 
 
 def decode_attn_rope(qkv: torch.Tensor, kv: torch.Tensor, cos_t: torch.Tensor, sin_t: torch.Tensor, B: int, H: int,
-                     Lq: int, P: int, D: int) -> torch.Tensor:
+                     Lq: int, P: int, D: int, split_k: bool = True) -> torch.Tensor:
     """Attention of the Lq new rows per sample against a head-major prefix cache + themselves: qkv bf16 [B*Lq, 3*H*D]
     un-rotated (RoPE of q and of the new keys happens in the kernel; cos/sin = table rows P..P+Lq-1); kv bf16
     [B, 2, H, P, D] = the rotated prefix keys | values.  Returns ctx bf16 [B*Lq, H*D]."""
@@ -640,11 +640,18 @@ def decode_attn_rope(qkv: torch.Tensor, kv: torch.Tensor, cos_t: torch.Tensor, s
     if tuple(cos_t.shape) != (Lq, D // 2) or not (cos_t.is_contiguous() and sin_t.is_contiguous()):
         raise _lib.MlaError("decode_attn_rope: cos/sin must be contiguous [Lq, D/2]")
     ctx = torch.empty((B * Lq, H * D), dtype=torch.bfloat16, device=qkv.device)
-    check(_lib.lib().mla_decode_attn_rope(_p(qkv), C.c_int64(qkv.stride(0)), _p(kv),
-                                          C.c_void_p(kv.data_ptr() + 2 * H * P * D), C.c_int64(2 * H * P * D),
-                                          C.c_int64(P * D), C.c_int64(D), _p(cos_t), _p(sin_t), _p(ctx),
-                                          C.c_int64(ctx.stride(0)), C.c_int32(B), C.c_int32(H), C.c_int32(Lq),
-                                          C.c_int32(P + Lq), C.c_int32(D), C.c_float(D ** -0.5), _stream()))
+    lib = _lib.lib()
+    ws = cnt = None
+    if split_k and P + Lq > 128:
+        lib.mla_decode_attn_workspace.restype = C.c_size_t
+        nbytes = lib.mla_decode_attn_workspace(C.c_int32(B), C.c_int32(H), C.c_int32(Lq), C.c_int32(P + Lq), C.c_int32(D))
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=qkv.device)
+        cnt = torch.zeros(B * H * Lq, dtype=torch.int32, device=qkv.device)
+    check(lib.mla_decode_attn_rope(_p(qkv), C.c_int64(qkv.stride(0)), _p(kv),
+                                   C.c_void_p(kv.data_ptr() + 2 * H * P * D), C.c_int64(2 * H * P * D),
+                                   C.c_int64(P * D), C.c_int64(D), _p(cos_t), _p(sin_t), _p(ctx),
+                                   C.c_int64(ctx.stride(0)), C.c_int32(B), C.c_int32(H), C.c_int32(Lq),
+                                   C.c_int32(P + Lq), C.c_int32(D), C.c_float(D ** -0.5), _p(ws), _p(cnt), _stream()))
     return ctx
 
 
