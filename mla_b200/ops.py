@@ -627,10 +627,12 @@ def decode_attn(q: torch.Tensor, kv: torch.Tensor, B: int, H: int, Lq: int, Lk: 
 
 
 def decode_attn_rope(qkv: torch.Tensor, kv: torch.Tensor, cos_t: torch.Tensor, sin_t: torch.Tensor, B: int, H: int,
-                     Lq: int, P: int, D: int, split_k: bool = True) -> torch.Tensor:
+                     Lq: int, P: int, D: int, split_k: bool = False) -> torch.Tensor:
     """Attention of the Lq new rows per sample against a head-major prefix cache + themselves: qkv bf16 [B*Lq, 3*H*D]
     un-rotated (RoPE of q and of the new keys happens in the kernel; cos/sin = table rows P..P+Lq-1); kv bf16
-    [B, 2, H, P, D] = the rotated prefix keys | values.  Returns ctx bf16 [B*Lq, H*D]."""
+    [B, 2, H, P, D] = the rotated prefix keys | values.  Returns ctx bf16 [B*Lq, H*D].  split_k spreads the keys of
+    each query over ceil(keys/128) CTAs with a last-arrival merge; measured slower at 546 keys (20.6 + 3.4 us for the
+    counter memset against 17.6 us, profiles/r01_launches_decode_layer_v8_splitk.csv), so it is off by default."""
     _req(qkv, torch.bfloat16, "qkv")
     _req(kv, torch.bfloat16, "kv")
     if tuple(qkv.shape) != (B * Lq, 3 * H * D) or not qkv.is_contiguous():

@@ -102,7 +102,7 @@ def test_decode_attn_with_fused_rope(cuda_lib, D, H, P):
     # the denoise loop keeps the prefix head-major: [B, 2, H, P, D]
     hm = cache.view(B, P + n, 2, H, D)[:, :P].permute(0, 2, 3, 1, 4).contiguous()
     hm0 = hm.clone()
-    got = ops.decode_attn_rope(qkv, hm, cos, sin, B, H, n, P, D)
+    got = ops.decode_attn_rope(qkv, hm, cos, sin, B, H, n, P, D, split_k=True)
     q2, c2 = qkv.clone(), cache.clone()
     ops.rope_cache(q2, c2, cos, sin, B, n, P, H, D)
     want = ops.decode_attn(q2, c2, B, H, n, P + n, D)
@@ -110,7 +110,7 @@ def test_decode_attn_with_fused_rope(cuda_lib, D, H, P):
     one = ops.decode_attn_rope(qkv, hm, cos, sin, B, H, n, P, D, split_k=False)
     assert rel_err(one, want) < 1e-6, rel_err(one, want)
     assert rel_err(got, want) < (1e-6 if P + n <= 128 else 4e-3), rel_err(got, want)
-    again = ops.decode_attn_rope(qkv, hm, cos, sin, B, H, n, P, D)                         # counters re-armed
+    again = ops.decode_attn_rope(qkv, hm, cos, sin, B, H, n, P, D, split_k=True)           # counters re-armed
     assert torch.equal(again, got)
     assert torch.equal(hm, hm0)                                                             # cache untouched
 
