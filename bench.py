@@ -168,7 +168,7 @@ def gemm_roofline(tokens: int, peak_tf: float, iters: int = 5):
             "the same 12 launches: profiles/r01_ncu_full_summary.json)",
             "algorithmic_bytes_per_launch": round(sum(2.0 * (m * k + n * k) + (2.0 if i < 8 else 4.0) * m * n
                                                       for i, (m, n, k) in enumerate(GEMM_SHAPES(T))) / 12),
-            "kernel": "gemm_bf16_kernel (tcgen05, 12 GEMM shapes of one decoder layer fwd+bwd)",
+            "kernel": "gemm2_bf16_kernel (tcgen05 cta_group::2, 12 GEMM shapes of one decoder layer fwd+bwd)",
             "launch_ms_avg": round(ms / len(calls), 4)}
 
 

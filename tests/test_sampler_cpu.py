@@ -89,3 +89,28 @@ def test_oracle_sampler_end_to_end_close_to_reference():
             return O.forward(sd32, batch, cfg, dict(timestep=t, x=x), compute_dtype=torch.float32)["noise_pred"]
     got = S.ddim_sample_loop(model, torch.from_numpy(z["noise"]), int(z["ddim_steps"]))
     assert rel_err(got, torch.from_numpy(z["sample"])) < 3e-2
+
+
+@pytest.mark.parametrize("n", [1, 4, 8, 10, 20])
+def test_product_schedule_equals_oracle(n):
+    """Host logic of the CUDA sampler (mla_b200/sampler.py, no kernel runs): timestep map, float64 alphas and the
+    four fp32 coefficients per step that mla_ddim_step consumes."""
+    from mla_b200 import create_diffusion
+    from oracle import sampler as S
+    dd = create_diffusion("ddim%d" % n, "squaredcos_cap_v2", 100, sigma_small=True, learn_sigma=False)
+    keep, tab = S.ddim_tables(n)
+    assert dd.timestep_map == keep and dd.num_timesteps == n and dd.original_num_steps == 100
+    assert np.array_equal(dd.alphas_cumprod, S.ddim_schedule(n)[1])
+    want = np.stack([tab[:, 0].astype(np.float32), tab[:, 1].astype(np.float32),
+                     np.sqrt(tab[:, 2].astype(np.float32)), np.sqrt(np.float32(1) - tab[:, 2].astype(np.float32))], 1)
+    assert dd._coef.dtype == np.float32 and np.array_equal(dd._coef, want)
+    with pytest.raises(NotImplementedError):
+        dd.ddim_sample_loop(lambda x, t: x, (1, 1, 7), torch.zeros(1, 1, 7), eta=0.5)
+
+
+def test_training_diffusion_unchanged_by_respacing_support():
+    from mla_b200 import create_diffusion
+    d = create_diffusion(timestep_respacing="", noise_schedule="squaredcos_cap_v2", diffusion_steps=100)
+    assert d.num_timesteps == 100 and not hasattr(d, "timestep_map")
+    with pytest.raises(NotImplementedError):
+        create_diffusion(timestep_respacing="10,10", diffusion_steps=100)
