@@ -313,12 +313,14 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / n
 
-    try:
-        ms_fwd = round(time_fn(fwd_only, max(2, args.steps // 2)), 2)
-        ms_fwd_bwd = round(time_fn(fwd_bwd, max(2, args.steps // 2)), 2)
-    except Exception as ex:                 # secondary numbers must never take the headline line down
-        sys.stderr.write(f"fwd / fwd+bwd timing failed: {ex}\n")
-        ms_fwd = ms_fwd_bwd = None
+    ms_fwd = ms_fwd_bwd = None
+    if world == 1:                          # per-GPU quantities: measured on the single-GPU run only
+        try:
+            ms_fwd = round(time_fn(fwd_only, max(2, args.steps // 2)), 2)
+            ms_fwd_bwd = round(time_fn(fwd_bwd, max(2, args.steps // 2)), 2)
+        except Exception as ex:             # secondary numbers must never take the headline line down
+            sys.stderr.write(f"fwd / fwd+bwd timing failed: {ex}\n")
+            ms_fwd = ms_fwd_bwd = None
     clocks = sampler.stop() if rank == 0 else None
     mla.vlm.check_errors()
     mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
