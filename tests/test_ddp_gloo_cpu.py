@@ -71,3 +71,41 @@ def test_gradient_exchange_world2(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def _ckpt_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mla_b200.llama import LlamaModel
+        from mla_b200.trainer import DataParallelTrainer
+        torch.manual_seed(0)
+
+        class Wrap(torch.nn.Module):          # the attributes save_checkpoint reads from the MLA wrapper
+            def __init__(self):
+                super().__init__()
+                self.vlm = torch.nn.ModuleDict(dict(llm_backbone=LlamaModel(64, 32, 64, 2, 4),
+                                                    projector_2d=torch.nn.Linear(4, 4)))
+                self.trainable_module_keys = ["vlm.llm_backbone", "vlm.projector_2d"]
+                self.all_module_keys = list(self.trainable_module_keys)
+        m = Wrap()
+        tr = DataParallelTrainer(m)
+        tr.step_count = 3 + rank                          # only rank 0's optimizer record is written
+        path = tr.save_checkpoint(out_dir, global_step=5, epoch=1, train_loss=0.5)
+        assert path.name == "step-000005-epoch-01-loss=0.5000.pt"
+        assert path.exists()                               # visible to every rank after the barrier
+        blob = torch.load(path, weights_only=True)["model"]
+        assert set(blob) == {"llm_backbone", "projector_2d"}
+        opt = torch.load(path.with_suffix(".optimizer"), weights_only=True)
+        assert opt["optimizer"]["step"] == 3 and opt["scheduler"] == {"epoch": 1, "global_step": 5}
+        open(os.path.join(out_dir, f"ckpt_ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_checkpoint_written_once_world2(tmp_path):
+    """Rank 0 writes its replica (no gather), every rank leaves save_checkpoint behind the same barrier."""
+    world = 2
+    mp.spawn(_ckpt_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ckpt_ok{r}").exists() for r in range(world))
+    assert len(list((tmp_path / "checkpoints").glob("*.pt"))) == 1
