@@ -114,3 +114,22 @@ def test_training_diffusion_unchanged_by_respacing_support():
     assert d.num_timesteps == 100 and not hasattr(d, "timestep_map")
     with pytest.raises(NotImplementedError):
         create_diffusion(timestep_respacing="10,10", diffusion_steps=100)
+
+
+def test_prompt_builder_matches_reference_when_available():
+    """The one-turn prompt of predict_action_diff (model_mla.py:627-631) through our PurePromptBuilder vs the
+    reference's (models/backbones/llm/prompting/base_prompter.py) — only where /root/reference exists."""
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    ref_shim.load()
+    from models.backbones.llm.prompting import PurePromptBuilder as Ref
+    from mla_b200.backbone import PurePromptBuilder as Ours
+    for text in ("close the jar", "  put <image> the rubbish in bin ", "stack 2 blocks"):
+        msg = f"What action should the robot take to {text.lower()}?"
+        a, b = Ref("prismatic"), Ours("prismatic")
+        assert a.add_turn("human", msg) == b.add_turn("human", msg)
+        assert a.get_prompt() == b.get_prompt()
+        assert a.add_turn("gpt", "ok") == b.add_turn("gpt", "ok")
+        assert a.get_prompt() == b.get_prompt()
+        assert a.get_potential_prompt("next") == b.get_potential_prompt("next")
