@@ -134,3 +134,41 @@ def test_oracle_reproduces_reference_generation_heads():
     assert rel_err(out["alpha_all"], torch.from_numpy(z["alpha_all"])) < 2e-2
     assert rel_err(out["pointcloud_coord_generation"], torch.from_numpy(z["pointcloud_coord_generation"])) < 3e-2
     assert rel_err(out["tactile_generation"], torch.from_numpy(z["tactile_generation"])) < 3e-2
+
+
+@pytest.mark.parametrize("name", ["tiny_img", "tiny_pc"])
+def test_oracle_autograd_reproduces_reference_tokenizer_gradients(name):
+    """Stage "pretrain" (prismatic.py:427-434): the gradients the unmodified reference gives the two tokenizers
+    (tests/golden/pretrain_*.npz, recorded by make_golden_pretrain.py on the forward of the goldens above) against
+    autograd through the oracle in the same bf16-on-CPU arithmetic.  This pins the oracle as the gradient checker of
+    tests/test_tower_bwd_gpu.py."""
+    from oracle import mla as O
+    g = np.load(os.path.join(GOLD, "pretrain_" + name + ".npz"))
+    z, batch = load_case(name)
+    c = case_cfg(name)
+    _, sd = build_state_dict(c)
+    keys = [k[len("gradnorm."):] for k in g.files if k.startswith("gradnorm.")]
+    assert keys and all(k.startswith(("vlm.vision_tower_2d.", "vlm.vision_tower_3d.")) for k in keys)
+    sd = dict(sd)
+    for k in keys:
+        sd[k] = sd[k].clone().requires_grad_(True)
+    out = O.forward(sd, batch, oracle_cfg(c), draws_of(z), compute_dtype=torch.bfloat16, flavor="cpu")
+    assert abs(float(out["total_loss"]) - float(g["total_loss"])) <= 2e-3 * abs(float(g["total_loss"]))
+    out["total_loss"].backward()
+    gmax = max(float(g["gradnorm." + k]) for k in keys)
+    worst = 0.0
+    for k in keys:
+        ref_norm = float(g["gradnorm." + k])
+        got = sd[k].grad
+        assert got is not None, k
+        if ref_norm < 1e-4 * gmax:            # conv bias in front of a train-mode BatchNorm: identically zero gradient
+            assert float(got.float().norm()) < 2e-3 * gmax, k
+            continue
+        assert abs(float(got.float().norm()) - ref_norm) <= 0.1 * ref_norm, (k, float(got.float().norm()), ref_norm)
+        if "grad." + k in g.files:
+            e = rel_err(got.float(), torch.from_numpy(g["grad." + k]))
+            worst = max(worst, e)
+            assert e < 0.15, (k, e)           # two bf16 backward passes through the same graph (different op kernels)
+    # parameters the reference leaves without a gradient (GlobalAttention, class/split embeddings, cls_token, pos_embed)
+    for k in g["params_without_grad"].tolist():
+        assert k not in keys
