@@ -76,6 +76,13 @@ typedef struct mla_gemm_args {
   const void* rope_sin;
   int32_t rope_seq;
   int32_t rope_cols;
+  /* Fused SwiGLU for the gate|up projection (LlamaMLP, modeling_llama.py:240; CTA-pair kernel): B = [gate; up] stored
+   * [2f, K], f a multiple of 128.  swiglu_out bf16 [M, f] (pitch ld_swiglu) receives bf16(bf16(silu(gate)) * up); c
+   * (the [M, 2f] gate|up matrix backward wants) is then optional — NULL skips its store.  NULL swiglu_out = off.
+   * EXPERIMENTAL in round 1: built and exercised by tests/test_gemm2_gpu.py only under MLA_EXPERIMENTAL=1; the training
+   * step uses it only with MLA_FUSE_SWIGLU=1. */
+  void* swiglu_out;
+  int64_t ld_swiglu;
 } mla_gemm_args;
 int mla_gemm_bf16(const mla_gemm_args* args, void* stream);
 /* Kernel selection for mla_gemm_bf16: 0 = one CTA per 128x256 tile, 1 = CTA pairs (tcgen05.mma.cta_group::2, 256x256

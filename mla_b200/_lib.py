@@ -26,6 +26,7 @@ class GemmArgs(C.Structure):
         ("bias", C.c_void_p), ("residual", C.c_void_p), ("ldr", C.c_int64),
         ("pre_act", C.c_void_p), ("ldp", C.c_int64), ("sched_ws", C.c_void_p),
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_seq", C.c_int32), ("rope_cols", C.c_int32),
+        ("swiglu_out", C.c_void_p), ("ld_swiglu", C.c_int64),
     ]
 
 

@@ -118,7 +118,9 @@ __device__ __forceinline__ void tile_coords2(int tile, int tiles_m, int tiles_n,
   tn = r / gm;
 }
 
-template <int A_MN, int B_MN>
+// SWIGLU = 1 (gate|up projection, K-major operands): tile tn = 128 gate columns + the matching 128 up columns — the
+// peer CTA's half of the B panel is fetched from the `up` rows — and the epilogue applies SwiGLU (gemm_epilogue.cuh).
+template <int A_MN, int B_MN, int SWIGLU = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
                   int K, int group_m, int* sched, GemmEpilogue ep) {
@@ -141,7 +143,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
   const int tiles_m = (M + 2 * G2_BM - 1) / (2 * G2_BM);
-  const int tiles_n = (N + G2_BN - 1) / G2_BN;
+  const int tiles_n = SWIGLU ? ep.swiglu_f / G2_BNH : (N + G2_BN - 1) / G2_BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + G2_BK - 1) / G2_BK;
 
@@ -203,7 +205,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         int tm, tn;
         tile_coords2(tile, tiles_m, tiles_n, group_m, tm, tn);
         const int m0 = tm * 2 * G2_BM + int(rank) * G2_BM;
-        const int n0 = tn * G2_BN + int(rank) * G2_BNH;
+        const int n0 = SWIGLU ? tn * G2_BNH + int(rank) * ep.swiglu_f : tn * G2_BN + int(rank) * G2_BNH;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * G2_STAGE_BYTES;
@@ -299,7 +301,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + acc * G2_BN;
-      gemm_store_tile(ep, taddr, row, n0, M, N);
+      if constexpr (SWIGLU) gemm_store_tile_swiglu(ep, taddr, row, tn, M);
+      else gemm_store_tile(ep, taddr, row, n0, M, N);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));
@@ -339,17 +342,17 @@ static int encode_operand_map2(CUtensorMap* map, const void* ptr, int mn_major, 
   return encode_tmap_2d_bf16(map, ptr, dims, strides, box);
 }
 
-template <int A_MN, int B_MN>
+template <int A_MN, int B_MN, int SWIGLU = 0>
 static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const GemmEpilogue& ep,
                         int* sched, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kern = gemm2_bf16_kernel<A_MN, B_MN>;
+  auto kern = gemm2_bf16_kernel<A_MN, B_MN, SWIGLU>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES);
     if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "cudaFuncSetAttribute(gemm2 smem): %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int tiles = ((M + 2 * G2_BM - 1) / (2 * G2_BM)) * ((N + G2_BN - 1) / G2_BN);
+  const int tiles = ((M + 2 * G2_BM - 1) / (2 * G2_BM)) * (SWIGLU ? ep.swiglu_f / G2_BNH : (N + G2_BN - 1) / G2_BN);
   const int max_clusters = num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   int group_m = int((48ll << 20) / (int64_t(2 * G2_BM) * K * 2));
@@ -369,6 +372,7 @@ int gemm2_dispatch(const mla_gemm_args* g, const GemmEpilogue& ep, cudaStream_t 
   if (int rc = encode_operand_map2(&mb, g->b, g->b_mn_major, g->n, g->k, g->ldb)) return rc;
   const int M = int(g->m), N = int(g->n), K = int(g->k);
   int* sched = static_cast<int*>(g->sched_ws);
+  if (ep.swiglu_f > 0) return launch_gemm2<0, 0, 1>(ma, mb, M, N, K, ep, sched, stream);   // validated by the caller
   if (!g->a_mn_major && !g->b_mn_major) return launch_gemm2<0, 0>(ma, mb, M, N, K, ep, sched, stream);
   if (!g->a_mn_major && g->b_mn_major) return launch_gemm2<0, 1>(ma, mb, M, N, K, ep, sched, stream);
   if (g->a_mn_major && !g->b_mn_major) return launch_gemm2<1, 0>(ma, mb, M, N, K, ep, sched, stream);

@@ -26,6 +26,10 @@ struct GemmEpilogue {
   const __nv_bfloat16* rope_sin;
   int rope_seq;
   int rope_cols;                   // multiple of 256; 0 = off
+  // fused SwiGLU (CTA-pair kernel only): the tile holds 128 gate columns | the matching 128 up columns
+  __nv_bfloat16* swiglu_out;       // bf16 [M, swiglu_f] = bf16(bf16(silu(gate)) * up)
+  int64_t ld_swiglu;
+  int swiglu_f;                    // columns of gate (= of up); 0 = off
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -83,6 +87,46 @@ __device__ __forceinline__ void gemm_store_tile_rope(const GemmEpilogue& ep, uin
                                                                  pack_bf16x2(o1[4], o1[5]), pack_bf16x2(o1[6], o1[7]));
       *reinterpret_cast<uint4*>(crow + c2 * 32 + j) = make_uint4(pack_bf16x2(o2[0], o2[1]), pack_bf16x2(o2[2], o2[3]),
                                                                  pack_bf16x2(o2[4], o2[5]), pack_bf16x2(o2[6], o2[7]));
+    }
+  }
+}
+
+// SwiGLU epilogue (LlamaMLP, modeling_llama.py:240, fused into the gate|up projection): tile tn of the CTA-pair kernel
+// holds gate columns [128 tn, 128 tn + 128) in TMEM columns 0..127 and the up columns f + the same range in 128..255
+// (the peer CTA's half of the B panel comes from the `up` rows), so chunk c pairs with chunk c + 4.  Rounding points of
+// swiglu_fwd_kernel: projection -> bf16, silu -> bf16, product -> bf16.  c (the gate|up matrix) is optional.
+__device__ __forceinline__ void gemm_store_tile_swiglu(const GemmEpilogue& ep, uint32_t taddr, int64_t row, int tn, int M) {
+  const bool row_ok = row < M;
+  const int g0 = tn * 128;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    uint32_t rg[32], ru[32];
+    tmem_ld_32x32b_x32(taddr + c * 32, rg);
+    tmem_ld_32x32b_x32(taddr + (c + 4) * 32, ru);
+    tmem_ld_wait();
+    if (!row_ok) continue;
+    float g[32], u[32], a[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      g[j] = bf16_round(__uint_as_float(rg[j]) * ep.alpha);
+      u[j] = bf16_round(__uint_as_float(ru[j]) * ep.alpha);
+      a[j] = bf16_round(g[j] * (1.f / (1.f + __expf(-g[j])))) * u[j];
+    }
+    __nv_bfloat16* arow = ep.swiglu_out + row * ep.ld_swiglu + g0 + c * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8)
+      *reinterpret_cast<uint4*>(arow + j) = make_uint4(pack_bf16x2(a[j], a[j + 1]), pack_bf16x2(a[j + 2], a[j + 3]),
+                                                      pack_bf16x2(a[j + 4], a[j + 5]), pack_bf16x2(a[j + 6], a[j + 7]));
+    if (ep.c != nullptr) {
+      __nv_bfloat16* grow = reinterpret_cast<__nv_bfloat16*>(ep.c) + row * ep.ldc + g0 + c * 32;
+      __nv_bfloat16* urow = grow + ep.swiglu_f;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        *reinterpret_cast<uint4*>(grow + j) = make_uint4(pack_bf16x2(g[j], g[j + 1]), pack_bf16x2(g[j + 2], g[j + 3]),
+                                                        pack_bf16x2(g[j + 4], g[j + 5]), pack_bf16x2(g[j + 6], g[j + 7]));
+        *reinterpret_cast<uint4*>(urow + j) = make_uint4(pack_bf16x2(u[j], u[j + 1]), pack_bf16x2(u[j + 2], u[j + 3]),
+                                                        pack_bf16x2(u[j + 4], u[j + 5]), pack_bf16x2(u[j + 6], u[j + 7]));
+      }
     }
   }
 }

@@ -323,6 +323,18 @@ extern "C" int mla_gemm_bf16(const mla_gemm_args* g, void* stream_) {
   ep.rope_cos = static_cast<const __nv_bfloat16*>(g->rope_cos);
   ep.rope_sin = static_cast<const __nv_bfloat16*>(g->rope_sin);
   ep.rope_seq = g->rope_seq; ep.rope_cols = g->rope_cols;
+  ep.swiglu_out = static_cast<__nv_bfloat16*>(g->swiglu_out); ep.ld_swiglu = g->ld_swiglu;
+  ep.swiglu_f = g->swiglu_out ? int(g->n / 2) : 0;
+  if (g->swiglu_out != nullptr) {
+    if (g->a_mn_major || g->b_mn_major || g->c_dtype != 0 || g->bias || g->residual || g->pre_act ||
+        g->activation != MLA_ACT_NONE || g->rope_cols != 0)
+      return set_error(MLA_ERR_ARG, "gemm: fused SwiGLU applies to a plain K-major bf16 gate|up projection");
+    if ((g->n & 255) || (g->ld_swiglu & 7) || (g->c && (g->ldc & 7)) || (reinterpret_cast<uintptr_t>(g->swiglu_out) & 15))
+      return set_error(MLA_ERR_ARG, "gemm: fused SwiGLU needs N = 2f with f a multiple of 128 and 16-byte aligned rows");
+    if (g->m > INT32_MAX) return set_error(MLA_ERR_ARG, "gemm: dims exceed int32");
+    // C (the gate|up matrix itself) is optional here: NULL skips its store
+    return gemm2_dispatch(g, ep, reinterpret_cast<cudaStream_t>(stream_));
+  }
   if (g->rope_cols != 0) {
     if (g->rope_cols < 0 || (g->rope_cols & 255) || g->rope_cols > g->n || g->rope_seq <= 0 || !g->rope_cos || !g->rope_sin)
       return set_error(MLA_ERR_ARG, "gemm: fused RoPE needs rope_cols a multiple of 256 within N, rope_seq > 0 and both tables");

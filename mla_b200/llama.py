@@ -33,6 +33,9 @@ from . import ops
 OVERLAP = {"wgrad": os.environ.get("MLA_WGRAD_STREAM", "0") == "1"}
 _SIDE_STREAMS: dict = {}
 FUSE_ROPE = {"on": os.environ.get("MLA_FUSE_ROPE", "1") == "1"}     # RoPE inside the q|k|v GEMM epilogue (head_dim 128)
+# SwiGLU inside the gate|up GEMM epilogue (CTA-pair kernel; inter % 128 == 0).  EXPERIMENTAL: written at the end of round 1
+# without GPU time left to validate it, so it is OFF unless MLA_FUSE_SWIGLU=1 (tests: MLA_EXPERIMENTAL=1).
+FUSE_SWIGLU = {"on": os.environ.get("MLA_FUSE_SWIGLU", "0") == "1"}
 
 
 def side_stream(device) -> "torch.cuda.Stream":
@@ -197,8 +200,12 @@ class LlamaDecoderLayer(nn.Module):
     def _mlp_half(self, x_mid: torch.Tensor):
         _, _, wgu, wd, _, l2 = self.compute_weights()
         n2 = ops.rmsnorm_fwd(x_mid, l2, self.eps)
-        gu = ops.gemm(n2, wgu)
-        act = ops.swiglu_fwd(gu)
+        if FUSE_SWIGLU["on"] and self.inter % 128 == 0 and n2.shape[0] >= 1024:
+            act = torch.empty((n2.shape[0], self.inter), dtype=torch.bfloat16, device=n2.device)
+            gu = ops.gemm(n2, wgu, swiglu_out=act)
+        else:
+            gu = ops.gemm(n2, wgu)
+            act = ops.swiglu_fwd(gu)
         y = ops.gemm(act, wd, residual=x_mid)
         return n2, gu, act, y
 

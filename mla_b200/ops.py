@@ -40,11 +40,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          out: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16,
          bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, residual: Optional[torch.Tensor] = None,
          pre_act: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = False,
-         rope: Optional[tuple] = None) -> torch.Tensor:
+         rope: Optional[tuple] = None, swiglu_out: Optional[torch.Tensor] = None,
+         store_c: bool = True) -> torch.Tensor:
     """C = epilogue(alpha * A_op @ B_op).
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True);  b: [N,K] (b_mn=False, nn.Linear weight) or [K,N] (b_mn=True).
     rope = (cos [S,64] bf16, sin [S,64] bf16, S, n_cols): rotate the leading n_cols columns (head_dim 128) in the epilogue.
+    swiglu_out (EXPERIMENTAL, see include/mla_b200.h): bf16 [M, N/2] receiving SwiGLU of the [gate | up] projection in
+    the epilogue; with store_c=False the projection itself is not written (returns None).
     """
     _req(a, torch.bfloat16, "a")
     _req(b, torch.bfloat16, "b")
@@ -54,15 +57,18 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
     if K != Kb:
         raise _lib.MlaError(f"gemm: contraction mismatch {K} vs {Kb}")
-    if out is None:
-        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    if swiglu_out is not None and not store_c:
+        out, ldc = None, N
     else:
-        if tuple(out.shape) != (M, N):
-            raise _lib.MlaError(f"gemm: out shape {tuple(out.shape)} != {(M, N)}")
-        out_dtype = out.dtype
-    ldc = _rowmajor_2d(out, "out")
+        if out is None:
+            out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+        else:
+            if tuple(out.shape) != (M, N):
+                raise _lib.MlaError(f"gemm: out shape {tuple(out.shape)} != {(M, N)}")
+            out_dtype = out.dtype
+        ldc = _rowmajor_2d(out, "out")
     g = GemmArgs()
-    g.a, g.b, g.c = a.data_ptr(), b.data_ptr(), out.data_ptr()
+    g.a, g.b, g.c = a.data_ptr(), b.data_ptr(), (out.data_ptr() if out is not None else None)
     g.m, g.n, g.k = M, N, K
     g.lda, g.ldb, g.ldc = lda, ldb, ldc
     g.a_mn_major, g.b_mn_major = int(a_mn), int(b_mn)
@@ -88,6 +94,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         if tuple(cos_t.shape) != (seq, 64) or tuple(sin_t.shape) != (seq, 64) or not (cos_t.is_contiguous() and sin_t.is_contiguous()):
             raise _lib.MlaError("gemm: fused RoPE needs contiguous [seq, 64] tables (head_dim 128)")
         g.rope_cos, g.rope_sin, g.rope_seq, g.rope_cols = cos_t.data_ptr(), sin_t.data_ptr(), seq, ncols
+    if swiglu_out is not None:
+        _req(swiglu_out, torch.bfloat16, "swiglu_out")
+        if tuple(swiglu_out.shape) != (M, N // 2):
+            raise _lib.MlaError(f"gemm: swiglu_out shape {tuple(swiglu_out.shape)} != {(M, N // 2)}")
+        g.swiglu_out, g.ld_swiglu = swiglu_out.data_ptr(), _rowmajor_2d(swiglu_out, "swiglu_out")
     if DYNAMIC_TILES["on"]:
         g.sched_ws = _sched_ws(a.device).data_ptr()
     check(_lib.lib().mla_gemm_bf16(C.byref(g), _stream()))

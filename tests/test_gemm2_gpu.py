@@ -104,3 +104,24 @@ def test_fused_rope_epilogue(cuda_lib, mode):
         assert torch.equal(got, want)
     finally:
         cuda_lib.mla_gemm_set_mode(C.c_int32(1))
+
+
+@pytest.mark.skipif(__import__("os").environ.get("MLA_EXPERIMENTAL") != "1",
+                    reason="SwiGLU-in-epilogue was written without GPU time left to validate it (round 1): opt-in")
+@pytest.mark.parametrize("M,f,K", [(1024, 256, 512), (3000, 1408, 1024), (17536, 11008, 4096)])
+def test_fused_swiglu_epilogue_matches_unfused(cuda_lib, M, f, K):
+    """gate|up projection with SwiGLU in the CTA-pair epilogue == projection followed by swiglu_fwd, bit for bit."""
+    import torch
+    from mla_b200 import ops
+    torch.manual_seed(M)
+    x = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(2 * f, K, device="cuda") * K ** -0.5).to(torch.bfloat16)
+    gu_ref = ops.gemm(x, w)
+    act_ref = ops.swiglu_fwd(gu_ref)
+    act = torch.empty((M, f), dtype=torch.bfloat16, device="cuda")
+    gu = ops.gemm(x, w, swiglu_out=act)
+    assert torch.equal(gu, gu_ref)
+    assert torch.equal(act, act_ref)
+    act2 = torch.empty_like(act)
+    assert ops.gemm(x, w, swiglu_out=act2, store_c=False) is None
+    assert torch.equal(act2, act_ref)
