@@ -55,3 +55,37 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_ctypes_structs_match_header(tmp_path):
+    """The argument structs crossing the C ABI: size and every field offset of the ctypes mirrors (mla_b200/_lib.py)
+    equal what a C compiler derives from include/mla_b200.h."""
+    import shutil
+    import subprocess
+    from mla_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    pairs = {"mla_gemm_args": _lib.GemmArgs, "mla_attn_args": _lib.AttnArgs, "mla_mha_args": _lib.MhaArgs,
+             "mla_gen_image_args": _lib.GenImageArgs, "mla_gemv_args": _lib.GemvArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "mla_b200.h")}"',
+             'int main(void) {']
+    for cname, ct in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    r = subprocess.run([gcc, "-std=c11", "-o", str(exe), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr          # also proves the header is plain C and names every mirrored field
+    out = subprocess.run([str(exe)], capture_output=True, text=True).stdout
+    want = {}
+    for line in out.splitlines():
+        s, f, v = line.split()
+        want[(s, f)] = int(v)
+    for cname, ct in pairs.items():
+        assert ctypes.sizeof(ct) == want[(cname, "size")], cname
+        for fname, _ in ct._fields_:
+            assert getattr(ct, fname).offset == want[(cname, fname)], (cname, fname)
