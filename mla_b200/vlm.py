@@ -38,13 +38,13 @@ class PrismaticVLM(nn.Module):
                  past_action_window_size: int = 0, class_dropout_prob: float = 0.0, norm_stats=None,
                  use_diff: bool = False, use_pointcloud: bool = False, use_tactile: bool = False,
                  use_contrastive: bool = False, llm_vision_layers: int = 1, use_generation: bool = True,
-                 gen_image: bool = False, gen_pointcloud: bool = True, gen_tactile: bool = True,
-                 use_roi: bool = False, image_hidden_dim: int = 1024, num_image_gen_queries: int = 128,
-                 image_decoder_layers: int = 3, image_decoder_heads: int = 8, image_patch_size: int = 42,
-                 roi_dilation_kernel_size: int = 3, pointcloud_trans_dim: int = 1024,
-                 pointcloud_decoder_layers: int = 4, pointcloud_decoder_heads: int = 8, pointcloud_group_size: int = 8,
-                 pointcloud_num_groups: int = 128, tactile_decoder_layers: int = 2, tactile_decoder_heads: int = 4,
-                 **kwargs) -> None:
+                 gen_image: bool = False, num_image_gen_queries: int = 128, image_decoder_layers: int = 3,
+                 image_decoder_heads: int = 8, image_patch_size: int = 42, use_roi: bool = False,
+                 roi_dilation_kernel_size: int = 3, gen_pointcloud: bool = True, gen_tactile: bool = True,
+                 pointcloud_trans_dim: int = 1024, pointcloud_decoder_layers: int = 4, pointcloud_decoder_heads: int = 8,
+                 pointcloud_group_size: int = 8, pointcloud_num_groups: int = 128, tactile_decoder_layers: int = 2,
+                 tactile_decoder_heads: int = 4, image_hidden_dim: int = 1024, **kwargs) -> None:
+        # positional order = the reference's (prismatic.py:149-185); image_hidden_dim (hard-coded 1024 there, :219) is ours
         super().__init__()
         self.model_family, self.model_id = "prismatic", model_id
         self.llm_backbone = llm_backbone

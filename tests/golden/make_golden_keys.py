@@ -35,6 +35,20 @@ def main():
                                "requires_grad": sorted(k for k, p in mla.named_parameters() if p.requires_grad)}
         rec[name] = r
         print(name, len(r["state_dict"]), "keys", {s: len(v["requires_grad"]) for s, v in r["stages"].items()})
+    import inspect
+
+    def sig(fn):
+        out = []
+        for n, p in inspect.signature(fn).parameters.items():
+            d = p.default
+            d = None if d is inspect.Parameter.empty else (d if isinstance(d, (int, float, bool, str, type(None))) else repr(d))
+            out.append([n, str(p.kind).split(".")[-1], p.default is not inspect.Parameter.empty, d])
+        return out
+    rec["__signatures__"] = {"MLA.__init__": sig(ns.MLA.__init__), "MLA.forward": sig(ns.MLA.forward),
+                             "PrismaticVLM.__init__": sig(ns.PrismaticVLM.__init__),
+                             "PrismaticVLM.forward": sig(ns.PrismaticVLM.forward),
+                             "MLA.predict_action_diff": sig(ns.MLA.predict_action_diff),
+                             "MLA.create_ddim": sig(ns.MLA.create_ddim)}
     json.dump(rec, open(os.path.join(OUT, "state_dict_keys.json"), "w"), indent=0, sort_keys=True)
     print("wrote", os.path.getsize(os.path.join(OUT, "state_dict_keys.json")), "bytes")
 

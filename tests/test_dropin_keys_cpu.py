@@ -12,6 +12,7 @@ import torch
 from test_oracle_vs_golden import GOLD, build_state_dict, case_cfg
 
 REC = json.load(open(os.path.join(GOLD, "state_dict_keys.json")))
+SIGS = REC.pop("__signatures__")
 
 
 @pytest.mark.parametrize("name", sorted(REC))
@@ -32,3 +33,36 @@ def test_state_dict_and_stage_contract(name):
         got = sorted(k for k, p in mla.named_parameters() if p.requires_grad)
         assert got == want["requires_grad"], (stage, sorted(set(got) ^ set(want["requires_grad"]))[:8])
         assert list(mla.trainable_module_keys) == want["trainable_module_keys"], stage
+
+
+# parameters we add on purpose (always after the reference's, keyword-only in practice)
+EXTRAS = {"PrismaticVLM.__init__": {"image_hidden_dim"}, "PrismaticVLM.forward": {"image_repeat"},
+          "MLA.predict_action_diff": {"camera_name", "use_kv_cache"}}
+# defaults we relax on purpose: the benches build MLA without an action tokenizer
+RELAXED = {("MLA.__init__", "action_tokenizer")}
+
+
+@pytest.mark.parametrize("what", sorted(SIGS))
+def test_call_signatures_match_reference(what):
+    """Same parameter names, same positional order, same defaults as the reference's MLA / PrismaticVLM entry points
+    (a caller that passes positionally or by keyword lands on the same parameter); our few extras come last."""
+    import inspect
+    from mla_b200 import MLA, PrismaticVLM
+    fn = {"MLA.__init__": MLA.__init__, "MLA.forward": MLA.forward, "PrismaticVLM.__init__": PrismaticVLM.__init__,
+          "PrismaticVLM.forward": PrismaticVLM.forward, "MLA.predict_action_diff": MLA.predict_action_diff,
+          "MLA.create_ddim": MLA.create_ddim}[what]
+    ours = inspect.signature(fn).parameters
+    ref = SIGS[what]
+    ref_names = [r[0] for r in ref if r[1] not in ("VAR_KEYWORD", "VAR_POSITIONAL")]
+    our_names = [n for n, p in ours.items() if p.kind not in (p.VAR_KEYWORD, p.VAR_POSITIONAL)]
+    extras = [n for n in our_names if n not in ref_names]
+    assert set(extras) <= EXTRAS.get(what, set()), extras
+    assert our_names[:len(ref_names)] == ref_names                       # identical positional order, extras after
+    for name, _kind, has_default, default in ref:
+        if name not in ours or (what, name) in RELAXED:
+            continue
+        p = ours[name]
+        assert (p.default is not inspect.Parameter.empty) == has_default, (what, name)
+        if has_default and isinstance(default, (int, float, bool, str, type(None))) and not isinstance(p.default, type(inspect)):
+            if isinstance(p.default, (int, float, bool, str, type(None))):
+                assert p.default == default, (what, name, p.default, default)
