@@ -53,9 +53,9 @@ class LlamaConfig:
 class CausalLMOutputWithPast:
     """transformers/modeling_outputs.py:706-713 (the reference's three extra fields included)."""
     loss: Optional[torch.Tensor] = None
-    logits: Optional[torch.Tensor] = None
     img_pc_contrastive_loss: Optional[torch.Tensor] = None
     tactile_contrastive_loss: Optional[torch.Tensor] = None
+    logits: Optional[torch.Tensor] = None
     all_logits_for_action: Optional[torch.Tensor] = None
     past_key_values: Any = None
     hidden_states: Optional[Tuple[torch.Tensor, ...]] = None

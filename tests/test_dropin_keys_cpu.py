@@ -66,3 +66,12 @@ def test_call_signatures_match_reference(what):
         if has_default and isinstance(default, (int, float, bool, str, type(None))) and not isinstance(p.default, type(inspect)):
             if isinstance(p.default, (int, float, bool, str, type(None))):
                 assert p.default == default, (what, name, p.default, default)
+
+
+def test_output_type_fields_match_reference():
+    """CausalLMOutputWithPast with the reference's three extra fields, in its order (transformers/modeling_outputs.py:706-713)."""
+    import dataclasses
+    from mla_b200 import CausalLMOutputWithPast
+    assert [f.name for f in dataclasses.fields(CausalLMOutputWithPast)] == [
+        "loss", "img_pc_contrastive_loss", "tactile_contrastive_loss", "logits", "all_logits_for_action",
+        "past_key_values", "hidden_states", "attentions"]
