@@ -102,6 +102,47 @@ class LlamaForCausalLM(nn.Module):
     def get_input_embeddings(self):
         return self.model.embed_tokens
 
+    @property
+    def generation_config(self):
+        """What VLM.generation_config hands to GenerationMixin (models/vlm/base_vlm.py:49): the special-token ids."""
+        from types import SimpleNamespace
+        c = self.config
+        return SimpleNamespace(bos_token_id=c.bos_token_id, eos_token_id=c.eos_token_id, pad_token_id=c.pad_token_id)
+
+    def resize_token_embeddings(self, new_num_tokens: Optional[int] = None, pad_to_multiple_of: Optional[int] = None):
+        """transformers' PreTrainedModel.resize_token_embeddings as scripts/train.py:143-144 and llama2.py:75-77 use it:
+        grow (or shrink) embed_tokens and lm_head to `new_num_tokens` rounded up to `pad_to_multiple_of`, keeping the
+        existing rows; new rows ~ N(0, initializer_range) (train.py:145-155 then overwrites them with the mean row).
+        Updates config.vocab_size and returns the input embedding module."""
+        emb, head = self.model.embed_tokens, self.lm_head
+        if new_num_tokens is None:
+            return emb
+        if pad_to_multiple_of is not None:
+            if not isinstance(pad_to_multiple_of, int) or pad_to_multiple_of <= 0:
+                raise ValueError(f"pad_to_multiple_of must be a positive integer, got {pad_to_multiple_of}")
+            new_num_tokens = (new_num_tokens + pad_to_multiple_of - 1) // pad_to_multiple_of * pad_to_multiple_of
+        old = emb.weight.shape[0]
+        if new_num_tokens == old:
+            return emb
+        keep = min(old, new_num_tokens)
+        std = self.config.initializer_range
+        new_emb = nn.Embedding(new_num_tokens, emb.weight.shape[1], emb.padding_idx, device=emb.weight.device,
+                               dtype=emb.weight.dtype)
+        new_head = nn.Linear(head.in_features, new_num_tokens, bias=False, device=head.weight.device,
+                             dtype=head.weight.dtype)
+        with torch.no_grad():
+            new_emb.weight.normal_(mean=0.0, std=std)
+            new_head.weight.normal_(mean=0.0, std=std)
+            if new_emb.padding_idx is not None and new_emb.padding_idx < new_num_tokens:
+                new_emb.weight[new_emb.padding_idx].zero_()
+            new_emb.weight[:keep] = emb.weight[:keep]
+            new_head.weight[:keep] = head.weight[:keep]
+        new_emb.weight.requires_grad_(emb.weight.requires_grad)
+        new_head.weight.requires_grad_(head.weight.requires_grad)
+        self.model.embed_tokens, self.lm_head = new_emb, new_head
+        self.config.vocab_size = self.vocab_size = new_num_tokens
+        return new_emb
+
     def get_output_embeddings(self):
         return self.lm_head
 

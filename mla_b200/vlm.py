@@ -115,6 +115,11 @@ class PrismaticVLM(nn.Module):
         self._err_flag = None
 
     # ------------------------------------------------------------------ reference API surface
+    @property
+    def device(self) -> torch.device:
+        """base_vlm.py:46-48: the device of the first parameter."""
+        return next(self.parameters()).device
+
     def get_prompt_builder(self, system_prompt: Optional[str] = None):
         """prismatic.py:411-413."""
         return self.llm_backbone.prompt_builder_fn(self.model_family, system_prompt=system_prompt)

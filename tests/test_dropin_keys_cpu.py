@@ -75,3 +75,35 @@ def test_output_type_fields_match_reference():
     assert [f.name for f in dataclasses.fields(CausalLMOutputWithPast)] == [
         "loss", "img_pc_contrastive_loss", "tactile_contrastive_loss", "logits", "all_logits_for_action",
         "past_key_values", "hidden_states", "attentions"]
+
+
+def test_embedding_resize_like_train_py():
+    """scripts/train.py:132-155 (smart_tokenizer_and_embedding_resize): add <BOD>/<EOD>, resize with
+    pad_to_multiple_of=64, then overwrite the new rows with the mean row — on our LlamaForCausalLM."""
+    from mla_b200 import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(vocab_size=32001, hidden_size=32, intermediate_size=64, num_hidden_layers=1, num_attention_heads=4)
+    llm = LlamaForCausalLM(cfg)
+    with torch.no_grad():
+        llm.model.embed_tokens.weight.normal_()
+        llm.lm_head.weight.normal_()
+    e0, h0 = llm.get_input_embeddings().weight.detach().clone(), llm.get_output_embeddings().weight.detach().clone()
+    out = llm.resize_token_embeddings(32003, pad_to_multiple_of=64)
+    assert out is llm.get_input_embeddings()
+    assert llm.get_input_embeddings().weight.shape == (32064, 32) and llm.lm_head.weight.shape == (32064, 32)
+    assert llm.config.vocab_size == 32064 and llm.lm_head.in_features == 32
+    assert torch.equal(llm.get_input_embeddings().weight[:32001], e0) and torch.equal(llm.lm_head.weight[:32001], h0)
+    assert llm.get_input_embeddings().weight.requires_grad and llm.get_input_embeddings().weight.dtype == torch.float32
+    n_new = 2
+    ie, oe = llm.get_input_embeddings().weight.data, llm.get_output_embeddings().weight.data
+    ie[-n_new:] = ie[:-n_new].mean(dim=0, keepdim=True)
+    oe[-n_new:] = oe[:-n_new].mean(dim=0, keepdim=True)
+    assert llm.resize_token_embeddings(32064) is llm.get_input_embeddings()            # no-op at the same size
+    assert llm.resize_token_embeddings(None) is llm.get_input_embeddings()
+    g = llm.generation_config
+    assert (g.bos_token_id, g.eos_token_id, g.pad_token_id) == (1, 2, cfg.pad_token_id)
+
+
+def test_vlm_device_property():
+    c = case_cfg("tiny_img")
+    mla, _ = build_state_dict(c, dtype=torch.float32)
+    assert mla.vlm.device == torch.device("cpu")
