@@ -18,7 +18,12 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("MLA_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# /root/reference in the build container; on the GPU box (where that path does not exist) the git-ignored install of
+# the same unmodified sources under baseline/_ref (tools/install_reference.py)
+REF_ROOT = os.environ.get("MLA_REFERENCE_ROOT") or next(
+    (p for p in ("/root/reference", os.path.join(_HERE, "baseline", "_ref")) if os.path.isdir(os.path.join(p, "models", "mla"))),
+    "/root/reference")
 
 
 def available() -> bool:
