@@ -2,11 +2,14 @@
 """Benchmark of the MLA training step (BASELINE.json metric: multimodal tokens/s, Llama-2-7B MLA, bf16).
 
     python bench.py --gpus 1 --steps K --warmup W            # our CUDA path (one process per GPU under torchrun for N>1)
-    python bench.py --impl reference ...                     # the reference algorithm on the host CPU (oracle port)
+    python bench.py --impl reference ...                     # the UNMODIFIED reference's own code on the host CPU cores
 
-A step = forward + backward + gradient all-reduce (N>1) + clip + AdamW of one synthetic batch:
-workload "cfg2" = BASELINE configs[1]: Llama-2-7B MLA, image-only tokens + 32 text tokens, per-GPU batch 8 x 4
+A step = forward + backward + gradient all-reduce (N>1) + clip + AdamW of one synthetic batch, per-GPU batch 8 x 4
 diffusion repeats = 32 sequences of 548 tokens (17,536 multimodal tokens per GPU per step), random-init weights.
+Default workload: N = 1 -> "cfg2" = BASELINE configs[1] (Llama-2-7B MLA, image-only tokens + 32 text tokens) as the
+headline, with BASELINE configs[2] ("cfg3": + point cloud + tactile + both InfoNCE losses) measured in the same run
+and reported under "also"; N > 1 -> "cfg4" = BASELINE configs[3], the full configuration under DDP (cfg3's flags,
+global batch 8 N).  `--workload` overrides.
 `value` is timed with the batch already resident in HBM; `e2e` times the same step through the public module call
 with the batch in pinned host memory (H2D inside the timed region) and a D2H read of the loss every step.
 """
@@ -30,6 +33,8 @@ WORKLOADS = {
     # name: (use_pointcloud, use_tactile, use_contrastive, description)
     "cfg2": (False, False, False, "MLA Llama2-7B, image-only (672x672 patchified -> 256 tokens) + 32 text toks, bs=8 x 4 repeats"),
     "cfg3": (True, True, True, "MLA Llama2-7B, image+pointcloud+tactile alignment + contrastive loss, bs=8 x 4 repeats"),
+    # BASELINE configs[3]: the full configuration (use_pointcloud + contrastive + diffusion head) under DDP, global bs = 8 N
+    "cfg4": (True, True, True, "MLA Llama2-7B full (pointcloud+tactile+contrastive+diffusion head), DDP, per-GPU bs=8 x 4 repeats"),
     # BASELINE configs[4]: post-training (gen_img + gen_pc + use_roi), 14 camera views -> 3876 fused tokens per sequence
     "cfg5": (True, True, True, "MLA post-training (gen_image+gen_pointcloud+use_roi), 14 views -> seq 3876, bs=1 x 4 repeats"),
 }
@@ -172,12 +177,57 @@ def gemm_roofline(tokens: int, peak_tf: float, iters: int = 5):
             "launch_ms_avg": round(ms / len(calls), 4)}
 
 
-def cpu_baseline(sample_layers: int = 2, threads: int = 0):
-    """The reference algorithm (oracle port) on the host cores: fp32, a `sample_layers`-layer slice of the 7B decoder
-    at full width on one sequence (B=1, R=1, S=548), forward+backward; tokens/s extrapolated to 32 layers."""
-    from oracle import llama as O
+def reference_cpu(steps: int, warmup: int, layers_cpu: int = 4, threads: int = 0, workload: str = "cfg2"):
+    """The reference's OWN code on the host cores — `MLA.forward` + backward of the UNMODIFIED reference
+    (models/mla/model_mla.py:118, imported from baseline/_ref or /root/reference through oracle/ref_shim.py; vendored
+    transformers 4.40.1 Llama with SDPA attention: flash-attn has no CPU path), fp32 parameters under
+    autocast(cpu, bf16) as scripts/train.py builds them, all host threads.
+    Bounded sample of the workload: ONE of the step's 32 sequences (per-GPU batch 1 x 1 diffusion repeat = 548 fused
+    tokens) through a model with the first `layers_cpu` of the 32 decoder layers (everything else — tokenizers,
+    embedders, lm_head + CE, diffusion head, loss — at full size).  Every timed step is executed; the reported rate
+    is tokens x (layers_cpu / 32) / measured seconds, i.e. normalised to the full depth (the decoder is 97 % of the
+    FLOPs and linear in depth; the non-decoder parts are counted 32/layers_cpu times too often, which favours us by
+    a few percent and is stated here).  One full-depth step measured on the same host class is committed under
+    profiles/r02_ref_cpu_fulldepth.json.  Falls back to the oracle port when no reference tree is present."""
+    import contextlib
+    import io
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
+    from oracle import ref_shim
+    S = 548
+    if not ref_shim.available():
+        return _port_cpu(steps, warmup, threads)
+    from oracle.ref_model import build_reference_7b, ref_call
+    from mla_b200.synthetic import make_batch
+    use_pc = WORKLOADS[workload][0]
+    quiet = contextlib.redirect_stdout(io.StringIO())        # the reference prints its loss dict every forward
+    with quiet, contextlib.redirect_stderr(io.StringIO()):
+        mla, _ = build_reference_7b(workload, layers_cpu, torch.float32, "cpu", "sdpa")
+    batch = make_batch(1, 32, 0, 672, 1024, seed=1234, use_pointcloud=use_pc, use_tactile=use_pc)
+    params = [p for p in mla.parameters() if p.requires_grad]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        with quiet:
+            loss = ref_call(mla, batch, "cpu", repeats=1)
+        loss.backward()
+        for p in params:
+            p.grad = None
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    per_step = sum(times) / len(times)
+    value = S * (layers_cpu / L) / per_step
+    return {"value": round(value, 3), "unit": "tokens/s", "cores": threads, "kind": "reference",
+            "sample": f"unmodified reference MLA.forward+backward on CPU (fp32 params, autocast bf16, SDPA), 1 sequence x "
+                      f"{S} tokens through {layers_cpu} of {L} decoder layers at 7B width, {len(times)} timed steps of "
+                      f"{per_step:.2f} s each; rate normalised by depth ({layers_cpu}/{L}); full-depth check: "
+                      f"profiles/r02_ref_cpu_fulldepth.json",
+            "seconds_per_sample_step": round(per_step, 3), "layers_cpu": layers_cpu, "tokens_per_sample_step": S}
+
+
+def _port_cpu(steps: int, warmup: int, threads: int, sample_layers: int = 2):
+    """Fallback when the reference tree is absent: the oracle port (fp32 restatement) of the decoder."""
+    from oracle import llama as O
     S = 548
     g = torch.Generator().manual_seed(0)
     layers = []
@@ -189,34 +239,63 @@ def cpu_baseline(sample_layers: int = 2, threads: int = 0):
         layers.append(d)
     norm = torch.ones(H, requires_grad=True)
     x = torch.randn(1, S, H, generator=g) * 0.02
-    t0 = time.perf_counter()
-    hs = O.decoder(x, layers, norm, HEADS, 1e-5, None)
-    hs[-1].square().mean().backward()
-    dt = time.perf_counter() - t0
-    full = dt * (L / sample_layers)
-    return {"value": round(S / full, 3), "unit": "tokens/s", "cores": threads, "kind": "port",
-            "sample": f"oracle (fp32 PyTorch restatement) fwd+bwd of a {sample_layers}-layer slice of the 7B decoder, "
-                      f"1 sequence x 548 tokens, {dt:.1f} s measured, extrapolated x{L // sample_layers} to 32 layers",
-            "seconds_measured": round(dt, 2)}
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        hs = O.decoder(x, layers, norm, HEADS, 1e-5, None)
+        hs[-1].square().mean().backward()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    per_step = sum(times) / len(times)
+    return {"value": round(S * (sample_layers / L) / per_step, 3), "unit": "tokens/s", "cores": threads, "kind": "port",
+            "sample": f"oracle port (fp32 restatement) of a {sample_layers}-layer slice of the 7B decoder, 1 sequence x {S} "
+                      f"tokens, {len(times)} timed steps of {per_step:.2f} s, rate normalised by depth",
+            "seconds_per_sample_step": round(per_step, 3), "layers_cpu": sample_layers, "tokens_per_sample_step": S}
 
 
-def run_ours(args):
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
+def cpu_baseline_subprocess(workload: str):
+    """cpu_baseline leg of our arm: the reference arm's sample (1 warm-up + 3 timed steps) in a child process, so the
+    import shim of the reference (it shadows `transformers`) never shares an interpreter with the product path."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
+           "--workload", workload]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="", RANK="0", WORLD_SIZE="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    for line in reversed(r.stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)["cpu_baseline"]
+    raise RuntimeError((r.stderr or r.stdout)[-300:])
+
+
+def reference_gpu_record():
+    """R-GPU: the unmodified reference (PyTorch + flash-attn 2.8.3) on one B200, measured by tools/ref_gpu.py this round
+    and committed under profiles/ — a recorded number, not re-measured in this run."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_ref_gpu_cfg2.json")))
+        runs = {r["variant"].split(":")[0].split(",")[0] + (" ckpt" if r.get("activation_checkpointing") else " no-ckpt"): r
+                for r in d["runs"]}
+        full = next(r for r in d["runs"] if "step_ms" in r)
+        fb = next(r for r in d["runs"] if "fwd_bwd_ms" in r and r["activation_checkpointing"])
+        return {"source": "profiles/r02_ref_gpu_cfg2.json (tools/ref_gpu.py step, recorded, same B200 pool)",
+                "workload": d["workload"], "attn": f"flash_attn {d['flash_attn']}", "step_ms": full["step_ms"],
+                "tokens_per_s": full["tokens_per_s"], "fwd_ms": fb["fwd_ms"], "fwd_bwd_ms_checkpointed": fb["fwd_bwd_ms"],
+                "fwd_bwd_ms_no_checkpointing": next((r["fwd_bwd_ms"] for r in d["runs"] if "fwd_bwd_ms" in r
+                                                     and not r["activation_checkpointing"]), None)}
+    except Exception:
+        return None
+
+
+def measure_ours(args, workload: str, world: int, rank: int, local: int, with_breakdown: bool):
+    """Builds the drop-in module for `workload`, runs warm-up + timed steps (device-resident and end-to-end), frees it.
+    Returns the measurements of this workload (identical on every rank: times are max-reduced over ranks)."""
     import torch.distributed as dist
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from mla_b200 import _lib
     from mla_b200.synthetic import batch_bytes, make_batch, map_tensors
     from mla_b200.trainer import DataParallelTrainer, plan_save_levels
-    _lib.check(_lib.lib().mla_device_check())
 
-    use_pc, use_tac, _, desc = WORKLOADS[args.workload]
-    B, R, Lt, T = (args.batch or DEFAULT_BATCH.get(args.workload, 8)), 4, 32, 0
-    views = EXTRA_VIEWS.get(args.workload, 0)
-    mla = build_model(args.workload, T, args.stage)
+    use_pc, use_tac, _, desc = WORKLOADS[workload]
+    B, R, Lt, T = (args.batch or DEFAULT_BATCH.get(workload, 8)), 4, 32, 0
+    views = EXTRA_VIEWS.get(workload, 0)
+    mla = build_model(workload, T, args.stage)
     trainer = DataParallelTrainer(mla, lr=2e-5, weight_decay=0.0, max_grad_norm=1.0)
     S = 1 + 256 + 256 * (1 + views) + 1 + (Lt - 1) + 1 + 1 + (T + 1)
     tokens = B * R * S
@@ -227,17 +306,20 @@ def run_ours(args):
     mla.vlm.llm_backbone.llm.model.set_save_levels(levels)
 
     host = make_batch(B, Lt, T, 672, 1024, seed=1234 + rank, use_pointcloud=use_pc, use_tactile=use_tac, pin=True,
-                      extra_views=views, generation=args.workload in GENERATION)
+                      extra_views=views, generation=workload in GENERATION)
     devb = map_tensors(host, lambda t: t.cuda(non_blocking=True))
     kw = dict(camera_name="rlbench_front", repeated_diffusion_steps=R, use_diff=True)
 
-    def call(b):
+    def fwd_loss(b):
         loss_dict, _ = mla(input_ids=b["input_ids"], attention_mask=b["attention_mask"], labels=b["labels"],
                            actions=b["actions"], images=b["images"], point_cloud=b.get("point_cloud"),
                            tactile=b.get("tactile"), proprio=b["proprio"], gripper_xyz=b.get("gripper_xyz"),
                            action_masks=b["action_masks"], next_images=b.get("next_images"),
                            next_point_cloud=b.get("next_point_cloud"), next_tactile=b.get("next_tactile"), **kw)
-        loss = loss_dict["total_loss"]
+        return loss_dict["total_loss"]
+
+    def call(b):
+        loss = fwd_loss(b)
         loss.backward()
         trainer.step()
         return loss
@@ -246,6 +328,12 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def reduce_max(ms):
+        t = torch.tensor([ms], device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     def timed(n, batch, read_loss):
         barrier()
@@ -258,10 +346,7 @@ def run_ours(args):
                 last = float(loss.item())       # D2H read of the step's result
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()) / n, last
+        return reduce_max(e0.elapsed_time(e1)) / n, last
 
     for _ in range(max(args.warmup, 3)):
         loss = call(devb)
@@ -284,14 +369,6 @@ def run_ours(args):
         with torch.no_grad():
             return fwd_loss(b)
 
-    def fwd_loss(b):
-        loss_dict, _ = mla(input_ids=b["input_ids"], attention_mask=b["attention_mask"], labels=b["labels"],
-                           actions=b["actions"], images=b["images"], point_cloud=b.get("point_cloud"),
-                           tactile=b.get("tactile"), proprio=b["proprio"], gripper_xyz=b.get("gripper_xyz"),
-                           action_masks=b["action_masks"], next_images=b.get("next_images"),
-                           next_point_cloud=b.get("next_point_cloud"), next_tactile=b.get("next_tactile"), **kw)
-        return loss_dict["total_loss"]
-
     def fwd_bwd(b):
         fwd_loss(b).backward()
         trainer.exchange()                  # N > 1: the gradient all-reduce issued from backward is part of it
@@ -308,13 +385,10 @@ def run_ours(args):
             fn(devb)
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()) / n
+        return reduce_max(e0.elapsed_time(e1)) / n
 
     ms_fwd = ms_fwd_bwd = None
-    if world == 1:                          # per-GPU quantities: measured on the single-GPU run only
+    if world == 1 and with_breakdown:       # per-GPU quantities: measured on the single-GPU run only
         try:
             ms_fwd = round(time_fn(fwd_only, max(2, args.steps // 2)), 2)
             ms_fwd_bwd = round(time_fn(fwd_bwd, max(2, args.steps // 2)), 2)
@@ -323,18 +397,57 @@ def run_ours(args):
             ms_fwd = ms_fwd_bwd = None
     clocks = sampler.stop() if rank == 0 else None
     mla.vlm.check_errors()
-    mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+    exch = trainer.exchange_stats() if hasattr(trainer, "exchange_stats") else None
+    res = dict(workload=workload, desc=desc, B=B, R=R, S=S, tokens=tokens, levels=levels, ms_dev=ms_dev, ms_e2e=ms_e2e,
+               last_loss=last_loss, launches=int(launches), ms_fwd=ms_fwd, ms_fwd_bwd=ms_fwd_bwd, clocks=clocks,
+               mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, h2d=batch_bytes(host), exchange=exch,
+               unused_params=sum(1 for p in mla.parameters() if p.requires_grad and id(p) not in layer_ids
+                                 and id(p) not in trainer.state))
+    # free the training state (the next workload / the isolated kernel timing need the memory)
+    del trainer, mla, model_, small, devb, host, loss
+    import gc
+    gc.collect()
+    from mla_b200 import ops
+    ops.clear_bf16_cache()
+    torch.cuda.empty_cache()
+    torch.cuda.reset_peak_memory_stats()
+    return res
 
+
+def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from mla_b200 import _lib
+    _lib.check(_lib.lib().mla_device_check())
+
+    workload = args.workload or ("cfg2" if world == 1 else "cfg4")
+    m = measure_ours(args, workload, world, rank, local, with_breakdown=True)
+    also = None
+    if world == 1 and not args.workload and not args.no_also:
+        try:        # BASELINE configs[2] on the same GPU in the same run (secondary: must never take the headline down)
+            a = measure_ours(args, "cfg3", world, rank, local, with_breakdown=False)
+            also = {"cfg3": {"workload": f"cfg3: {a['desc']}", "ms_per_step": round(a["ms_dev"], 2),
+                             "value": round(a["tokens"] / a["ms_dev"] * 1e3, 1), "unit": "tokens/s",
+                             "e2e_value": round(a["tokens"] / a["ms_e2e"] * 1e3, 1), "e2e_ms_per_step": round(a["ms_e2e"], 2),
+                             "h2d_bytes_per_step": a["h2d"], "gpu_launches": a["launches"], "last_loss": a["last_loss"],
+                             "peak_mem_gb": round(a["mem_gb"], 1),
+                             "step_frac_of_peak": round(step_flops(a["tokens"], a["S"]) / a["ms_dev"] / 1e9 / peaks()[2], 4)}}
+        except Exception as ex:
+            sys.stderr.write(f"cfg3 measurement failed: {ex}\n")
+            also = {"cfg3": {"error": str(ex)[:200]}}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     hbm, tf_burst, tf_sust, src = peaks()
-    # free the training state before the isolated kernel timing
+    tokens, S, ms_dev, ms_e2e = m["tokens"], m["S"], m["ms_dev"], m["ms_e2e"]
     roof = None
     try:
-        del trainer
-        torch.cuda.empty_cache()
         roof = gemm_roofline(tokens, tf_sust)
         roof["peak_source"] = f"bf16_tflops_sustained of {src} MEASURED_PEAKS.json (kernel timed back to back, power-capped)"
     except Exception as ex:  # e.g. not enough free memory next to the model
@@ -346,26 +459,33 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         try:
-            cpu = cpu_baseline(sample_layers=4)
+            cpu = cpu_baseline_subprocess("cfg2" if workload == "cfg2" else "cfg3")
         except Exception as ex:
-            cpu = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"[:200]}
+            cpu = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"[:200]}
+    levels = m["levels"]
     out = {
         "metric": "multimodal_tokens_per_sec", "value": round(world * tokens / ms_dev * 1e3, 1), "unit": "tokens/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev, 2),
-        "fwd_ms": ms_fwd, "fwd_bwd_ms": ms_fwd_bwd,
+        "fwd_ms": m["ms_fwd"], "fwd_bwd_ms": m["ms_fwd_bwd"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "per_gpu_batch": B, "repeated_diffusion_steps": R,
-                   "seq_len": S, "tokens_per_gpu_step": tokens, "global_batch": B * world, "parallelism": f"dp{world}",
+        "config": {"workload": f"{workload}: {m['desc']}", "per_gpu_batch": m["B"], "repeated_diffusion_steps": m["R"],
+                   "seq_len": S, "tokens_per_gpu_step": tokens, "global_batch": m["B"] * world, "parallelism": f"dp{world}",
                    "stage": ("pretrain (vision tokenizers trained)" if args.stage == "pretrain" else
-                             "post-training (generation heads on)" if args.workload in GENERATION
+                             "post-training (generation heads on)" if workload in GENERATION
                              else "finetune (vision tokenizers frozen)"), "optimizer": "AdamW fp32 master + fp32 grads",
                    "activation_save_levels": {lv: levels.count(lv) for lv in sorted(set(levels))},
                    "l2": "step streams >100 GB of weights/activations (>> 126 MB L2); no explicit flush needed",
-                   "peak_mem_gb": round(mem_gb, 1)},
+                   "peak_mem_gb": round(m["mem_gb"], 1),
+                   "trainable_params_without_gradient": m["unused_params"]},
         "e2e": {"value": round(world * tokens / ms_e2e * 1e3, 1), "unit": "tokens/s", "ms_per_step": round(ms_e2e, 2),
-                "h2d_bytes_per_step": batch_bytes(host), "d2h_bytes_per_step": 4, "last_loss": last_loss},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 4, "last_loss": m["last_loss"]},
+        "gpu_launches": m["launches"], "clocks": m["clocks"], "roofline": roof, "cpu_baseline": cpu,
+        "reference_gpu": reference_gpu_record(),
     }
+    if m["exchange"]:
+        out["gradient_exchange"] = m["exchange"]
+    if also:
+        out["also"] = also
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -373,29 +493,24 @@ def run_ours(args):
 
 # ------------------------------------------------------------------------------------------------------ reference
 def run_reference(args):
-    """The reference's own CPU path for this metric: the oracle port (the reference cannot be pip-installed here:
-    its pyproject pins torch 2.5.1 / tensorflow 2.15 / timm and there is no index)."""
+    """Reference arm: the UNMODIFIED reference's own CPU execution of the path on the host cores (see reference_cpu).
+    Under torchrun only rank 0 runs; the other ranks exit 0 without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    times = []
-    res = None
-    for i in range(args.warmup + args.steps):
-        res = cpu_baseline(sample_layers=1)
-        if i >= args.warmup:
-            times.append(res["seconds_measured"])
-    S = 548
-    per_step = sum(times) / len(times) * L      # extrapolated full-depth step of one sequence
-    value = S / per_step
-    use_pc, use_tac, _, desc = WORKLOADS[args.workload]
-    out = {"impl": "reference", "metric": "multimodal_tokens_per_sec", "value": round(value, 3), "unit": "tokens/s",
-           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": round(per_step * 1e3, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{args.workload}: {desc}", "note": "CPU: 1 sequence per step, 1-layer slice x32"},
-           "cpu_baseline": {"value": round(value, 3), "unit": "tokens/s", "cores": res["cores"], "kind": "port",
-                            "sample": res["sample"]},
-           "e2e": {"value": round(value, 3), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload = args.workload or ("cfg2" if world == 1 else "cfg4")
+    res = reference_cpu(args.steps, args.warmup, layers_cpu=args.layers_cpu, workload=workload)
+    desc = WORKLOADS[workload][3]
+    out = {"impl": "reference", "metric": "multimodal_tokens_per_sec", "value": res["value"], "unit": "tokens/s",
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": round(res["seconds_per_sample_step"] * 1e3, 1), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "bf16 autocast over fp32 params (CPU)", "data": "synthetic",
+           "config": {"workload": f"{workload}: {desc}",
+                      "sample": f"ms_per_step is the measured time of one SAMPLE step ({res['tokens_per_sample_step']} tokens "
+                                f"through {res['layers_cpu']}/{L} layers); value = depth-normalised tokens/s"},
+           "cpu_baseline": res,
+           "e2e": {"value": res["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
 
 
@@ -405,10 +520,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="", choices=[""] + sorted(WORKLOADS),
+                    help="default: cfg2 (+ cfg3 under 'also') on one GPU, cfg4 (the full configuration) under DDP")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 8; 1 for cfg5)")
     ap.add_argument("--save-level", default="auto", choices=["auto", "layer", "mlp", "none"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="single GPU: skip the secondary cfg3 measurement")
+    ap.add_argument("--layers-cpu", type=int, default=4, help="reference arm: decoder layers of the CPU sample")
     ap.add_argument("--stage", default="", choices=["", "pretrain", "finetune", "post-training"],
                     help="freeze_backbones stage (default: finetune; post-training for cfg5)")
     args = ap.parse_args()

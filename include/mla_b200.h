@@ -79,8 +79,8 @@ typedef struct mla_gemm_args {
   /* Fused SwiGLU for the gate|up projection (LlamaMLP, modeling_llama.py:240; CTA-pair kernel): B = [gate; up] stored
    * [2f, K], f a multiple of 128.  swiglu_out bf16 [M, f] (pitch ld_swiglu) receives bf16(bf16(silu(gate)) * up); c
    * (the [M, 2f] gate|up matrix backward wants) is then optional — NULL skips its store.  NULL swiglu_out = off.
-   * EXPERIMENTAL in round 1: built and exercised by tests/test_gemm2_gpu.py only under MLA_EXPERIMENTAL=1; the training
-   * step uses it only with MLA_FUSE_SWIGLU=1. */
+   * Bit-identical to the projection followed by mla_swiglu_fwd (tests/test_gemm2_gpu.py); the training step uses it by
+   * default (MLA_FUSE_SWIGLU=0 restores the separate pass). */
   void* swiglu_out;
   int64_t ld_swiglu;
 } mla_gemm_args;
@@ -150,6 +150,14 @@ size_t mla_attn_bwd_sm100_workspace(int32_t batch, int32_t seq, int32_t heads);
 int mla_attn_bwd_sm100(const void* qkv, int64_t ld_qkv, const void* o, const void* d_o, int64_t ld_o, const void* lse,
                        const void* mask, void* dqkv, int64_t ld_dqkv, void* workspace, int32_t batch, int32_t seq,
                        int32_t heads, float scale, void* stream);
+/* Pipelined generation of the same backward (two math-warp groups ping-pong over the streamed tiles, 3-slot TMA ring,
+ * double-buffered P/dS staging): same contract and workspace.  rope_cos / rope_sin (bf16 [seq, 64], or both NULL): when
+ * given, the transposed rotary embedding — the backward of apply_rotary_pos_emb, modeling_llama.py:184-208 — is applied
+ * to the dq and dk column blocks in the epilogue, so dqkv holds the gradient w.r.t. the projection outputs BEFORE RoPE
+ * (bit-identical to mla_attn_bwd_sm100 followed by mla_rope_inplace(transpose = 1)). */
+int mla_attn_bwd2_sm100(const void* qkv, int64_t ld_qkv, const void* o, const void* d_o, int64_t ld_o, const void* lse,
+                        const void* mask, void* dqkv, int64_t ld_dqkv, void* workspace, const void* rope_cos,
+                        const void* rope_sin, int32_t batch, int32_t seq, int32_t heads, float scale, void* stream);
 
 /* ---- small row/elementwise kernels around the GEMMs ---------------------------------------------------------
  * (ATen glue in the reference: dtype casts under autocast, activation backward, bias gradients, torch.cat / index

@@ -92,6 +92,16 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const 
   }
 }
 
+// Host launcher of the prep kernel, shared with the pipelined generation (attention_bwd2_sm100.cu).
+int attn_bwd_prep_launch(const void* o, const void* d_o, int64_t ld_o, const void* lse, float* lse2, float* delta, int B,
+                         int S, int H, int S_pad, cudaStream_t s) {
+  const int64_t rows = int64_t(B) * H * S_pad;
+  attn_bwd_prep_kernel<<<unsigned((rows * 32 + 255) / 256), 256, 0, s>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o,
+                                                                        ld_o, (const float*)lse, lse2, delta, B, S, H, S_pad);
+  MLA_CHECK_LAUNCH("attn_bwd_prep");
+  return MLA_OK;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(BW_THREADS, 1)
 attn_bwd_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __grid_constant__ CUtensorMap map_qkv_str,
@@ -424,11 +434,7 @@ extern "C" int mla_attn_bwd_sm100(const void* qkv, int64_t ld_qkv, const void* o
   const int s_pad = (seq + 127) / 128 * 128;
   float* lse2 = (float*)workspace;
   float* delta = lse2 + size_t(batch) * heads * s_pad;
-  const int64_t rows = int64_t(batch) * heads * s_pad;
-  attn_bwd_prep_kernel<<<unsigned((rows * 32 + 255) / 256), 256, 0, s>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o,
-                                                                        ld_o, (const float*)lse, lse2, delta, batch, seq,
-                                                                        heads, s_pad);
-  MLA_CHECK_LAUNCH("attn_bwd_prep");
+  if (int rc = attn_bwd_prep_launch(o, d_o, ld_o, lse, lse2, delta, batch, seq, heads, s_pad, s)) return rc;
   CUtensorMap m_qkv_fix, m_qkv_str, m_do_fix, m_do_str;
   const uint64_t dims_qkv[2] = {uint64_t(3) * heads * BW_D, uint64_t(batch) * seq};
   const uint64_t dims_do[2] = {uint64_t(heads) * BW_D, uint64_t(batch) * seq};

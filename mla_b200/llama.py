@@ -33,9 +33,9 @@ from . import ops
 OVERLAP = {"wgrad": os.environ.get("MLA_WGRAD_STREAM", "0") == "1"}
 _SIDE_STREAMS: dict = {}
 FUSE_ROPE = {"on": os.environ.get("MLA_FUSE_ROPE", "1") == "1"}     # RoPE inside the q|k|v GEMM epilogue (head_dim 128)
-# SwiGLU inside the gate|up GEMM epilogue (CTA-pair kernel; inter % 128 == 0).  EXPERIMENTAL: written at the end of round 1
-# without GPU time left to validate it, so it is OFF unless MLA_FUSE_SWIGLU=1 (tests: MLA_EXPERIMENTAL=1).
-FUSE_SWIGLU = {"on": os.environ.get("MLA_FUSE_SWIGLU", "0") == "1"}
+# SwiGLU inside the gate|up GEMM epilogue (CTA-pair kernel; inter % 128 == 0): bit-identical to the projection followed
+# by swiglu_fwd (tests/test_gemm2_gpu.py, validated on B200 in round 2).  MLA_FUSE_SWIGLU=0 restores the separate pass.
+FUSE_SWIGLU = {"on": os.environ.get("MLA_FUSE_SWIGLU", "1") == "1"}
 
 
 def side_stream(device) -> "torch.cuda.Stream":
@@ -110,7 +110,8 @@ class LlamaDecoderLayer(nn.Module):
         self.save_level = "layer"
         self._c = None          # bf16 compute copies
         self._versions = None
-        self._g = None          # fp32 gradient arenas
+        self._g = None          # fp32 gradient arenas (views of _gflat)
+        self._gflat = None
         self._grads_fresh = True
         self._grad_ready_cb = None   # set by the data-parallel trainer: called when this layer's arenas are final
         self._weights_ready = None   # CUDA event: the optimizer's side-stream update of this layer has landed
@@ -149,17 +150,20 @@ class LlamaDecoderLayer(nn.Module):
         return self._c
 
     def grad_arenas(self):
-        """fp32 [3h,h], [h,h], [2f,h], [h,f], [h], [h]; param.grad aliases views of these."""
+        """fp32 [3h,h], [h,h], [2f,h], [h,f], [h], [h] — views of ONE flat buffer per layer (`_gflat`: the data-parallel
+        trainer reduces a layer's gradients with a single collective); param.grad aliases views of these."""
         ps = self._masters()
         dev = ps[0].device
         if self._g is None or self._g[0].device != dev:
             h, f = self.hidden_size, self.inter
-            self._g = (torch.zeros(3 * h, h, dtype=torch.float32, device=dev),
-                       torch.zeros(h, h, dtype=torch.float32, device=dev),
-                       torch.zeros(2 * f, h, dtype=torch.float32, device=dev),
-                       torch.zeros(h, f, dtype=torch.float32, device=dev),
-                       torch.zeros(h, dtype=torch.float32, device=dev),
-                       torch.zeros(h, dtype=torch.float32, device=dev))
+            sizes = [3 * h * h, h * h, 2 * f * h, h * f, h, h]
+            shapes = [(3 * h, h), (h, h), (2 * f, h), (h, f), (h,), (h,)]
+            self._gflat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+            off, views = 0, []
+            for n, sh in zip(sizes, shapes):
+                views.append(self._gflat[off:off + n].view(sh))
+                off += n
+            self._g = tuple(views)
             self._views = None
         if getattr(self, "_views", None) is None:
             h, f = self.hidden_size, self.inter
@@ -265,9 +269,13 @@ class LlamaDecoderLayer(nn.Module):
         # ---- attention half
         wgrad(dx_mid, ctx, go)                                                       # dWo  = dx_mid^T ctx
         dctx = ops.gemm(dx_mid, wo, b_mn=True)
-        dqkv = ops.attn_bwd(dctx, qkv, ctx, lse, sh.B, sh.S, sh.H, sh.D, sh.mask)
+        if ops.attn_bwd_fuses_rope(sh.D) and FUSE_ROPE["on"]:
+            # the backward of RoPE rides in the attention kernel's epilogue (no extra pass over dq | dk)
+            dqkv = ops.attn_bwd(dctx, qkv, ctx, lse, sh.B, sh.S, sh.H, sh.D, sh.mask, rope=(sh.cos, sh.sin))
+        else:
+            dqkv = ops.attn_bwd(dctx, qkv, ctx, lse, sh.B, sh.S, sh.H, sh.D, sh.mask)
+            ops.rope_(dqkv, 0, 2 * sh.H, sh.D, sh.S, sh.cos, sh.sin, transpose=True)
         del dctx, ctx, qkv
-        ops.rope_(dqkv, 0, 2 * sh.H, sh.D, sh.S, sh.cos, sh.sin, transpose=True)
         wgrad(dqkv, n1, gqkv)                                                        # dWqkv = dqkv^T n1
         dn1 = ops.gemm(dqkv, wqkv, b_mn=True)
         del dqkv, n1

@@ -46,7 +46,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True);  b: [N,K] (b_mn=False, nn.Linear weight) or [K,N] (b_mn=True).
     rope = (cos [S,64] bf16, sin [S,64] bf16, S, n_cols): rotate the leading n_cols columns (head_dim 128) in the epilogue.
-    swiglu_out (EXPERIMENTAL, see include/mla_b200.h): bf16 [M, N/2] receiving SwiGLU of the [gate | up] projection in
+    swiglu_out (see include/mla_b200.h): bf16 [M, N/2] receiving SwiGLU of the [gate | up] projection in
     the epilogue; with store_c=False the projection itself is not written (returns None).
     """
     _req(a, torch.bfloat16, "a")
@@ -214,7 +214,10 @@ def swiglu_bwd_act(dact: torch.Tensor, gu: torch.Tensor):
 import os as _os
 
 _attn_default = _os.environ.get("MLA_ATTN_IMPL", "sm100")      # A/B switch for benchmarking: "sm100" | "mma"
-ATTN_IMPL = {"fwd": _attn_default, "bwd": _attn_default}
+# backward generations of the tcgen05 path: "sm100" = attention_bwd_sm100.cu, "sm100v2" = the pipelined kernel
+# (attention_bwd2_sm100.cu), which can also apply the transposed RoPE in its epilogue (attn_bwd(..., rope=(cos, sin)))
+ATTN_IMPL = {"fwd": _attn_default,
+             "bwd": _os.environ.get("MLA_ATTN_BWD", "sm100v2") if _attn_default == "sm100" else _attn_default}
 
 
 def _attn_args(qkv: torch.Tensor, B: int, S: int, H: int, D: int, mask: Optional[torch.Tensor]) -> "_lib.AttnArgs":
@@ -251,19 +254,42 @@ def attn_fwd(qkv: torch.Tensor, B: int, S: int, H: int, D: int, mask: Optional[t
     return ctx, lse
 
 
+def attn_bwd_fuses_rope(D: int) -> bool:
+    """True when attn_bwd can apply the transposed RoPE itself (the pipelined tcgen05 kernel, head_dim 128)."""
+    return D == 128 and ATTN_IMPL["bwd"] == "sm100v2"
+
+
 def attn_bwd(dctx: torch.Tensor, qkv: torch.Tensor, ctx: torch.Tensor, lse: torch.Tensor, B: int, S: int, H: int,
-             D: int, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Returns d_qkv [B*S, 3*H*D] (dq | dk | dv) — gradients w.r.t. the post-RoPE q,k and v."""
+             D: int, mask: Optional[torch.Tensor] = None, rope: Optional[tuple] = None) -> torch.Tensor:
+    """Returns d_qkv [B*S, 3*H*D] (dq | dk | dv) — gradients w.r.t. the post-RoPE q,k and v; with rope = (cos, sin)
+    (bf16 [S, 64]; only where attn_bwd_fuses_rope) w.r.t. the PRE-RoPE q and k: the transposed rotation is applied in
+    the kernel's epilogue."""
     a = _attn_args(qkv, B, S, H, D, mask)
     _req(dctx, torch.bfloat16, "dctx")
     if not (dctx.is_contiguous() and ctx.is_contiguous()):
         raise _lib.MlaError("attention bwd: ctx / dctx must be contiguous")
+    if rope is not None and not attn_bwd_fuses_rope(D):
+        raise _lib.MlaError("attention bwd: fused RoPE transpose needs the pipelined tcgen05 kernel (head_dim 128)")
     dqkv = torch.empty_like(qkv, memory_format=torch.contiguous_format)
-    if D == 128 and ATTN_IMPL["bwd"] == "sm100":
+    if D == 128 and ATTN_IMPL["bwd"] in ("sm100", "sm100v2"):
         lib = _lib.lib()
         lib.mla_attn_bwd_sm100_workspace.restype = C.c_size_t
         ws = torch.empty(lib.mla_attn_bwd_sm100_workspace(C.c_int32(B), C.c_int32(S), C.c_int32(H)) // 4,
                          dtype=torch.float32, device=qkv.device)
+        if ATTN_IMPL["bwd"] == "sm100v2":
+            cos_t = sin_t = None
+            if rope is not None:
+                cos_t, sin_t = rope
+                _req(cos_t, torch.bfloat16, "rope cos")
+                _req(sin_t, torch.bfloat16, "rope sin")
+                if tuple(cos_t.shape) != (S, 64) or tuple(sin_t.shape) != (S, 64) or not (
+                        cos_t.is_contiguous() and sin_t.is_contiguous()):
+                    raise _lib.MlaError("attention bwd: fused RoPE needs contiguous [seq, 64] tables")
+            check(lib.mla_attn_bwd2_sm100(C.c_void_p(qkv.data_ptr()), C.c_int64(a.ld_qkv), _p(ctx), _p(dctx),
+                                          C.c_int64(ctx.stride(0)), _p(lse), C.c_void_p(a.mask), _p(dqkv),
+                                          C.c_int64(dqkv.stride(0)), _p(ws), _p(cos_t), _p(sin_t), C.c_int32(B),
+                                          C.c_int32(S), C.c_int32(H), C.c_float(a.scale), _stream()))
+            return dqkv
         check(lib.mla_attn_bwd_sm100(C.c_void_p(qkv.data_ptr()), C.c_int64(a.ld_qkv), _p(ctx), _p(dctx),
                                      C.c_int64(ctx.stride(0)), _p(lse), C.c_void_p(a.mask), _p(dqkv),
                                      C.c_int64(dqkv.stride(0)), _p(ws), C.c_int32(B), C.c_int32(S), C.c_int32(H),

@@ -5,8 +5,11 @@ with gradient all-reduce over NVLink and no parameter all-gather on the hot path
 reference's optimizer semantics — AdamW(lr, weight decay on >=2-D non-bias params only, fsdp.py:242-257),
 clip_grad_norm_(max_grad_norm) before the step (:310, base_strategy_mla.py:372), constant or warmup+cosine LR — and
 its step order (forward, backward, clip, step, zero_grad), with:
-  * one NCCL all-reduce per decoder layer's fp32 gradient arenas, issued from that layer's backward so it overlaps
-    the rest of backward; a handful more for the small modules' autograd gradients;
+  * ONE NCCL all-reduce per decoder layer (its gradient arenas are views of one flat fp32 buffer), issued from that
+    layer's backward so it overlaps the rest of backward; one more for the small modules' gradients (flattened);
+    fp32 by default as the reference reduces (`reduce_in_full_precision`, fsdp.py:184-187), bf16 on request;
+  * gradient accumulation: `with trainer.no_sync():` around every micro-batch but the last defers the exchange (the
+    reference's grad_accumulation_steps, base_strategy_mla.py:100,:366-379);
   * the global norm, clip coefficient, 1/world averaging and the AdamW update computed on the device (no host sync),
     the update refreshing the bf16 compute copies in the same pass.
 Samples are independent (per-replica InfoNCE negatives and BatchNorm statistics, as in the reference), so there is no
@@ -36,7 +39,13 @@ class DataParallelTrainer:
     def __init__(self, model: torch.nn.Module, lr: float = 2e-5, weight_decay: float = 0.0,
                  max_grad_norm: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8,
                  lr_scheduler_type: str = "constant", warmup_steps: int = 0, total_steps: Optional[int] = None,
-                 process_group=None):
+                 process_group=None, reduce_dtype: Optional[torch.dtype] = None, broadcast_from_rank0: bool = True,
+                 error_check_interval: int = 50):
+        if lr_scheduler_type not in ("constant", "linear-warmup+cosine-decay"):
+            # the reference's two schedules (training/strategies/fsdp.py:236,:262,:286)
+            raise ValueError(f"Learning Rate Schedule with type `{lr_scheduler_type}` is not supported!")
+        if lr_scheduler_type != "constant" and not total_steps:
+            raise ValueError("linear-warmup+cosine-decay needs total_steps (the reference derives it from the dataset size)")
         self.model = model
         self.lr, self.weight_decay, self.max_grad_norm = lr, weight_decay, max_grad_norm
         self.betas, self.eps = betas, eps
@@ -45,6 +54,14 @@ class DataParallelTrainer:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.step_count = 0
         self._handles: List = []
+        self._sync = True                 # False inside no_sync(): backward accumulates locally, no exchange
+        self._reduced: set = set()        # ids of layers whose arenas already hold rank sums (this step)
+        self._others_flat = None
+        import os as _os
+        env_rd = _os.environ.get("MLA_GRAD_REDUCE_DTYPE", "")
+        self.reduce_dtype = reduce_dtype or (torch.bfloat16 if env_rd == "bf16" else torch.float32)
+        self.error_check_interval = error_check_interval
+        self._exch_bytes = 0
         self.layers: List[LlamaDecoderLayer] = [m for m in model.modules() if isinstance(m, LlamaDecoderLayer)]
         layer_params = set()
         for l in self.layers:
@@ -62,29 +79,75 @@ class DataParallelTrainer:
                       if p.requires_grad and id(p) not in layer_params]
         self.state: Dict[int, tuple] = {}
         dev = next(model.parameters()).device
+        if self.world > 1 and broadcast_from_rank0:
+            # what torch DDP does at construction: every replica starts from rank 0's parameters and buffers
+            # (BatchNorm running statistics of the point tokenizer included)
+            with torch.no_grad():
+                for t in list(model.parameters()) + list(model.buffers()):
+                    dist.broadcast(t.data, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+                    if isinstance(t, torch.nn.Parameter):
+                        torch.autograd.graph.increment_version(t)
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._scale = torch.zeros(2, dtype=torch.float32, device=dev)
 
     # ------------------------------------------------------------------ gradient exchange
+    def no_sync(self):
+        """Context manager for gradient accumulation: backward passes inside it add into the local gradient arenas
+        without any exchange; the first backward outside it reduces the accumulated sums (torch DDP's no_sync)."""
+        trainer = self
+
+        class _NoSync:
+            def __enter__(self_):
+                self_.prev, trainer._sync = trainer._sync, False
+
+            def __exit__(self_, *exc):
+                trainer._sync = self_.prev
+                return False
+        return _NoSync()
+
+    def _all_reduce(self, flat: torch.Tensor) -> None:
+        """In-place SUM over ranks of a flat fp32 buffer, asynchronously (handle kept)."""
+        self._exch_bytes += flat.numel() * (2 if self.reduce_dtype == torch.bfloat16 else 4)
+        if self.reduce_dtype == torch.bfloat16:
+            # opt-in: halves the bytes on NVLink; the sum is formed in bf16 (the reference's default is fp32)
+            lo = ops.cast_bf16(flat) if flat.is_cuda else flat.to(torch.bfloat16)   # (CPU: gloo tests of the host logic)
+            h = dist.all_reduce(lo, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            self._handles.append((h, lo, flat))
+        else:
+            self._handles.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True), None, None))
+
     def _layer_grads_ready(self, layer: LlamaDecoderLayer) -> None:
-        """Called at the end of a decoder layer's backward: its arenas are final, reduce them while earlier layers
-        are still running backward."""
-        for g in layer._g:
-            self._handles.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        """Called at the end of a decoder layer's backward: unless accumulating (no_sync), its arenas are final — reduce
+        them (one collective per layer) while earlier layers are still running backward."""
+        if id(layer) in self._reduced:
+            raise RuntimeError(
+                "a decoder layer ran backward again after its gradients were already all-reduced in this step: wrap every "
+                "micro-batch but the last in `with trainer.no_sync():` (gradient accumulation) and call step() after the last")
+        if not self._sync:
+            return
+        self._reduced.add(id(layer))
+        self._all_reduce(layer._gflat)
 
     def _reduce_others(self) -> None:
-        for _, p, _ in self.other:
-            if p.grad is not None:
-                self._handles.append(dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        """The small modules' autograd gradients, flattened into one buffer -> one collective -> scattered back."""
+        gs = [p.grad for _, p, _ in self.other if p.grad is not None]
+        if not gs:
+            return
+        flat = torch.cat([g.reshape(-1).float() for g in gs])
+        self._all_reduce(flat)
+        self._others_flat = (flat, gs)
 
     def current_lr(self) -> float:
+        """LR of the optimizer step being taken.  transformers' get_cosine_schedule_with_warmup evaluates its lambda at
+        the number of COMPLETED scheduler steps, so the k-th optimizer step (k = step_count, 1-based) runs at lambda(k-1):
+        the very first step has lr 0 when there is a warm-up (fsdp.py:258-260 also zeroes the initial lr)."""
         if self.lr_scheduler_type == "constant":
             return self.lr
-        s = self.step_count
+        s = max(0, self.step_count - 1)
         if s < self.warmup_steps:
             return self.lr * s / max(1, self.warmup_steps)
-        prog = (s - self.warmup_steps) / max(1, (self.total_steps or s + 1) - self.warmup_steps)
-        return self.lr * max(0.0, 0.5 * (1.0 + math.cos(math.pi * min(1.0, prog))))
+        prog = (s - self.warmup_steps) / max(1, self.total_steps - self.warmup_steps)
+        return self.lr * max(0.0, 0.5 * (1.0 + math.cos(math.pi * prog)))
 
     # ------------------------------------------------------------------ optimizer step
     def _adam(self, param: torch.nn.Parameter, g: torch.Tensor, decay: bool, bf16_dst: Optional[torch.Tensor],
@@ -107,10 +170,25 @@ class DataParallelTrainer:
         the 1/world averaging is folded into the optimizer's gradient scale.  Parameters without a gradient (lm_head
         in diffusion mode, unused tokenizer parameters) are skipped consistently on every rank."""
         if self.world > 1:
+            if not self._sync:
+                raise RuntimeError("exchange()/step() called inside no_sync(): leave the context for the last micro-batch")
+            for l in self.layers:       # layers whose last backward ran under no_sync (or none at all this call)
+                if not l._grads_fresh and id(l) not in self._reduced and l._gflat is not None:
+                    self._reduced.add(id(l))
+                    self._all_reduce(l._gflat)
             self._reduce_others()
-            for h in self._handles:
+            for h, lo, dst in self._handles:
                 h.wait()
+                if lo is not None:      # bf16 reduce: widen the rank sum back into the fp32 arena
+                    dst.copy_(lo)
             self._handles.clear()
+            if self._others_flat is not None:
+                flat, gs = self._others_flat
+                off = 0
+                for g in gs:
+                    g.copy_(flat[off:off + g.numel()].view_as(g))
+                    off += g.numel()
+                self._others_flat = None
 
     def step(self) -> None:
         """clip_grad_norm_ + AdamW.step + zero_grad, after loss.backward()."""
@@ -128,8 +206,8 @@ class DataParallelTrainer:
         for l in self.layers:
             if l._grads_fresh:
                 continue          # no backward reached this layer since the last step
-            for g in l._g:
-                check(lib.mla_sumsq_f32(ops._p(g), C.c_int64(g.numel()), ops._p(self._sumsq), s))
+            g = l._gflat
+            check(lib.mla_sumsq_f32(ops._p(g), C.c_int64(g.numel()), ops._p(self._sumsq), s))
         for _, p, _ in self.other:
             if p.grad is not None:
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
@@ -165,6 +243,22 @@ class DataParallelTrainer:
             self._adam(p, g, decay, None, lr)
             torch.autograd.graph.increment_version(p)      # invalidates the cached bf16 compute copy
             p.grad = None
+        self._reduced.clear()
+        if self.error_check_interval and self.step_count % self.error_check_interval == 0:
+            # device-side error flags (a sample without EOS/tag token: the reference raises IndexError,
+            # prismatic.py:983) are read back every N steps so the hot path stays free of host syncs
+            chk = getattr(getattr(self.model, "vlm", None), "check_errors", None)
+            if chk is not None:
+                chk()
+
+    def exchange_stats(self) -> Optional[dict]:
+        """Bytes handed to NCCL per step so far (for the bench's busbw figure); None on a single replica."""
+        if self.world == 1 or self.step_count == 0:
+            return None
+        per_step = self._exch_bytes / max(1, self.step_count)
+        return {"collectives_per_step": len(self.layers) + 1, "bytes_per_step": int(per_step),
+                "reduce_dtype": str(self.reduce_dtype).replace("torch.", ""),
+                "busbw_factor": round(2.0 * (self.world - 1) / self.world, 4)}
 
     def grad_norm(self) -> torch.Tensor:
         """Mean-gradient global norm of the last step (device scalar)."""

@@ -133,11 +133,17 @@ class PrismaticVLM(nn.Module):
     def initialize_weights(self):
         """prismatic.py:299-321 — xavier-uniform for every nn.Linear (the LLM included, as `self.apply` does),
         unit LayerNorm, N(0, 0.02) embedders, zero-initialised final projection."""
+        from .llama import _Proj
+
         def _basic_init(m):
             if isinstance(m, nn.Linear):
                 torch.nn.init.xavier_uniform_(m.weight)
                 if m.bias is not None:
                     nn.init.constant_(m.bias, 0)
+            elif isinstance(m, _Proj):
+                # the decoder's q/k/v/o/gate/up/down are nn.Linear in the reference, so `self.apply` re-initialises them
+                # too; here they are bias-free parameter holders with nn.Linear's [out, in] layout
+                torch.nn.init.xavier_uniform_(m.weight)
             elif isinstance(m, nn.LayerNorm):
                 nn.init.constant_(m.weight, 1.0)
                 nn.init.constant_(m.bias, 0)

@@ -80,10 +80,12 @@ def test_attn_bwd_sm100(cuda_lib, B, S, H, masked):
             mask[1, S // 3: S // 3 + 5] = False
     ctx, lse = ops.attn_fwd(qkv, B, S, H, D, mask)
     dctx = torch.randn(B * S, h, device="cuda").to(torch.bfloat16)
+    keep = dict(ops.ATTN_IMPL)
     ops.ATTN_IMPL["bwd"] = "mma"
     d_ref = ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, mask)
     ops.ATTN_IMPL["bwd"] = "sm100"
     d_new = ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, mask)
+    ops.ATTN_IMPL.update(keep)
     torch.cuda.synchronize()
     qf = qkv.float().requires_grad_(True)
     q, k, v = [qf[:, i * h:(i + 1) * h].reshape(B, S, H, D).transpose(1, 2) for i in range(3)]
@@ -95,6 +97,45 @@ def test_attn_bwd_sm100(cuda_lib, B, S, H, masked):
     assert torch.isfinite(d_new.float()).all()
 
 
+@pytest.mark.parametrize("B,S,H,masked", [(1, 128, 1, False), (2, 150, 2, False), (2, 548, 2, False), (2, 548, 2, True),
+                                          (1, 700, 1, True), (1, 64, 1, False), (1, 257, 2, True), (3, 1060, 2, False),
+                                          (1, 3876, 1, False), (1, 40, 1, False)])
+def test_attn_bwd_pipelined_matches_first_generation(cuda_lib, B, S, H, masked):
+    """attention_bwd2_sm100.cu (two math groups, 3-slot ring, double-buffered staging) computes the same products in the
+    same order as attention_bwd_sm100.cu: bit-identical dq | dk | dv; with the RoPE transpose fused into its epilogue it
+    equals the first generation followed by the in-place transposed rotation, bit for bit."""
+    from mla_b200 import ops
+    torch.manual_seed(13 + S)
+    D = 128
+    h = H * D
+    qkv = torch.randn(B * S, 3 * h, device="cuda").to(torch.bfloat16)
+    mask = None
+    if masked:
+        mask = torch.ones(B, S, dtype=torch.bool, device="cuda")
+        mask[0, S - 9:] = False
+        if B > 1:
+            mask[1, S // 3: S // 3 + 5] = False
+    ctx, lse = ops.attn_fwd(qkv, B, S, H, D, mask)
+    dctx = torch.randn(B * S, h, device="cuda").to(torch.bfloat16)
+    ang = torch.rand(S, D // 2, device="cuda") * 6.28
+    cos, sin = ang.cos().bfloat16().contiguous(), ang.sin().bfloat16().contiguous()
+    keep = dict(ops.ATTN_IMPL)
+    try:
+        ops.ATTN_IMPL["bwd"] = "sm100"
+        want = ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, mask)
+        ops.ATTN_IMPL["bwd"] = "sm100v2"
+        for _ in range(3):      # several launches back to back: barrier phases / TMEM re-allocation
+            got = ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, mask)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
+        got_r = ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, mask, rope=(cos, sin))
+        ops.rope_(want, 0, 2 * H, D, S, cos, sin, transpose=True)
+        torch.cuda.synchronize()
+        assert torch.equal(got_r, want)
+    finally:
+        ops.ATTN_IMPL.update(keep)
+
+
 def test_attn_bwd_sm100_speed(cuda_lib):
     from mla_b200 import ops
     B, S, H, D = 32, 548, 32, 128
@@ -102,7 +143,8 @@ def test_attn_bwd_sm100_speed(cuda_lib):
     ctx, lse = ops.attn_fwd(qkv, B, S, H, D, None)
     dctx = torch.randn_like(ctx)
     res = {}
-    for impl in ("mma", "sm100"):
+    keep = dict(ops.ATTN_IMPL)
+    for impl in ("mma", "sm100", "sm100v2"):
         ops.ATTN_IMPL["bwd"] = impl
         for _ in range(3):
             ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, None)
@@ -114,5 +156,7 @@ def test_attn_bwd_sm100_speed(cuda_lib):
         e1.record()
         torch.cuda.synchronize()
         res[impl] = e0.elapsed_time(e1) / 10
-    ops.ATTN_IMPL["bwd"] = "sm100"
-    print(f"\nattn bwd [32,548,32,128]: mma.sync {res['mma']:.3f} ms, tcgen05 {res['sm100']:.3f} ms")
+    ops.ATTN_IMPL.update(keep)
+    fl = 2.5 * 4.0 * S * S * D * H * B / 2
+    print(f"\nattn bwd [32,548,32,128]: mma.sync {res['mma']:.3f} ms, tcgen05 gen 1 {res['sm100']:.3f} ms "
+          f"({fl / res['sm100'] / 1e9:.0f} TFLOP/s), pipelined {res['sm100v2']:.3f} ms ({fl / res['sm100v2'] / 1e9:.0f} TFLOP/s)")

@@ -67,6 +67,95 @@ def _worker(rank, world, port, out_dir):
         dist.destroy_process_group()
 
 
+def _accum_worker(rank, world, port, out_dir):
+    """Gradient accumulation (no_sync), the double-backward guard, the bf16 reduce option, the rank-0 broadcast."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mla_b200.llama import LlamaModel
+        from mla_b200.trainer import DataParallelTrainer
+        torch.manual_seed(100 + rank)                          # replicas built DIFFERENTLY: the trainer must align them
+        model = LlamaModel(64, 32, 64, 2, 4)
+        for p_ in model.parameters():
+            torch.nn.init.normal_(p_, std=0.02)
+        model.register_buffer("running_stat", torch.full((3,), float(rank)))
+        extra = torch.nn.Linear(4, 4)
+        root = torch.nn.ModuleDict(dict(llm=model, extra=extra))
+        for reduce_dtype in (None, torch.bfloat16):
+            tr = DataParallelTrainer(root, lr=1e-3, reduce_dtype=reduce_dtype)
+            w = model.layers[1].mlp.up_proj.weight.detach().clone()
+            ws = [torch.zeros_like(w) for _ in range(world)]
+            dist.all_gather(ws, w)
+            assert torch.equal(ws[0], ws[1]), "parameters were not broadcast from rank 0"
+            assert torch.all(model.running_stat == 0.0), "buffers were not broadcast from rank 0"
+
+            def fake_backward(val):
+                for li, layer in enumerate(tr.layers):
+                    layer.grad_arenas()
+                    live = layer._attach_grads()
+                    for g in layer._g:
+                        if live:
+                            g.add_(val * (li + 1))
+                        else:
+                            g.fill_(val * (li + 1))
+                    layer._grads_fresh = False
+                    layer._grad_ready_cb(layer)
+
+            with tr.no_sync():
+                fake_backward(float(rank + 1))                 # micro-batch 1: local only
+            assert not tr._handles and not tr._reduced
+            fake_backward(10.0 * (rank + 1))                   # micro-batch 2: reduces the accumulated sums
+            assert len(tr._handles) == len(tr.layers)          # ONE collective per decoder layer
+            extra.weight.grad = torch.full_like(extra.weight, float(rank + 1))
+            tr.exchange()
+            tot = sum(11.0 * (r + 1) for r in range(world))
+            for li, layer in enumerate(tr.layers):
+                for g in layer._g:
+                    assert torch.all(g == tot * (li + 1)), (rank, li, g.flatten()[0].item(), tot * (li + 1))
+            assert torch.all(extra.weight.grad == sum(r + 1 for r in range(world)))
+            # a further backward in the same step would add onto rank sums: refused loudly
+            with pytest.raises(RuntimeError, match="no_sync"):
+                fake_backward(1.0)
+            tr._reduced.clear()
+            for layer in tr.layers:
+                layer.mark_grads_fresh()
+            with pytest.raises(RuntimeError, match="no_sync"):
+                with tr.no_sync():
+                    tr.exchange()
+        open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_accumulation_and_broadcast_world2(tmp_path):
+    world = 2
+    mp.spawn(_accum_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_lr_schedule_matches_reference():
+    """linear-warmup+cosine-decay == transformers.get_cosine_schedule_with_warmup as the reference steps it
+    (fsdp.py:258-260: lr starts at 0; the k-th optimizer step runs at lambda(k-1)); other names raise like the reference."""
+    import math
+    from mla_b200.llama import LlamaModel
+    from mla_b200.trainer import DataParallelTrainer
+    m = LlamaModel(64, 32, 64, 1, 4)
+    with pytest.raises(ValueError, match="not supported"):
+        DataParallelTrainer(m, lr_scheduler_type="cosine")
+    with pytest.raises(ValueError, match="total_steps"):
+        DataParallelTrainer(m, lr_scheduler_type="linear-warmup+cosine-decay", warmup_steps=3)
+    tr = DataParallelTrainer(m, lr=2e-5, lr_scheduler_type="linear-warmup+cosine-decay", warmup_steps=3, total_steps=20)
+    ref = torch.optim.AdamW([torch.nn.Parameter(torch.zeros(1))], lr=2e-5)
+    sched = torch.optim.lr_scheduler.LambdaLR(ref, lambda s: (s / 3.0) if s < 3 else max(
+        0.0, 0.5 * (1.0 + math.cos(math.pi * (s - 3) / 17.0))))       # the lambda of get_cosine_schedule_with_warmup
+    for k in range(1, 21):
+        tr.step_count = k
+        assert abs(tr.current_lr() - ref.param_groups[0]["lr"]) < 1e-12, k
+        ref.step()
+        sched.step()
+    assert DataParallelTrainer(m, lr=1e-4).current_lr() == 1e-4
+
+
 def test_gradient_exchange_world2(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)

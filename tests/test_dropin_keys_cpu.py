@@ -107,3 +107,22 @@ def test_vlm_device_property():
     c = case_cfg("tiny_img")
     mla, _ = build_state_dict(c, dtype=torch.float32)
     assert mla.vlm.device == torch.device("cpu")
+
+
+def test_initialize_weights_reaches_decoder_projections():
+    """prismatic.py:299-321: `self.apply(_basic_init)` xavier-initialises EVERY nn.Linear, the LLM's q/k/v/o/gate/up/down
+    included (they are `_Proj` holders here) — bounded by sqrt(6 / (fan_in + fan_out)), unlike the HF N(0, 0.02) init."""
+    import math
+    import torch
+    from mla_b200.backbone import LLMBackbone, LlamaConfig
+    from mla_b200.vlm import PrismaticVLM
+    torch.manual_seed(0)
+    cfg = LlamaConfig(vocab_size=32064, hidden_size=128, intermediate_size=352, num_hidden_layers=2, num_attention_heads=4)
+    vlm = PrismaticVLM("tiny", LLMBackbone(config=cfg), token_size=128, action_dim=7, use_diff=True, use_pointcloud=False,
+                       use_tactile=False, use_contrastive=False, use_generation=False)
+    vlm.initialize_weights()
+    for name, (fi, fo) in (("self_attn.q_proj", (128, 128)), ("mlp.gate_proj", (128, 352)), ("mlp.down_proj", (352, 128))):
+        w = vlm.llm_backbone.llm.model.layers[1].get_submodule(name).weight
+        bound = math.sqrt(6.0 / (fi + fo))
+        assert float(w.abs().max()) <= bound + 1e-6, name
+        assert float(w.std()) == pytest.approx(bound / math.sqrt(3.0), rel=0.05), name       # uniform(-b, b)

@@ -106,8 +106,6 @@ def test_fused_rope_epilogue(cuda_lib, mode):
         cuda_lib.mla_gemm_set_mode(C.c_int32(1))
 
 
-@pytest.mark.skipif(__import__("os").environ.get("MLA_EXPERIMENTAL") != "1",
-                    reason="SwiGLU-in-epilogue was written without GPU time left to validate it (round 1): opt-in")
 @pytest.mark.parametrize("M,f,K", [(1024, 256, 512), (3000, 1408, 1024), (17536, 11008, 4096)])
 def test_fused_swiglu_epilogue_matches_unfused(cuda_lib, M, f, K):
     """gate|up projection with SwiGLU in the CTA-pair epilogue == projection followed by swiglu_fwd, bit for bit."""
