@@ -177,18 +177,16 @@ def gemm_roofline(tokens: int, peak_tf: float, iters: int = 5):
             "launch_ms_avg": round(ms / len(calls), 4)}
 
 
-def reference_cpu(steps: int, warmup: int, layers_cpu: int = 4, threads: int = 0, workload: str = "cfg2"):
+def reference_cpu(steps: int, warmup: int, layers_cpu: int = 32, threads: int = 0, workload: str = "cfg2"):
     """The reference's OWN code on the host cores — `MLA.forward` + backward of the UNMODIFIED reference
     (models/mla/model_mla.py:118, imported from baseline/_ref or /root/reference through oracle/ref_shim.py; vendored
     transformers 4.40.1 Llama with SDPA attention: flash-attn has no CPU path), fp32 parameters under
-    autocast(cpu, bf16) as scripts/train.py builds them, all host threads.
+    autocast(cpu, bf16) as scripts/train.py builds them, all host threads, the full 32-layer Llama-2-7B-shaped model.
     Bounded sample of the workload: ONE of the step's 32 sequences (per-GPU batch 1 x 1 diffusion repeat = 548 fused
-    tokens) through a model with the first `layers_cpu` of the 32 decoder layers (everything else — tokenizers,
-    embedders, lm_head + CE, diffusion head, loss — at full size).  Every timed step is executed; the reported rate
-    is tokens x (layers_cpu / 32) / measured seconds, i.e. normalised to the full depth (the decoder is 97 % of the
-    FLOPs and linear in depth; the non-decoder parts are counted 32/layers_cpu times too often, which favours us by
-    a few percent and is stated here).  One full-depth step measured on the same host class is committed under
-    profiles/r02_ref_cpu_fulldepth.json.  Falls back to the oracle port when no reference tree is present."""
+    tokens) per timed step; every timed step is executed in full and value = 548 / measured seconds (no extrapolation
+    at the default depth).  `layers_cpu` < 32 (hosts short of the ~60 GB the fp32 model + gradients need) runs the
+    first layers only and normalises the rate by depth, which is then said in `sample`.
+    Falls back to the oracle port when no reference tree is present."""
     import contextlib
     import io
     threads = threads or os.cpu_count() or 1
@@ -201,8 +199,10 @@ def reference_cpu(steps: int, warmup: int, layers_cpu: int = 4, threads: int = 0
     from mla_b200.synthetic import make_batch
     use_pc = WORKLOADS[workload][0]
     quiet = contextlib.redirect_stdout(io.StringIO())        # the reference prints its loss dict every forward
+    t0 = time.perf_counter()
     with quiet, contextlib.redirect_stderr(io.StringIO()):
         mla, _ = build_reference_7b(workload, layers_cpu, torch.float32, "cpu", "sdpa")
+    t_build = time.perf_counter() - t0
     batch = make_batch(1, 32, 0, 672, 1024, seed=1234, use_pointcloud=use_pc, use_tactile=use_pc)
     params = [p for p in mla.parameters() if p.requires_grad]
     times = []
@@ -217,12 +217,13 @@ def reference_cpu(steps: int, warmup: int, layers_cpu: int = 4, threads: int = 0
             times.append(time.perf_counter() - t0)
     per_step = sum(times) / len(times)
     value = S * (layers_cpu / L) / per_step
+    depth = ("the full 32-layer model" if layers_cpu == L else
+             f"{layers_cpu} of {L} decoder layers at 7B width, rate normalised by depth ({layers_cpu}/{L})")
     return {"value": round(value, 3), "unit": "tokens/s", "cores": threads, "kind": "reference",
             "sample": f"unmodified reference MLA.forward+backward on CPU (fp32 params, autocast bf16, SDPA), 1 sequence x "
-                      f"{S} tokens through {layers_cpu} of {L} decoder layers at 7B width, {len(times)} timed steps of "
-                      f"{per_step:.2f} s each; rate normalised by depth ({layers_cpu}/{L}); full-depth check: "
-                      f"profiles/r02_ref_cpu_fulldepth.json",
-            "seconds_per_sample_step": round(per_step, 3), "layers_cpu": layers_cpu, "tokens_per_sample_step": S}
+                      f"{S} tokens (1 of the step's 32) through {depth}, {len(times)} timed steps of {per_step:.2f} s each",
+            "seconds_per_sample_step": round(per_step, 3), "layers_cpu": layers_cpu, "tokens_per_sample_step": S,
+            "build_seconds": round(t_build, 1)}
 
 
 def _port_cpu(steps: int, warmup: int, threads: int, sample_layers: int = 2):
@@ -254,9 +255,10 @@ def _port_cpu(steps: int, warmup: int, threads: int, sample_layers: int = 2):
 
 
 def cpu_baseline_subprocess(workload: str):
-    """cpu_baseline leg of our arm: the reference arm's sample (1 warm-up + 3 timed steps) in a child process, so the
-    import shim of the reference (it shadows `transformers`) never shares an interpreter with the product path."""
-    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
+    """cpu_baseline leg of our arm: the reference arm's sample (1 warm-up + 2 timed full-depth steps, ~20 s of CPU work
+    on the GPU box's 16 cores) in a child process, so the import shim of the reference (it shadows `transformers`) never
+    shares an interpreter with the product path."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
            "--workload", workload]
     env = dict(os.environ, CUDA_VISIBLE_DEVICES="", RANK="0", WORLD_SIZE="1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
@@ -508,7 +510,7 @@ def run_reference(args):
            "vs_baseline": None, "dtype": "bf16 autocast over fp32 params (CPU)", "data": "synthetic",
            "config": {"workload": f"{workload}: {desc}",
                       "sample": f"ms_per_step is the measured time of one SAMPLE step ({res['tokens_per_sample_step']} tokens "
-                                f"through {res['layers_cpu']}/{L} layers); value = depth-normalised tokens/s"},
+                                f"= 1 of the step's 32 sequences, {res['layers_cpu']}/{L} layers)"},
            "cpu_baseline": res,
            "e2e": {"value": res["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -526,7 +528,7 @@ def main():
     ap.add_argument("--save-level", default="auto", choices=["auto", "layer", "mlp", "none"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="single GPU: skip the secondary cfg3 measurement")
-    ap.add_argument("--layers-cpu", type=int, default=4, help="reference arm: decoder layers of the CPU sample")
+    ap.add_argument("--layers-cpu", type=int, default=32, help="reference arm: decoder layers of the CPU sample (32 = full model)")
     ap.add_argument("--stage", default="", choices=["", "pretrain", "finetune", "post-training"],
                     help="freeze_backbones stage (default: finetune; post-training for cfg5)")
     args = ap.parse_args()

@@ -78,10 +78,9 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
       : "memory");
 }
 
-// 576 threads x 112 registers = 63 K of the 64 K register file (__launch_bounds__(576) would round the block up to 640
-// threads and cap the kernel at 96 registers, which spills)
+// 18 warps are allocated as 20 (warp allocation granularity 4): 640 x 96 registers is what the register file allows
 template <int MODE>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(B2_THREADS, 1)
 attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __grid_constant__ CUtensorMap map_qkv_str,
                        const __grid_constant__ CUtensorMap map_do_fix, const __grid_constant__ CUtensorMap map_do_str,
                        Bw2Params p) {

@@ -68,17 +68,46 @@ def layer7b_errors(out, z):
     return e
 
 
+def layer7b_truth():
+    """fp32 evaluation of the same layer (oracle/llama.py on the bf16-rounded weights, torch fp32 on the GPU): the truth
+    both bf16 implementations are measured against.  Same keys as layer7b_errors' inputs."""
+    from golden.make_golden_gpu import LAYER7B, layer7b_inputs
+    from mla_b200 import llama
+    from oracle import fixtures, llama as O
+    c = LAYER7B
+    m = llama.LlamaModel(8, c["h"], c["f"], 1, c["heads"], eps=c["eps"])
+    sd = fixtures.fill_state_dict(m.layers[0].state_dict(), seed=7)
+    names = dict(q_proj="self_attn.q_proj.weight", k_proj="self_attn.k_proj.weight", v_proj="self_attn.v_proj.weight",
+                 o_proj="self_attn.o_proj.weight", gate_proj="mlp.gate_proj.weight", up_proj="mlp.up_proj.weight",
+                 down_proj="mlp.down_proj.weight", ln1="input_layernorm.weight", ln2="post_attention_layernorm.weight")
+    p = {k: sd[v].to(torch.bfloat16).float().cuda().requires_grad_(True) for k, v in names.items()}
+    x, dy, mask = layer7b_inputs("cuda")
+    xf = x.float().requires_grad_(True)
+    cos, sin = O.rope_tables(c["S"], c["h"] // c["heads"], 10000.0, torch.float32)
+    y = O.decoder_layer(xf, p, c["heads"], c["eps"], cos.cuda(), sin.cuda(), mask)
+    y.backward(dy.float())
+    return dict(y=y.detach().reshape(-1, c["h"]), dx=xf.grad.reshape(-1, c["h"]),
+                grads={v: p[k].grad for k, v in names.items()}, mask=mask.reshape(-1))
+
+
 def test_full_width_layer_matches_reference_gpu(cuda_lib):
+    """Ours vs the reference's GPU run of one full-width layer, judged against the fp32 truth: our bf16 result must be as
+    close to the truth as the reference's own bf16 (flash-attn) result is (x1.5 + floor), norms must agree to 1e-3, and
+    the two bf16 results must sit within twice the reference's own distance to the truth of each other."""
     z = _gold("layer7b")
-    e = layer7b_errors(run_layer7b(), z)
-    # the increment the layer adds to the residual stream is ~0.3 of |y|: 2e-3 on y is ~6e-3 on the increment
-    assert e["y_rows"] < 2e-3 and e["y_colsum"] < 2e-3 and e["y_norm"] < 5e-4, e
-    assert e["dx_rows"] < 6e-3 and e["dx_colsum"] < 6e-3 and e["dx_norm"] < 2e-3, e
-    for k, v in e.items():
-        if k.startswith("grad."):
-            assert v < 1e-2, (k, v)
-        if k.startswith("gradnorm."):
-            assert v < 3e-3, (k, v)
+    ours, truth = run_layer7b(), layer7b_truth()
+    e_ours_ref = layer7b_errors(ours, z)
+    e_ref_tru = layer7b_errors(truth, z)          # == distance(reference, truth) on the stored probes
+    rows = torch.from_numpy(z["rows"]).cuda()
+    e_ours_tru = {"y_rows": rel_err(ours["y"][rows], truth["y"][rows]), "dx_rows": rel_err(ours["dx"][rows], truth["dx"][rows])}
+    for k, g in ours["grads"].items():
+        e_ours_tru["grad." + k] = rel_err(g.flatten()[:65536], truth["grads"][k].flatten()[:65536])
+    for k, v in e_ours_tru.items():
+        assert v < 1.5 * e_ref_tru[k] + 1e-3, (k, "ours-vs-truth", v, "reference-vs-truth", e_ref_tru[k])
+        assert e_ours_ref[k] < 2.0 * e_ref_tru[k] + 2e-3, (k, "ours-vs-reference", e_ours_ref[k], "reference-vs-truth", e_ref_tru[k])
+    for k, v in e_ours_ref.items():
+        if k.endswith("_norm") or k.startswith("gradnorm."):
+            assert v < 1e-3, (k, v)
 
 
 def e2e_errors(name):
@@ -117,6 +146,17 @@ def e2e_errors(name):
     e["ref_gpu_vs_ref_cpu.total_loss"] = abs(float(zg["total_loss"]) - float(zc["total_loss"])) / abs(float(zc["total_loss"]))
     e["ref_gpu_vs_ref_cpu.hidden_last"] = rel_err(torch.from_numpy(zg["hidden_last"])[valid], torch.from_numpy(zc["hidden_last"])[valid])
     e["ref_gpu_vs_ref_cpu.noise_pred"] = rel_err(torch.from_numpy(zg["noise_pred"]), torch.from_numpy(zc["noise_pred"]))
+    e["ref_gpu_vs_ref_cpu.hidden_first"] = rel_err(torch.from_numpy(zg["hidden_first"]), torch.from_numpy(zc["hidden_first"]))
+    if "hidden_8" in zg.files and "hidden_8" in zc.files:
+        e["ref_gpu_vs_ref_cpu.hidden_8"] = rel_err(torch.from_numpy(zg["hidden_8"])[valid], torch.from_numpy(zc["hidden_8"])[valid])
+    for k in zg.files:
+        if k.startswith("gradnorm.") and k in zc.files:
+            e["ref_gpu_vs_ref_cpu." + k] = abs(float(zg[k]) - float(zc[k])) / float(zc[k])
+        elif k.startswith("grad.") and k in zc.files:
+            e["ref_gpu_vs_ref_cpu." + k] = rel_err(torch.from_numpy(zg[k]), torch.from_numpy(zc[k]))
+    for k in ("img_pc_contrastive_loss", "tactile_contrastive_loss"):
+        if k in zg.files and k in zc.files:
+            e["ref_gpu_vs_ref_cpu." + k] = abs(float(zg[k]) - float(zc[k])) / abs(float(zc[k]))
     return e
 
 
@@ -125,7 +165,7 @@ def test_mla_matches_reference_gpu_golden(cuda_lib, name):
     e = e2e_errors(name)
     # ours must sit as close to the reference's GPU run as the reference's own two backends sit to each other (x2 + floor)
     assert e["total_loss.gpu"] < 2 * e["ref_gpu_vs_ref_cpu.total_loss"] + 2e-3, e
-    assert e["hidden_first.gpu"] < 4e-3, e
+    assert e["hidden_first.gpu"] < 2 * e["ref_gpu_vs_ref_cpu.hidden_first"] + 4e-3, e
     assert e["hidden_last.gpu"] < 2 * e["ref_gpu_vs_ref_cpu.hidden_last"] + 4e-3, e
     assert e["noise_pred.gpu"] < 2 * e["ref_gpu_vs_ref_cpu.noise_pred"] + 4e-3, e
     for k, v in e.items():

@@ -35,13 +35,19 @@ def main():
                   f"{'' if rr is None else f'{rr:.2e}'} |")
         print()
     z = np.load(os.path.join(T.GOLD, "layer7b_gpu.npz"))
-    e = T.layer7b_errors(T.run_layer7b(), z)
+    ours, truth = T.run_layer7b(), T.layer7b_truth()
+    e, et = T.layer7b_errors(ours, z), T.layer7b_errors(truth, z)
+    rows = torch.from_numpy(z["rows"]).cuda()
+    eo = {"y_rows": T.rel_err(ours["y"][rows], truth["y"][rows]), "dx_rows": T.rel_err(ours["dx"][rows], truth["dx"][rows])}
+    for k, g in ours["grads"].items():
+        eo["grad." + k] = T.rel_err(g.flatten()[:65536], truth["grads"][k].flatten()[:65536])
     print("## layer7b: one decoder layer at full Llama-2-7B width (h 4096, ffn 11008, 32 heads), 2 x 548 tokens, "
-          "second sequence padded, vs the reference LlamaDecoderLayer + flash_attn_varlen_func on B200\n")
-    print("| quantity | ours vs reference-GPU |")
-    print("|---|---|")
+          "second sequence padded, vs the reference LlamaDecoderLayer + flash_attn_varlen_func on B200 and vs the fp32 "
+          "truth of the same layer (oracle, fp32)\n")
+    print("| quantity | ours vs reference-GPU | ours vs fp32 truth | reference-GPU vs fp32 truth |")
+    print("|---|---|---|---|")
     for k, v in e.items():
-        print(f"| {k} | {v:.2e} |")
+        print(f"| {k} | {v:.2e} | {'' if k not in eo else f'{eo[k]:.2e}'} | {et[k]:.2e} |")
 
 
 if __name__ == "__main__":
