@@ -83,6 +83,18 @@ typedef struct mla_gemm_args {
    * default (MLA_FUSE_SWIGLU=0 restores the separate pass). */
   void* swiglu_out;
   int64_t ld_swiglu;
+  /* Fused SwiGLU BACKWARD for the input-gradient GEMM of the down projection (autograd of modeling_llama.py:240):
+   * with A = dy [M, h] and B = W_down, N = f (a multiple of 32), the epilogue rounds d_act = dy . W_down to bf16, reads
+   * gate|up from swiglu_bwd_gu (bf16 [M, 2f]) and writes d(gate|up) to swiglu_bwd_dgu (bf16 [M, 2f]) and, when
+   * swiglu_bwd_act is not NULL, the re-materialised act = bf16(bf16(silu(gate)) * up) (bf16 [M, f], the operand of the
+   * down projection's weight gradient).  c is not written.  Bit-identical to the GEMM followed by mla_swiglu_bwd_act.
+   * NULL swiglu_bwd_gu = off. */
+  const void* swiglu_bwd_gu;
+  int64_t ld_swiglu_bwd_gu;
+  void* swiglu_bwd_dgu;
+  int64_t ld_swiglu_bwd_dgu;
+  void* swiglu_bwd_act;
+  int64_t ld_swiglu_bwd_act;
 } mla_gemm_args;
 int mla_gemm_bf16(const mla_gemm_args* args, void* stream);
 /* Kernel selection for mla_gemm_bf16: 0 = one CTA per 128x256 tile, 1 = CTA pairs (tcgen05.mma.cta_group::2, 256x256
@@ -158,6 +170,10 @@ int mla_attn_bwd_sm100(const void* qkv, int64_t ld_qkv, const void* o, const voi
 int mla_attn_bwd2_sm100(const void* qkv, int64_t ld_qkv, const void* o, const void* d_o, int64_t ld_o, const void* lse,
                         const void* mask, void* dqkv, int64_t ld_dqkv, void* workspace, const void* rope_cos,
                         const void* rope_sin, int32_t batch, int32_t seq, int32_t heads, float scale, void* stream);
+/* How mla_attn_bwd2_sm100 hands P / dS to its accumulation MMAs: 1 (default; env MLA_ATTN_BWD_TS) = packed bf16 in
+ * tensor memory, read as the A operand straight from TMEM (no shared-memory staging: the kernel is bound by
+ * shared-memory operand bandwidth); 0 = staged in 128B-swizzled shared memory.  Same results bit for bit. */
+int mla_attn_bwd2_set_ts(int32_t on);
 
 /* ---- small row/elementwise kernels around the GEMMs ---------------------------------------------------------
  * (ATen glue in the reference: dtype casts under autocast, activation backward, bias gradients, torch.cat / index

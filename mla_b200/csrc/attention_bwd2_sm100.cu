@@ -23,6 +23,8 @@
 // tiles in a zig-zag and walk them persistently.
 // TMEM (512 cols): [S0|dP0|S1|dP1] 4 x 64, accumulators @256 (dV or dQ) and @384 (dK).
 // smem: fixed 2x32 KB | streamed 3 slots x (16+16) KB | 2 x (P^T 16 KB + dS^T 16 KB) | barriers | per-column lse/delta.
+#include <cstdlib>
+
 #include "mla_internal.cuh"
 #include "ptx.cuh"
 
@@ -79,7 +81,34 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 }
 
 // 18 warps are allocated as 20 (warp allocation granularity 4): 640 x 96 registers is what the register file allows
-template <int MODE>
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void b2_tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (bf16, two K-elements per 32-bit column, row = TMEM lane) is read
+// from tensor memory, so it costs no shared-memory bandwidth.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// TS = 1: P^T / dS^T (P / dS) are handed to the accumulation MMAs through TENSOR memory instead of shared memory: each
+// math thread packs its 32 values to bf16 pairs and stores them (tcgen05.st) over the first half of the S / dP columns it
+// has just read, and the accumulation products take their A operand from there.  The kernel is shared-memory-bandwidth
+// bound (the tensor core re-reads its A operand from shared memory for every K = 16 step: 160 KB per streamed tile at
+// 128 B/clk); this removes 32 KB of operand reads and 32 KB of staging writes per tile.  The S/dP buffer of group g is
+// recycled by the score products of tile c + 2, which the in-order tensor pipe executes after the accumulation products
+// of tile c that read it — no extra barrier.
+template <int MODE, int TS>
 __global__ void __launch_bounds__(B2_THREADS, 1)
 attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __grid_constant__ CUtensorMap map_qkv_str,
                        const __grid_constant__ CUtensorMap map_do_fix, const __grid_constant__ CUtensorMap map_do_str,
@@ -199,7 +228,7 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
       auto issue_sd = [&](int c) {
         const int s = c % B2_SLOTS, g = c & 1;
         mbar_wait(&in_full[s], (c / B2_SLOTS) & 1);
-        mbar_wait(&sd_empty[g], ((c >> 1) & 1) ^ 1);
+        if (!TS) mbar_wait(&sd_empty[g], ((c >> 1) & 1) ^ 1);   // TS: ordered behind ACC(c - 2) by the in-order tensor pipe
         tc_fence_after();
         const uint32_t aX = smem_u32(sX + s * B2_STR_BYTES), aY = smem_u32(sY + s * B2_STR_BYTES);
         const uint32_t tS = tmem_base + g * 128, tP = tS + 64;
@@ -239,7 +268,17 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
 #pragma unroll
           for (int kk = 0; kk < B2_IN / 16; ++kk) {
             const uint32_t acc = (j | kk) != 0 ? 1u : 0u;
-            if (MODE == 0) {
+            if (TS) {
+              // A from TMEM: 16 streamed columns = 8 packed TMEM columns; half h of the tile sits at column 32 h of its
+              // S (P^T) / dP (dS^T) block
+              const uint32_t tP = tmem_base + g * 128 + (kk >> 1) * 32 + (kk & 1) * 8, tD = tP + 64;
+              if (MODE == 0) {
+                umma_f16_ts(tmem_acc0, tP, umma_smem_desc_sw128(aY + kk * 2048, B2_STR_BYTES / 2, 1024), idesc_acc, acc);
+                umma_f16_ts(tmem_acc1, tD, umma_smem_desc_sw128(aX + kk * 2048, B2_STR_BYTES / 2, 1024), idesc_acc, acc);
+              } else {
+                umma_f16_ts(tmem_acc0, tD, umma_smem_desc_sw128(aX + kk * 2048, B2_STR_BYTES / 2, 1024), idesc_acc, acc);
+              }
+            } else if (MODE == 0) {
               umma_f16_ss(tmem_acc0, umma_smem_desc_sw128(aP + kk * 32, 16, 1024),
                           umma_smem_desc_sw128(aY + kk * 2048, B2_STR_BYTES / 2, 1024), idesc_acc, acc);   // dV += P^T.dO
               umma_f16_ss(tmem_acc1, umma_smem_desc_sw128(aD + kk * 32, 16, 1024),
@@ -307,12 +346,15 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
         tmem_ld_32x32b_x32(tS, vs);
         tmem_ld_32x32b_x32(tS + 64, vp);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sd_empty[grp]);
-        // this group's staging buffers are free once the accumulation MMAs of its previous tile (c - 2) retired
-        if (c >= 2) mbar_wait(&acc_done[grp], ((c >> 1) - 1) & 1);
+        if (!TS) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sd_empty[grp]);
+          // this group's staging buffers are free once the accumulation MMAs of its previous tile (c - 2) retired
+          if (c >= 2) mbar_wait(&acc_done[grp], ((c >> 1) - 1) & 1);
+        }
         const float4* stat4 = reinterpret_cast<const float4*>(s_stat + slot * 128 + half * 32);   // MODE 0: lse2 | delta
+        uint32_t pkp[8], pkd[8];
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
           float l2v[8], dlv[8];
@@ -338,14 +380,28 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
             pr[e] = pv;
             ds[e] = pv * (__uint_as_float(vp[cc]) - dl);
           }
-          const int off = r * 128 + (((half * 4 + g8) ^ (r & 7)) * 16);
-          if (MODE == 0)
-            *reinterpret_cast<uint4*>(myT1 + off) = make_uint4(pack_bf16x2(pr[0], pr[1]), pack_bf16x2(pr[2], pr[3]),
-                                                               pack_bf16x2(pr[4], pr[5]), pack_bf16x2(pr[6], pr[7]));
-          *reinterpret_cast<uint4*>(myT2 + off) = make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]),
-                                                             pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
+          if (TS) {
+            if (MODE == 0) {
+              pkp[(g8 & 1) * 4 + 0] = pack_bf16x2(pr[0], pr[1]); pkp[(g8 & 1) * 4 + 1] = pack_bf16x2(pr[2], pr[3]);
+              pkp[(g8 & 1) * 4 + 2] = pack_bf16x2(pr[4], pr[5]); pkp[(g8 & 1) * 4 + 3] = pack_bf16x2(pr[6], pr[7]);
+            }
+            pkd[(g8 & 1) * 4 + 0] = pack_bf16x2(ds[0], ds[1]); pkd[(g8 & 1) * 4 + 1] = pack_bf16x2(ds[2], ds[3]);
+            pkd[(g8 & 1) * 4 + 2] = pack_bf16x2(ds[4], ds[5]); pkd[(g8 & 1) * 4 + 3] = pack_bf16x2(ds[6], ds[7]);
+            if (g8 & 1) {     // 16 values = 8 packed columns ready: over this thread's own (already read) S / dP columns
+              if (MODE == 0) tmem_st_32x32b_x8(tS + (g8 >> 1) * 8, pkp);
+              tmem_st_32x32b_x8(tS + 64 + (g8 >> 1) * 8, pkd);
+            }
+          } else {
+            const int off = r * 128 + (((half * 4 + g8) ^ (r & 7)) * 16);
+            if (MODE == 0)
+              *reinterpret_cast<uint4*>(myT1 + off) = make_uint4(pack_bf16x2(pr[0], pr[1]), pack_bf16x2(pr[2], pr[3]),
+                                                                 pack_bf16x2(pr[4], pr[5]), pack_bf16x2(pr[6], pr[7]));
+            *reinterpret_cast<uint4*>(myT2 + off) = make_uint4(pack_bf16x2(ds[0], ds[1]), pack_bf16x2(ds[2], ds[3]),
+                                                               pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
+          }
         }
-        fence_proxy_async();
+        if (TS) b2_tmem_st_wait();
+        else fence_proxy_async();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ds_full[grp]);
@@ -442,6 +498,14 @@ using namespace mla;
 // mla_attn_bwd_sm100_workspace) plus: rope_cos / rope_sin (bf16 [seq, 64], or null) — when given, the gradients written
 // to the q and k column blocks of dqkv are those w.r.t. the PRE-RoPE projections (the transposed rotation is applied in
 // the epilogue), i.e. dqkv is ready for the weight-gradient / input-gradient GEMMs of the q|k|v projection.
+static int g_bwd2_ts = [] { const char* e = getenv("MLA_ATTN_BWD_TS"); return e ? atoi(e) : 1; }();
+
+// 0: P/dS staged in shared memory; 1 (default): handed over in tensor memory (A operand of the accumulation MMAs in TMEM)
+extern "C" int mla_attn_bwd2_set_ts(int32_t on) {
+  g_bwd2_ts = on ? 1 : 0;
+  return MLA_OK;
+}
+
 extern "C" int mla_attn_bwd2_sm100(const void* qkv, int64_t ld_qkv, const void* o, const void* d_o, int64_t ld_o,
                                    const void* lse, const void* mask, void* dqkv, int64_t ld_dqkv, void* workspace,
                                    const void* rope_cos, const void* rope_sin, int32_t batch, int32_t seq, int32_t heads,
@@ -471,9 +535,13 @@ extern "C" int mla_attn_bwd2_sm100(const void* qkv, int64_t ld_qkv, const void* 
   if (int rc = encode_tmap_2d_bf16(&m_do_str, d_o, dims_do, st_do, box_str)) return rc;
   static bool done = false;
   if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd2_sm100_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd2_sm100_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attn_bwd2_sm100_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
+      e = cudaFuncSetAttribute(attn_bwd2_sm100_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd2_sm100_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd2_sm100_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM);
     if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "attn_bwd2_sm100 smem attr: %s", cudaGetErrorString(e));
     done = true;
   }
@@ -482,9 +550,12 @@ extern "C" int mla_attn_bwd2_sm100(const void* qkv, int64_t ld_qkv, const void* 
   p.lse2 = lse2; p.delta = delta; p.mask = (const uint8_t*)mask;
   p.dqkv = (__nv_bfloat16*)dqkv; p.ld_dqkv = ld_dqkv;
   p.rope_cos = (const __nv_bfloat16*)rope_cos; p.rope_sin = (const __nv_bfloat16*)rope_sin;
-  attn_bwd2_sm100_kernel<0><<<batch * heads * 2, B2_THREADS, B2_SMEM, s>>>(m_qkv_fix, m_qkv_str, m_do_fix, m_do_str, p);
+  const int grid = batch * heads * 2;
+  if (g_bwd2_ts) attn_bwd2_sm100_kernel<0, 1><<<grid, B2_THREADS, B2_SMEM, s>>>(m_qkv_fix, m_qkv_str, m_do_fix, m_do_str, p);
+  else attn_bwd2_sm100_kernel<0, 0><<<grid, B2_THREADS, B2_SMEM, s>>>(m_qkv_fix, m_qkv_str, m_do_fix, m_do_str, p);
   MLA_CHECK_LAUNCH("attn_bwd2_sm100_dkv");
-  attn_bwd2_sm100_kernel<1><<<batch * heads * 2, B2_THREADS, B2_SMEM, s>>>(m_qkv_fix, m_qkv_str, m_do_fix, m_do_str, p);
+  if (g_bwd2_ts) attn_bwd2_sm100_kernel<1, 1><<<grid, B2_THREADS, B2_SMEM, s>>>(m_qkv_fix, m_qkv_str, m_do_fix, m_do_str, p);
+  else attn_bwd2_sm100_kernel<1, 0><<<grid, B2_THREADS, B2_SMEM, s>>>(m_qkv_fix, m_qkv_str, m_do_fix, m_do_str, p);
   MLA_CHECK_LAUNCH("attn_bwd2_sm100_dq");
   return MLA_OK;
 }

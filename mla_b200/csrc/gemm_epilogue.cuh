@@ -30,6 +30,14 @@ struct GemmEpilogue {
   __nv_bfloat16* swiglu_out;       // bf16 [M, swiglu_f] = bf16(bf16(silu(gate)) * up)
   int64_t ld_swiglu;
   int swiglu_f;                    // columns of gate (= of up); 0 = off
+  // fused SwiGLU BACKWARD (the input-gradient GEMM of the down projection, d_act = dy . Wd, N = f): the epilogue reads
+  // gate|up, rounds d_act to bf16 and writes d(gate|up) and the re-materialised act instead of d_act itself
+  const __nv_bfloat16* sb_gu;      // bf16 [M, 2f] (gate | up); null = off
+  int64_t ld_sb_gu;
+  __nv_bfloat16* sb_dgu;           // bf16 [M, 2f]
+  int64_t ld_sb_dgu;
+  __nv_bfloat16* sb_act;           // bf16 [M, f] or null
+  int64_t ld_sb_act;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -151,6 +159,34 @@ __device__ __forceinline__ void gemm_store_tile(const GemmEpilogue& ep, uint32_t
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
+    if (ep.sb_gu != nullptr) {
+      // SwiGLU backward (N = f, a multiple of 32): same rounding points as d_act -> bf16 -> swiglu_bwd_kernel
+      const __nv_bfloat16* grow = ep.sb_gu + row * ep.ld_sb_gu + col0;
+      __nv_bfloat16* dgrow = ep.sb_dgu + row * ep.ld_sb_dgu + col0;
+      __nv_bfloat16* arow = ep.sb_act ? ep.sb_act + row * ep.ld_sb_act + col0 : nullptr;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const uint4 gq = *reinterpret_cast<const uint4*>(grow + j);
+        const uint4 uq = *reinterpret_cast<const uint4*>(grow + N + j);
+        const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gq);
+        const __nv_bfloat162* uh = reinterpret_cast<const __nv_bfloat162*>(&uq);
+        float dg[8], du[8], ac[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 gf = __bfloat1622float2(gh[t]), uf = __bfloat1622float2(uh[t]);
+          swiglu_bwd_elem(gf.x, uf.x, bf16_round(v[j + 2 * t]), dg[2 * t], du[2 * t], ac[2 * t]);
+          swiglu_bwd_elem(gf.y, uf.y, bf16_round(v[j + 2 * t + 1]), dg[2 * t + 1], du[2 * t + 1], ac[2 * t + 1]);
+        }
+        *reinterpret_cast<uint4*>(dgrow + j) = make_uint4(pack_bf16x2(dg[0], dg[1]), pack_bf16x2(dg[2], dg[3]),
+                                                         pack_bf16x2(dg[4], dg[5]), pack_bf16x2(dg[6], dg[7]));
+        *reinterpret_cast<uint4*>(dgrow + N + j) = make_uint4(pack_bf16x2(du[0], du[1]), pack_bf16x2(du[2], du[3]),
+                                                             pack_bf16x2(du[4], du[5]), pack_bf16x2(du[6], du[7]));
+        if (arow)
+          *reinterpret_cast<uint4*>(arow + j) = make_uint4(pack_bf16x2(ac[0], ac[1]), pack_bf16x2(ac[2], ac[3]),
+                                                          pack_bf16x2(ac[4], ac[5]), pack_bf16x2(ac[6], ac[7]));
+      }
+      continue;
+    }
     if (ep.c_dtype == 1) {
       // fp32 output (weight gradients): optional accumulate, no activation path.
       float* crow = reinterpret_cast<float*>(ep.c) + row * ep.ldc + col0;

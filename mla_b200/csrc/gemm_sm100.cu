@@ -325,6 +325,20 @@ extern "C" int mla_gemm_bf16(const mla_gemm_args* g, void* stream_) {
   ep.rope_seq = g->rope_seq; ep.rope_cols = g->rope_cols;
   ep.swiglu_out = static_cast<__nv_bfloat16*>(g->swiglu_out); ep.ld_swiglu = g->ld_swiglu;
   ep.swiglu_f = g->swiglu_out ? int(g->n / 2) : 0;
+  ep.sb_gu = static_cast<const __nv_bfloat16*>(g->swiglu_bwd_gu); ep.ld_sb_gu = g->ld_swiglu_bwd_gu;
+  ep.sb_dgu = static_cast<__nv_bfloat16*>(g->swiglu_bwd_dgu); ep.ld_sb_dgu = g->ld_swiglu_bwd_dgu;
+  ep.sb_act = static_cast<__nv_bfloat16*>(g->swiglu_bwd_act); ep.ld_sb_act = g->ld_swiglu_bwd_act;
+  if (g->swiglu_bwd_gu != nullptr) {
+    if (g->swiglu_out || g->c_dtype != 0 || g->bias || g->residual || g->pre_act || g->activation != MLA_ACT_NONE ||
+        g->rope_cols != 0 || g->accumulate)
+      return set_error(MLA_ERR_ARG, "gemm: fused SwiGLU backward applies to a plain bf16 input-gradient GEMM");
+    if (!g->swiglu_bwd_dgu || (g->n & 31) || (g->ld_swiglu_bwd_gu & 7) || (g->ld_swiglu_bwd_dgu & 7) ||
+        (g->swiglu_bwd_act && (g->ld_swiglu_bwd_act & 7)) || g->ld_swiglu_bwd_gu < 2 * g->n || g->ld_swiglu_bwd_dgu < 2 * g->n ||
+        (reinterpret_cast<uintptr_t>(g->swiglu_bwd_gu) & 15) || (reinterpret_cast<uintptr_t>(g->swiglu_bwd_dgu) & 15) ||
+        (reinterpret_cast<uintptr_t>(g->swiglu_bwd_act) & 15))
+      return set_error(MLA_ERR_ARG, "gemm: fused SwiGLU backward needs N = f a multiple of 32, gate|up and d(gate|up) of "
+                                    "[M, 2f] with 16-byte aligned rows");
+  }
   if (g->swiglu_out != nullptr) {
     if (g->a_mn_major || g->b_mn_major || g->c_dtype != 0 || g->bias || g->residual || g->pre_act ||
         g->activation != MLA_ACT_NONE || g->rope_cols != 0)

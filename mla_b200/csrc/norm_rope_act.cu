@@ -303,14 +303,7 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dact, const 
     unpack8(*reinterpret_cast<const uint4*>(gu + r * 2 * f + f + c * 8), u);
     unpack8(*reinterpret_cast<const uint4*>(dact + r * f + c * 8), d);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float s = sigmoidf_(g[j]);
-      const float a = bf16_round(g[j] * s);
-      ac[j] = a * u[j];
-      du[j] = d[j] * a;
-      const float da = bf16_round(d[j] * u[j]);
-      dg[j] = da * (s * (1.f + g[j] * (1.f - s)));
-    }
+    for (int j = 0; j < 8; ++j) swiglu_bwd_elem(g[j], u[j], d[j], dg[j], du[j], ac[j]);
     *reinterpret_cast<uint4*>(dgu + r * 2 * f + c * 8) = pack8(dg);
     *reinterpret_cast<uint4*>(dgu + r * 2 * f + f + c * 8) = pack8(du);
     if (act_out) *reinterpret_cast<uint4*>(act_out + r * f + c * 8) = pack8(ac);

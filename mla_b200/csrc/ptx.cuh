@@ -160,4 +160,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// SwiGLU backward of one element (LlamaMLP, modeling_llama.py:240, autograd of act_fn(gate) * up on the bf16 path):
+// shared by swiglu_bwd_kernel (norm_rope_act.cu) and the fused epilogue of the down-projection's input-gradient GEMM
+// (gemm_epilogue.cuh) so that both produce the same bits.  g, u: gate / up; d: d(act).
+__device__ __forceinline__ void swiglu_bwd_elem(float g, float u, float d, float& dg, float& du, float& act) {
+  const float s = 1.f / (1.f + __expf(-g));
+  const float a = bf16_round(g * s);
+  act = a * u;
+  du = d * a;
+  const float da = bf16_round(d * u);
+  dg = da * (s * (1.f + g * (1.f - s)));
+}
+
 }  // namespace mla

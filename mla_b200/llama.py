@@ -36,6 +36,9 @@ FUSE_ROPE = {"on": os.environ.get("MLA_FUSE_ROPE", "1") == "1"}     # RoPE insid
 # SwiGLU inside the gate|up GEMM epilogue (CTA-pair kernel; inter % 128 == 0): bit-identical to the projection followed
 # by swiglu_fwd (tests/test_gemm2_gpu.py, validated on B200 in round 2).  MLA_FUSE_SWIGLU=0 restores the separate pass.
 FUSE_SWIGLU = {"on": os.environ.get("MLA_FUSE_SWIGLU", "1") == "1"}
+# SwiGLU BACKWARD inside the epilogue of the down projection's input-gradient GEMM (d_act is never written): same bits
+# as the GEMM followed by swiglu_bwd_act.  MLA_FUSE_SWIGLU_BWD=0 restores the separate pass.
+FUSE_SWIGLU_BWD = {"on": os.environ.get("MLA_FUSE_SWIGLU_BWD", "1") == "1"}
 
 
 def side_stream(device) -> "torch.cuda.Stream":
@@ -256,9 +259,16 @@ class LlamaDecoderLayer(nn.Module):
             a.record_stream(side)
 
         # ---- MLP half
-        dact = ops.gemm(dy, wd, b_mn=True)                                           # dact = dy Wd
-        dgu, act = ops.swiglu_bwd_act(dact, gu)                                      # + act = swiglu(gu), one pass
-        del dact, gu
+        if FUSE_SWIGLU_BWD["on"] and self.inter % 32 == 0:
+            # d_act = dy Wd never reaches HBM: the GEMM's epilogue turns it into d(gate|up) and re-materialises act
+            dgu = torch.empty_like(gu)
+            act = torch.empty((gu.shape[0], self.inter), dtype=torch.bfloat16, device=gu.device)
+            ops.gemm(dy, wd, b_mn=True, swiglu_bwd=(gu, dgu, act))
+        else:
+            dact = ops.gemm(dy, wd, b_mn=True)                                       # dact = dy Wd
+            dgu, act = ops.swiglu_bwd_act(dact, gu)                                  # + act = swiglu(gu), one pass
+            del dact
+        del gu
         wgrad(dy, act, gd)                                                           # dWd  = dy^T act
         del act
         wgrad(dgu, n2, ggu)                                                          # dWgu = dgu^T n2

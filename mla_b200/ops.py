@@ -41,13 +41,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, residual: Optional[torch.Tensor] = None,
          pre_act: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = False,
          rope: Optional[tuple] = None, swiglu_out: Optional[torch.Tensor] = None,
-         store_c: bool = True) -> torch.Tensor:
+         store_c: bool = True, swiglu_bwd: Optional[tuple] = None) -> torch.Tensor:
     """C = epilogue(alpha * A_op @ B_op).
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True);  b: [N,K] (b_mn=False, nn.Linear weight) or [K,N] (b_mn=True).
     rope = (cos [S,64] bf16, sin [S,64] bf16, S, n_cols): rotate the leading n_cols columns (head_dim 128) in the epilogue.
     swiglu_out (see include/mla_b200.h): bf16 [M, N/2] receiving SwiGLU of the [gate | up] projection in
     the epilogue; with store_c=False the projection itself is not written (returns None).
+    swiglu_bwd = (gu [M, 2N] bf16, dgu [M, 2N] bf16, act [M, N] bf16 or None): the product is d_act of a SwiGLU whose
+    gate|up is gu; the epilogue writes d(gate|up) into dgu and the re-materialised act, and nothing else (returns None).
     """
     _req(a, torch.bfloat16, "a")
     _req(b, torch.bfloat16, "b")
@@ -57,7 +59,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     N, Kb = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
     if K != Kb:
         raise _lib.MlaError(f"gemm: contraction mismatch {K} vs {Kb}")
-    if swiglu_out is not None and not store_c:
+    if swiglu_bwd is not None or (swiglu_out is not None and not store_c):
         out, ldc = None, N
     else:
         if out is None:
@@ -99,6 +101,19 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         if tuple(swiglu_out.shape) != (M, N // 2):
             raise _lib.MlaError(f"gemm: swiglu_out shape {tuple(swiglu_out.shape)} != {(M, N // 2)}")
         g.swiglu_out, g.ld_swiglu = swiglu_out.data_ptr(), _rowmajor_2d(swiglu_out, "swiglu_out")
+    if swiglu_bwd is not None:
+        gu_t, dgu_t, act_t = swiglu_bwd
+        _req(gu_t, torch.bfloat16, "swiglu_bwd gu")
+        _req(dgu_t, torch.bfloat16, "swiglu_bwd dgu")
+        if tuple(gu_t.shape) != (M, 2 * N) or tuple(dgu_t.shape) != (M, 2 * N):
+            raise _lib.MlaError(f"gemm: swiglu_bwd gu / dgu must be [{M}, {2 * N}]")
+        g.swiglu_bwd_gu, g.ld_swiglu_bwd_gu = gu_t.data_ptr(), _rowmajor_2d(gu_t, "swiglu_bwd gu")
+        g.swiglu_bwd_dgu, g.ld_swiglu_bwd_dgu = dgu_t.data_ptr(), _rowmajor_2d(dgu_t, "swiglu_bwd dgu")
+        if act_t is not None:
+            _req(act_t, torch.bfloat16, "swiglu_bwd act")
+            if tuple(act_t.shape) != (M, N):
+                raise _lib.MlaError(f"gemm: swiglu_bwd act must be [{M}, {N}]")
+            g.swiglu_bwd_act, g.ld_swiglu_bwd_act = act_t.data_ptr(), _rowmajor_2d(act_t, "swiglu_bwd act")
     if DYNAMIC_TILES["on"]:
         g.sched_ws = _sched_ws(a.device).data_ptr()
     check(_lib.lib().mla_gemm_bf16(C.byref(g), _stream()))

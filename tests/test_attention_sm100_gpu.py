@@ -124,15 +124,19 @@ def test_attn_bwd_pipelined_matches_first_generation(cuda_lib, B, S, H, masked):
         ops.ATTN_IMPL["bwd"] = "sm100"
         want = ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, mask)
         ops.ATTN_IMPL["bwd"] = "sm100v2"
-        for _ in range(3):      # several launches back to back: barrier phases / TMEM re-allocation
-            got = ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, mask)
-        torch.cuda.synchronize()
-        assert torch.equal(got, want)
-        got_r = ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, mask, rope=(cos, sin))
-        ops.rope_(want, 0, 2 * H, D, S, cos, sin, transpose=True)
-        torch.cuda.synchronize()
-        assert torch.equal(got_r, want)
+        want_r = want.clone()
+        ops.rope_(want_r, 0, 2 * H, D, S, cos, sin, transpose=True)
+        for ts in (0, 1):       # P/dS staged in shared memory | handed over in tensor memory (A operand from TMEM)
+            cuda_lib.mla_attn_bwd2_set_ts(ts)
+            for _ in range(3):      # several launches back to back: barrier phases / TMEM re-allocation
+                got = ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, mask)
+            torch.cuda.synchronize()
+            assert torch.equal(got, want), ts
+            got_r = ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, mask, rope=(cos, sin))
+            torch.cuda.synchronize()
+            assert torch.equal(got_r, want_r), ts
     finally:
+        cuda_lib.mla_attn_bwd2_set_ts(1)
         ops.ATTN_IMPL.update(keep)
 
 
@@ -144,8 +148,9 @@ def test_attn_bwd_sm100_speed(cuda_lib):
     dctx = torch.randn_like(ctx)
     res = {}
     keep = dict(ops.ATTN_IMPL)
-    for impl in ("mma", "sm100", "sm100v2"):
-        ops.ATTN_IMPL["bwd"] = impl
+    for impl in ("mma", "sm100", "sm100v2s", "sm100v2"):
+        ops.ATTN_IMPL["bwd"] = impl.rstrip("s") if impl.startswith("sm100v2") else impl
+        cuda_lib.mla_attn_bwd2_set_ts(0 if impl == "sm100v2s" else 1)
         for _ in range(3):
             ops.attn_bwd(dctx, qkv, ctx, lse, B, S, H, D, None)
         torch.cuda.synchronize()
@@ -159,4 +164,5 @@ def test_attn_bwd_sm100_speed(cuda_lib):
     ops.ATTN_IMPL.update(keep)
     fl = 2.5 * 4.0 * S * S * D * H * B / 2
     print(f"\nattn bwd [32,548,32,128]: mma.sync {res['mma']:.3f} ms, tcgen05 gen 1 {res['sm100']:.3f} ms "
-          f"({fl / res['sm100'] / 1e9:.0f} TFLOP/s), pipelined {res['sm100v2']:.3f} ms ({fl / res['sm100v2'] / 1e9:.0f} TFLOP/s)")
+          f"({fl / res['sm100'] / 1e9:.0f} TFLOP/s), pipelined/smem {res['sm100v2s']:.3f} ms "
+          f"({fl / res['sm100v2s'] / 1e9:.0f} TFLOP/s), pipelined/TMEM {res['sm100v2']:.3f} ms ({fl / res['sm100v2'] / 1e9:.0f} TFLOP/s)")

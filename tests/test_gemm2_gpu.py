@@ -123,3 +123,29 @@ def test_fused_swiglu_epilogue_matches_unfused(cuda_lib, M, f, K):
     act2 = torch.empty_like(act)
     assert ops.gemm(x, w, swiglu_out=act2, store_c=False) is None
     assert torch.equal(act2, act_ref)
+
+
+@pytest.mark.parametrize("M,f,K,mode", [(1024, 256, 512, 2), (3000, 1408, 1024, 2), (17536, 11008, 4096, 1), (300, 352, 128, 0)])
+def test_fused_swiglu_backward_epilogue_matches_unfused(cuda_lib, M, f, K, mode):
+    """d_act = dy . W_down with the SwiGLU backward in the epilogue == the GEMM followed by swiglu_bwd_act, bit for bit
+    (d(gate|up) and the re-materialised act); both the CTA-pair and the one-CTA kernel."""
+    from mla_b200 import ops
+    torch.manual_seed(M + f)
+    cuda_lib.mla_gemm_set_mode(C.c_int32(mode))
+    try:
+        dy = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+        wd = (torch.randn(K, f, device="cuda") * K ** -0.5).to(torch.bfloat16)        # W_down [h, f]: b_mn operand
+        gu = torch.randn(M, 2 * f, device="cuda").to(torch.bfloat16)
+        dact = ops.gemm(dy, wd, b_mn=True)
+        dgu_ref, act_ref = ops.swiglu_bwd_act(dact, gu)
+        dgu = torch.empty_like(gu)
+        act = torch.empty((M, f), dtype=torch.bfloat16, device="cuda")
+        assert ops.gemm(dy, wd, b_mn=True, swiglu_bwd=(gu, dgu, act)) is None
+        torch.cuda.synchronize()
+        assert torch.equal(dgu, dgu_ref)
+        assert torch.equal(act, act_ref)
+        dgu2 = torch.empty_like(gu)
+        ops.gemm(dy, wd, b_mn=True, swiglu_bwd=(gu, dgu2, None))
+        assert torch.equal(dgu2, dgu_ref)
+    finally:
+        cuda_lib.mla_gemm_set_mode(C.c_int32(1))
