@@ -129,7 +129,7 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
   int& s_any_masked = *reinterpret_cast<int*>(bars + 19);
   float* s_stat = reinterpret_cast<float*>(smem + B2_TILES_BYTES + 256);   // [slot][lse2|delta][64]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = int(warp_idx_uniform()), lane = threadIdx.x & 31;     // warp-uniform role index (see ptx.cuh)
   const int S = p.S;
   const int n_out = (S + B2_OUT - 1) / B2_OUT;
   const int n_in = (S + B2_IN - 1) / B2_IN;
@@ -221,32 +221,37 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // Executed by all 32 lanes (converged, warp-uniform values): barrier polls are warp-wide, every tcgen05.mma / commit
+    // elects its issuing lane itself.  Descriptors are built once and advanced by constants.
+    {
       constexpr uint32_t idesc_sd = umma_idesc_bf16(B2_OUT, B2_IN, 0, 0);    // 128 x 64,  K = d
       constexpr uint32_t idesc_acc = umma_idesc_bf16(B2_OUT, B2_D, 0, 1);    // 128 x 128, K = 64 streamed rows, B MN-major
-      const uint32_t aF1 = smem_u32(sF1), aF2 = smem_u32(sF2), aT1 = smem_u32(sT1), aT2 = smem_u32(sT2);
+      const uint64_t dF1 = umma_smem_desc_sw128(smem_u32(sF1), 16, 1024), dF2 = umma_smem_desc_sw128(smem_u32(sF2), 16, 1024);
+      const uint64_t dX0 = umma_smem_desc_sw128(smem_u32(sX), 16, 1024), dY0 = umma_smem_desc_sw128(smem_u32(sY), 16, 1024);
+      // the same streamed tiles read MN-major by the accumulation products (LBO = the other 64-column chunk)
+      const uint64_t dXm0 = umma_smem_desc_sw128(smem_u32(sX), B2_STR_BYTES / 2, 1024);
+      const uint64_t dYm0 = umma_smem_desc_sw128(smem_u32(sY), B2_STR_BYTES / 2, 1024);
+      const uint64_t dT1_0 = umma_smem_desc_sw128(smem_u32(sT1), 16, 1024), dT2_0 = umma_smem_desc_sw128(smem_u32(sT2), 16, 1024);
       auto issue_sd = [&](int c) {
         const int s = c % B2_SLOTS, g = c & 1;
         mbar_wait(&in_full[s], (c / B2_SLOTS) & 1);
         if (!TS) mbar_wait(&sd_empty[g], ((c >> 1) & 1) ^ 1);   // TS: ordered behind ACC(c - 2) by the in-order tensor pipe
         tc_fence_after();
-        const uint32_t aX = smem_u32(sX + s * B2_STR_BYTES), aY = smem_u32(sY + s * B2_STR_BYTES);
+        const uint64_t dX = umma_desc_advance(dX0, s * B2_STR_BYTES), dY = umma_desc_advance(dY0, s * B2_STR_BYTES);
         const uint32_t tS = tmem_base + g * 128, tP = tS + 64;
 #pragma unroll
         for (int kk = 0; kk < B2_D / 16; ++kk) {
           const uint32_t of = (kk >> 2) * (B2_FIX_BYTES / 2) + (kk & 3) * 32;
           const uint32_t os = (kk >> 2) * (B2_STR_BYTES / 2) + (kk & 3) * 32;
-          umma_f16_ss(tS, umma_smem_desc_sw128(aF1 + of, 16, 1024), umma_smem_desc_sw128(aX + os, 16, 1024), idesc_sd,
-                      kk != 0 ? 1u : 0u);
+          umma_f16_ss_elect(tS, umma_desc_advance(dF1, of), umma_desc_advance(dX, os), idesc_sd, kk != 0 ? 1u : 0u);
         }
 #pragma unroll
         for (int kk = 0; kk < B2_D / 16; ++kk) {
           const uint32_t of = (kk >> 2) * (B2_FIX_BYTES / 2) + (kk & 3) * 32;
           const uint32_t os = (kk >> 2) * (B2_STR_BYTES / 2) + (kk & 3) * 32;
-          umma_f16_ss(tP, umma_smem_desc_sw128(aF2 + of, 16, 1024), umma_smem_desc_sw128(aY + os, 16, 1024), idesc_sd,
-                      kk != 0 ? 1u : 0u);
+          umma_f16_ss_elect(tP, umma_desc_advance(dF2, of), umma_desc_advance(dY, os), idesc_sd, kk != 0 ? 1u : 0u);
         }
-        umma_commit(&sd_full[g]);
+        umma_commit_elect(&sd_full[g]);
       };
       int it = 0;
       for (int ti = 0;; ++ti) {
@@ -256,15 +261,15 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
         mbar_wait(fix_full, ti & 1);
         issue_sd(it);
         if (n > 1) issue_sd(it + 1);
-        else umma_commit(fix_empty);
+        else umma_commit_elect(fix_empty);
         for (int j = 0; j < n; ++j) {
           const int c = it + j;
           const int s = c % B2_SLOTS, g = c & 1;
           mbar_wait(&ds_full[g], (c >> 1) & 1);
           if (j == 0) mbar_wait(acc_empty, (ti & 1) ^ 1);    // previous outer tile's accumulators were read out
           tc_fence_after();
-          const uint32_t aX = smem_u32(sX + s * B2_STR_BYTES), aY = smem_u32(sY + s * B2_STR_BYTES);
-          const uint32_t aP = aT1 + g * B2_T_BYTES, aD = aT2 + g * B2_T_BYTES;
+          const uint64_t dXm = umma_desc_advance(dXm0, s * B2_STR_BYTES), dYm = umma_desc_advance(dYm0, s * B2_STR_BYTES);
+          const uint64_t dP = umma_desc_advance(dT1_0, g * B2_T_BYTES), dD = umma_desc_advance(dT2_0, g * B2_T_BYTES);
 #pragma unroll
           for (int kk = 0; kk < B2_IN / 16; ++kk) {
             const uint32_t acc = (j | kk) != 0 ? 1u : 0u;
@@ -273,27 +278,24 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
               // S (P^T) / dP (dS^T) block
               const uint32_t tP = tmem_base + g * 128 + (kk >> 1) * 32 + (kk & 1) * 8, tD = tP + 64;
               if (MODE == 0) {
-                umma_f16_ts(tmem_acc0, tP, umma_smem_desc_sw128(aY + kk * 2048, B2_STR_BYTES / 2, 1024), idesc_acc, acc);
-                umma_f16_ts(tmem_acc1, tD, umma_smem_desc_sw128(aX + kk * 2048, B2_STR_BYTES / 2, 1024), idesc_acc, acc);
+                umma_f16_ts_elect(tmem_acc0, tP, umma_desc_advance(dYm, kk * 2048), idesc_acc, acc);   // dV += P^T.dO
+                umma_f16_ts_elect(tmem_acc1, tD, umma_desc_advance(dXm, kk * 2048), idesc_acc, acc);   // dK += dS^T.Q
               } else {
-                umma_f16_ts(tmem_acc0, tD, umma_smem_desc_sw128(aX + kk * 2048, B2_STR_BYTES / 2, 1024), idesc_acc, acc);
+                umma_f16_ts_elect(tmem_acc0, tD, umma_desc_advance(dXm, kk * 2048), idesc_acc, acc);   // dQ += dS.K
               }
             } else if (MODE == 0) {
-              umma_f16_ss(tmem_acc0, umma_smem_desc_sw128(aP + kk * 32, 16, 1024),
-                          umma_smem_desc_sw128(aY + kk * 2048, B2_STR_BYTES / 2, 1024), idesc_acc, acc);   // dV += P^T.dO
-              umma_f16_ss(tmem_acc1, umma_smem_desc_sw128(aD + kk * 32, 16, 1024),
-                          umma_smem_desc_sw128(aX + kk * 2048, B2_STR_BYTES / 2, 1024), idesc_acc, acc);   // dK += dS^T.Q
+              umma_f16_ss_elect(tmem_acc0, umma_desc_advance(dP, kk * 32), umma_desc_advance(dYm, kk * 2048), idesc_acc, acc);
+              umma_f16_ss_elect(tmem_acc1, umma_desc_advance(dD, kk * 32), umma_desc_advance(dXm, kk * 2048), idesc_acc, acc);
             } else {
-              umma_f16_ss(tmem_acc0, umma_smem_desc_sw128(aD + kk * 32, 16, 1024),
-                          umma_smem_desc_sw128(aX + kk * 2048, B2_STR_BYTES / 2, 1024), idesc_acc, acc);   // dQ += dS.K
+              umma_f16_ss_elect(tmem_acc0, umma_desc_advance(dD, kk * 32), umma_desc_advance(dXm, kk * 2048), idesc_acc, acc);
             }
           }
-          umma_commit(&acc_done[g]);
-          umma_commit(&in_empty[s]);
-          if (j == n - 1) umma_commit(acc_full);
+          umma_commit_elect(&acc_done[g]);
+          umma_commit_elect(&in_empty[s]);
+          if (j == n - 1) umma_commit_elect(acc_full);
           // keep the score products two tiles ahead of the accumulation products
           if (j + 2 < n) issue_sd(c + 2);
-          else if (j + 2 == n) umma_commit(fix_empty);       // every score product of this outer tile has been issued
+          else if (j + 2 == n) umma_commit_elect(fix_empty);       // every score product of this outer tile has been issued
         }
         it += n;
       }

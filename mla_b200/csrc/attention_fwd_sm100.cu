@@ -78,7 +78,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   uint8_t* s_mask_tile = smem + FA_TILES_BYTES + 256;
   int& s_any_masked = *reinterpret_cast<int*>(smem + FA_TILES_BYTES + 256 + 64);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = int(warp_idx_uniform()), lane = threadIdx.x & 31;     // warp-uniform role index (see ptx.cuh)
   const int S = p.S;
   const int n_qt = (S + FA_BM - 1) / FA_BM;
   const int half_id = blockIdx.x & 1;                   // which of the two CTAs of this (batch, head)
@@ -147,27 +147,30 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // All 32 lanes run this loop (converged, warp-uniform values; each tcgen05.mma / commit elects its issuing lane):
+    // the per-instruction issue cost drops from ~130 cycles (divergent `lane == 0` region) to a few uniform-datapath
+    // instructions, which matters because a 128x64x16 product only occupies the tensor core for 32 cycles.
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(FA_BM, FA_BN, 0, 0);    // 128 x 64  (K = d)
       constexpr uint32_t idesc_pv = umma_idesc_bf16(FA_BM, FA_D, 0, 1);    // 128 x 128 (K = kv), V is MN-major
-      const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
+      const uint64_t dQ = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024), dP = umma_smem_desc_sw128(smem_u32(sP), 16, 1024);
+      const uint64_t dK0 = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t dV0 = umma_smem_desc_sw128(smem_u32(sV), FA_KV_BYTES / 2, 1024);
       auto issue_s = [&](int cur) {
         const int s = cur & 1;
         const uint32_t ph = (cur >> 1) & 1;
         mbar_wait(&k_full[s], ph);
         mbar_wait(&s_empty[s], ph ^ 1);
         tc_fence_after();
-        const uint32_t aK = smem_u32(sK + s * FA_KV_BYTES);
+        const uint64_t dK = umma_desc_advance(dK0, s * FA_KV_BYTES);
 #pragma unroll
         for (int kk = 0; kk < FA_D / 16; ++kk) {
           // Q: [128 rows x 128 B] chunks 16 KB apart; K: [64 rows x 128 B] chunks 8 KB apart; +32 B per 16-wide k step
-          umma_f16_ss(tmem_base + s * FA_BN,
-                      umma_smem_desc_sw128(aQ + (kk >> 2) * (FA_Q_BYTES / 2) + (kk & 3) * 32, 16, 1024),
-                      umma_smem_desc_sw128(aK + (kk >> 2) * (FA_KV_BYTES / 2) + (kk & 3) * 32, 16, 1024), idesc_s,
-                      kk != 0 ? 1u : 0u);
+          umma_f16_ss_elect(tmem_base + s * FA_BN, umma_desc_advance(dQ, (kk >> 2) * (FA_Q_BYTES / 2) + (kk & 3) * 32),
+                            umma_desc_advance(dK, (kk >> 2) * (FA_KV_BYTES / 2) + (kk & 3) * 32), idesc_s, kk != 0 ? 1u : 0u);
         }
-        umma_commit(&s_full[s]);
-        umma_commit(&k_empty[s]);
+        umma_commit_elect(&s_full[s]);
+        umma_commit_elect(&k_empty[s]);
       };
       int it = 0;
       for (int ti = 0;; ++ti) {
@@ -179,22 +182,22 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         for (int j = 0; j < n_kv; ++j) {
           const int cur = it + j;
           if (j + 1 < n_kv) issue_s(cur + 1);
-          else umma_commit(q_empty);               // every QK^T of this q tile has been issued
+          else umma_commit_elect(q_empty);               // every QK^T of this q tile has been issued
           const int s = cur & 1;
           mbar_wait(p_full, cur & 1);
           if (j == 0) mbar_wait(o_empty, (ti & 1) ^ 1);   // previous q tile's O has been read out
           mbar_wait(&v_full[s], (cur >> 1) & 1);
           tc_fence_after();
-          const uint32_t aV = smem_u32(sV + s * FA_KV_BYTES);
+          const uint64_t dV = umma_desc_advance(dV0, s * FA_KV_BYTES);
 #pragma unroll
           for (int kk = 0; kk < FA_BN / 16; ++kk) {
             // P: K-major [128 x 64 kv]; V: MN-major, d chunks 8 KB apart (LBO), 16 kv rows per step = 2048 B
-            umma_f16_ss(tmem_o, umma_smem_desc_sw128(aP + kk * 32, 16, 1024),
-                        umma_smem_desc_sw128(aV + kk * 2048, FA_KV_BYTES / 2, 1024), idesc_pv, (j | kk) != 0 ? 1u : 0u);
+            umma_f16_ss_elect(tmem_o, umma_desc_advance(dP, kk * 32), umma_desc_advance(dV, kk * 2048), idesc_pv,
+                              (j | kk) != 0 ? 1u : 0u);
           }
-          umma_commit(pv_done);
-          umma_commit(&v_empty[s]);
-          if (j == n_kv - 1) umma_commit(o_full);
+          umma_commit_elect(pv_done);
+          umma_commit_elect(&v_empty[s]);
+          if (j == n_kv - 1) umma_commit_elect(o_full);
         }
         it += n_kv;
       }

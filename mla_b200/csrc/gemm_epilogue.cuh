@@ -139,9 +139,72 @@ __device__ __forceinline__ void gemm_store_tile_swiglu(const GemmEpilogue& ep, u
   }
 }
 
+// SwiGLU-backward epilogue (the input-gradient GEMM of the down projection; N = f, a multiple of 32): per 32-column chunk
+// the thread needs 64 bytes of gate and 64 bytes of up from global memory.  Those loads are issued ONE CHUNK AHEAD (for
+// chunk c + 1 before the accumulator of chunk c is read and worked on), otherwise eight dependent DRAM round trips per
+// tile make the epilogue slower than the tile's MMAs (measured: the un-prefetched version cost 10 ms per step).
+// Same rounding points as d_act -> bf16 -> swiglu_bwd_kernel.
+__device__ __forceinline__ void gemm_store_tile_swiglu_bwd(const GemmEpilogue& ep, uint32_t taddr, int64_t row, int n0, int M,
+                                                           int N) {
+  const bool row_ok = row < M;
+  const int64_t rr = row_ok ? row : 0;                 // rows beyond M read row 0 (never stored)
+  const __nv_bfloat16* gbase = ep.sb_gu + rr * ep.ld_sb_gu;
+  uint4 gq[4], uq[4], gn[4], un[4];
+  auto fetch = [&](int col0, uint4 (&g)[4], uint4 (&u)[4]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      g[q] = *reinterpret_cast<const uint4*>(gbase + col0 + q * 8);
+      u[q] = *reinterpret_cast<const uint4*>(gbase + N + col0 + q * 8);
+    }
+  };
+  if (n0 < N) fetch(n0, gq, uq);
+#pragma unroll 1
+  for (int c = 0; c < GEMM_BN / 32; ++c) {
+    const int col0 = n0 + c * 32;
+    if (col0 >= N) break;  // warp-uniform
+    const bool more = (c + 1 < GEMM_BN / 32) && (col0 + 32 < N);
+    if (more) fetch(col0 + 32, gn, un);
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr + c * 32, r);
+    tmem_ld_wait();
+    if (row_ok) {
+      __nv_bfloat16* dgrow = ep.sb_dgu + row * ep.ld_sb_dgu + col0;
+      __nv_bfloat16* arow = ep.sb_act ? ep.sb_act + row * ep.ld_sb_act + col0 : nullptr;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gq[q]);
+        const __nv_bfloat162* uh = reinterpret_cast<const __nv_bfloat162*>(&uq[q]);
+        float dg[8], du[8], ac[8];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 gf = __bfloat1622float2(gh[t]), uf = __bfloat1622float2(uh[t]);
+          swiglu_bwd_elem(gf.x, uf.x, bf16_round(__uint_as_float(r[q * 8 + 2 * t]) * ep.alpha), dg[2 * t], du[2 * t], ac[2 * t]);
+          swiglu_bwd_elem(gf.y, uf.y, bf16_round(__uint_as_float(r[q * 8 + 2 * t + 1]) * ep.alpha), dg[2 * t + 1],
+                          du[2 * t + 1], ac[2 * t + 1]);
+        }
+        *reinterpret_cast<uint4*>(dgrow + q * 8) = make_uint4(pack_bf16x2(dg[0], dg[1]), pack_bf16x2(dg[2], dg[3]),
+                                                             pack_bf16x2(dg[4], dg[5]), pack_bf16x2(dg[6], dg[7]));
+        *reinterpret_cast<uint4*>(dgrow + N + q * 8) = make_uint4(pack_bf16x2(du[0], du[1]), pack_bf16x2(du[2], du[3]),
+                                                                 pack_bf16x2(du[4], du[5]), pack_bf16x2(du[6], du[7]));
+        if (arow)
+          *reinterpret_cast<uint4*>(arow + q * 8) = make_uint4(pack_bf16x2(ac[0], ac[1]), pack_bf16x2(ac[2], ac[3]),
+                                                              pack_bf16x2(ac[4], ac[5]), pack_bf16x2(ac[6], ac[7]));
+      }
+    }
+    if (more) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { gq[q] = gn[q]; uq[q] = un[q]; }
+    }
+  }
+}
+
 // taddr: TMEM address of this thread's warp-quarter and accumulator buffer; row: global output row of this thread.
 __device__ __forceinline__ void gemm_store_tile(const GemmEpilogue& ep, uint32_t taddr, int64_t row, int n0, int M, int N) {
   constexpr int BN = GEMM_BN;
+  if (ep.sb_gu != nullptr) {    // kernel-uniform
+    gemm_store_tile_swiglu_bwd(ep, taddr, row, n0, M, N);
+    return;
+  }
   if (n0 < ep.rope_cols) {      // warp-uniform (whole tile inside the rotated q|k column block)
     gemm_store_tile_rope(ep, taddr, row, n0, M);
     return;
@@ -159,34 +222,6 @@ __device__ __forceinline__ void gemm_store_tile(const GemmEpilogue& ep, uint32_t
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
-    if (ep.sb_gu != nullptr) {
-      // SwiGLU backward (N = f, a multiple of 32): same rounding points as d_act -> bf16 -> swiglu_bwd_kernel
-      const __nv_bfloat16* grow = ep.sb_gu + row * ep.ld_sb_gu + col0;
-      __nv_bfloat16* dgrow = ep.sb_dgu + row * ep.ld_sb_dgu + col0;
-      __nv_bfloat16* arow = ep.sb_act ? ep.sb_act + row * ep.ld_sb_act + col0 : nullptr;
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        const uint4 gq = *reinterpret_cast<const uint4*>(grow + j);
-        const uint4 uq = *reinterpret_cast<const uint4*>(grow + N + j);
-        const __nv_bfloat162* gh = reinterpret_cast<const __nv_bfloat162*>(&gq);
-        const __nv_bfloat162* uh = reinterpret_cast<const __nv_bfloat162*>(&uq);
-        float dg[8], du[8], ac[8];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float2 gf = __bfloat1622float2(gh[t]), uf = __bfloat1622float2(uh[t]);
-          swiglu_bwd_elem(gf.x, uf.x, bf16_round(v[j + 2 * t]), dg[2 * t], du[2 * t], ac[2 * t]);
-          swiglu_bwd_elem(gf.y, uf.y, bf16_round(v[j + 2 * t + 1]), dg[2 * t + 1], du[2 * t + 1], ac[2 * t + 1]);
-        }
-        *reinterpret_cast<uint4*>(dgrow + j) = make_uint4(pack_bf16x2(dg[0], dg[1]), pack_bf16x2(dg[2], dg[3]),
-                                                         pack_bf16x2(dg[4], dg[5]), pack_bf16x2(dg[6], dg[7]));
-        *reinterpret_cast<uint4*>(dgrow + N + j) = make_uint4(pack_bf16x2(du[0], du[1]), pack_bf16x2(du[2], du[3]),
-                                                             pack_bf16x2(du[4], du[5]), pack_bf16x2(du[6], du[7]));
-        if (arow)
-          *reinterpret_cast<uint4*>(arow + j) = make_uint4(pack_bf16x2(ac[0], ac[1]), pack_bf16x2(ac[2], ac[3]),
-                                                          pack_bf16x2(ac[4], ac[5]), pack_bf16x2(ac[6], ac[7]));
-      }
-      continue;
-    }
     if (ep.c_dtype == 1) {
       // fp32 output (weight gradients): optional accumulate, no activation path.
       float* crow = reinterpret_cast<float*>(ep.c) + row * ep.ldc + col0;

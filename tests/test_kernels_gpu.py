@@ -234,3 +234,37 @@ def test_lm_loss_path(cuda_lib):
     assert rel_err(out.logits, ref_logits) < 1e-2 and out.logits.dtype == torch.float32
     out.loss.backward()
     assert m.lm_head.weight.grad is not None and float(m.lm_head.weight.grad.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("M,valid_frac", [(8192, 1.0), (8192, 0.83), (1000, 0.5)])
+def test_infonce_kernels_full_size(cuda_lib, M, valid_frac):
+    """img<->pc InfoNCE at the size the training step reaches (M = B_eff * 256 = 8192 rows): similarity GEMM
+    + masked row/column softmax statistics + both gradients, against torch fp32 autograd of the reference formula
+    (contrastive.py:203-215: compaction of the valid rows, logits / 0.07, mean of the two cross-entropies) evaluated in
+    the reference's arithmetic (bf16 logits) and in fp32 (truth)."""
+    import torch.nn.functional as F
+    from mla_b200.contrastive import _InfoNCEFn
+    torch.manual_seed(M)
+    D, T = 256, 0.07
+    a = F.normalize(torch.randn(M, D, device="cuda"), dim=-1)
+    b = F.normalize(a + 0.7 * F.normalize(torch.randn(M, D, device="cuda"), dim=-1), dim=-1)   # positives correlate
+    valid = torch.rand(M, device="cuda") < valid_frac
+    ab, bb = a.to(torch.bfloat16).requires_grad_(True), b.to(torch.bfloat16).requires_grad_(True)
+    loss = _InfoNCEFn.apply(ab, bb, valid.to(torch.uint8).contiguous(), T)
+    loss.backward()
+
+    def ref(dt):
+        x, y = ab.detach().float().requires_grad_(True), bb.detach().float().requires_grad_(True)
+        xv, yv = x[valid], y[valid]
+        logits = (torch.matmul(xv.to(dt), yv.to(dt).t()) / T).float()
+        lab = torch.arange(xv.shape[0], device="cuda")
+        l = (F.cross_entropy(logits, lab) + F.cross_entropy(logits.t(), lab)) / 2
+        l.backward()
+        return l.detach(), x.grad, y.grad
+    l32, da32, db32 = ref(torch.float32)
+    l16, da16, db16 = ref(torch.bfloat16)
+    assert abs(float(loss) - float(l32)) <= 1.5 * abs(float(l16) - float(l32)) + 2e-3 * abs(float(l32)), (float(loss), float(l32), float(l16))
+    for got, t32, t16 in ((ab.grad, da32, da16), (bb.grad, db32, db16)):
+        e, e_ref = rel_err(got, t32), rel_err(t16, t32)
+        assert e < 1.5 * e_ref + 1e-2, (e, e_ref)
+        assert float(got[~valid].abs().max() if (~valid).any() else 0.0) == 0.0      # masked rows get no gradient
