@@ -24,6 +24,7 @@
 // TMEM (512 cols): [S0|dP0|S1|dP1] 4 x 64, accumulators @256 (dV or dQ) and @384 (dK).
 // smem: fixed 2x32 KB | streamed 3 slots x (16+16) KB | 2 x (P^T 16 KB + dS^T 16 KB) | barriers | per-column lse/delta.
 #include <cstdlib>
+#include <type_traits>
 
 #include "mla_internal.cuh"
 #include "ptx.cuh"
@@ -356,6 +357,9 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
           if (c >= 2) mbar_wait(&acc_done[grp], ((c >> 1) - 1) & 1);
         }
         const float4* stat4 = reinterpret_cast<const float4*>(s_stat + slot * 128 + half * 32);   // MODE 0: lse2 | delta
+        // MASKED = false: every element of the tile is visible (no diagonal, no padding): no predicates, no branches
+        auto tile_math = [&](auto masked_tag) {
+        constexpr bool MASKED = decltype(masked_tag)::value;
         uint32_t pkp[8], pkd[8];
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
@@ -371,14 +375,18 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
             const int cc = g8 * 8 + e;
             const float l2 = MODE == 0 ? l2v[e] : row_lse2;
             const float dl = MODE == 0 ? dlv[e] : row_delta;
-            bool vis = true;
-            if (MODE == 0) {
-              vis = row_ok && (!edge || orow <= in0 + cc);
-            } else if (edge) {
-              const int col = in0 + cc;
-              vis = (col <= orow) && (col < S) && (!use_mask || gmask[col]);
+            float x = __fmaf_rn(__uint_as_float(vs[cc]), sl2, -l2);     // lse2 = +inf (rows that take no part) -> P = 0
+            if (MASKED) {
+              bool vis;
+              if (MODE == 0) {
+                vis = row_ok && (!edge || orow <= in0 + cc);
+              } else {
+                const int col = in0 + cc;
+                vis = (col <= orow) && (col < S) && (!use_mask || gmask[col]);
+              }
+              x = vis ? x : -INFINITY;                                   // select, not a branch: ex2(-inf) = 0
             }
-            const float pv = vis ? b2_ex2(__fmaf_rn(__uint_as_float(vs[cc]), sl2, -l2)) : 0.f;   // lse2 = +inf -> 0
+            const float pv = b2_ex2(x);
             pr[e] = pv;
             ds[e] = pv * (__uint_as_float(vp[cc]) - dl);
           }
@@ -402,6 +410,10 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
                                                                pack_bf16x2(ds[4], ds[5]), pack_bf16x2(ds[6], ds[7]));
           }
         }
+        };
+        const bool fast = MODE == 0 ? (!edge && __all_sync(0xffffffffu, row_ok)) : !edge;      // warp-uniform
+        if (fast) tile_math(std::false_type{});
+        else tile_math(std::true_type{});
         if (TS) b2_tmem_st_wait();
         else fence_proxy_async();
         tc_fence_before();

@@ -108,6 +108,30 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       : "memory");
 }
 
+// warp-uniform issue variants (see ptx.cuh: every lane of the converged MMA warp executes them, one elected lane issues)
+__device__ __forceinline__ void umma_f16_ss_pair_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                       uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "h"(uint16_t(3))
+      : "memory");
+}
+
 __device__ __forceinline__ void tile_coords2(int tile, int tiles_m, int tiles_n, int group_m, int& tm, int& tn) {
   int group_size = group_m * tiles_n;
   int g = tile / group_size;
@@ -120,7 +144,7 @@ __device__ __forceinline__ void tile_coords2(int tile, int tiles_m, int tiles_n,
 
 // SWIGLU = 1 (gate|up projection, K-major operands): tile tn = 128 gate columns + the matching 128 up columns — the
 // peer CTA's half of the B panel is fetched from the `up` rows — and the epilogue applies SwiGLU (gemm_epilogue.cuh).
-template <int A_MN, int B_MN, int SWIGLU = 0>
+template <int A_MN, int B_MN, int SWIGLU = 0, int UNI = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int M, int N,
                   int K, int group_m, int* sched, GemmEpilogue ep) {
@@ -136,7 +160,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   int* sched_ids = reinterpret_cast<int*>(tmem_base_slot + 1);
   const bool dynamic = sched != nullptr;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = int(warp_idx_uniform());      // warp-uniform role index: the MMA warp's code stays convergent
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
@@ -235,6 +259,54 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
+    if constexpr (UNI) {
+    // All 32 lanes of the warp run the loop (warp-uniform values, barrier polls warp-wide); tcgen05.mma / commit elect
+    // their issuing lane themselves, so the operands sit in uniform registers and the ~20-instruction ELECT / R2UR /
+    // BRA.U.ANY sequence a divergent `lane == 0` region costs per MMA (about as long as the 128-cycle MMA itself) is gone.
+    if (leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * G2_BM, G2_BN, A_MN, B_MN);
+      const uint64_t dA0 = A_MN == 0 ? umma_smem_desc_sw128(smem_u32(smem), 16, 1024)
+                                     : umma_smem_desc_sw128(smem_u32(smem), G2_BK * 128, 1024);
+      const uint64_t dB0 = B_MN == 0 ? umma_smem_desc_sw128(smem_u32(smem) + G2_A_BYTES, 16, 1024)
+                                     : umma_smem_desc_sw128(smem_u32(smem) + G2_A_BYTES, G2_BK * 128, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      int tile = cluster_id;
+      for (int seq = 0;; ++seq) {
+        if (dynamic) {
+          const int sl = seq & (G2_SCHED - 1);
+          mbar_wait(&sched_full[sl], (seq / G2_SCHED) & 1);
+          tile = __shfl_sync(0xffffffffu, sched_ids[sl], 0);      // same value in every lane; tells the compiler so
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sched_empty[sl]);
+          if (tile < 0) break;
+        } else {
+          if (seq > 0) tile += num_clusters;
+          if (tile >= num_tiles) break;
+        }
+        mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * G2_BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t dA = umma_desc_advance(dA0, stage * G2_STAGE_BYTES), dB = umma_desc_advance(dB0, stage * G2_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < G2_BK / 16; ++k) {
+            umma_f16_ss_pair_elect(tmem_d, umma_desc_advance(dA, A_MN == 0 ? k * 32 : k * 2048),
+                                   umma_desc_advance(dB, B_MN == 0 ? k * 32 : k * 2048), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair_elect(&empty_bar[stage]);      // frees this slot in both CTAs
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair_elect(&tmem_full_bar[acc]);      // accumulator complete -> both epilogues
+        if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    } else {
+    // first-generation issue path (one lane in a divergent region), kept for A/B measurements (MLA_GEMM_UNIFORM_ISSUE=0)
     if (leader && lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * G2_BM, G2_BN, A_MN, B_MN);
       int stage = 0;
@@ -275,6 +347,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         umma_commit_pair(&tmem_full_bar[acc]);      // accumulator complete -> both epilogues
         if (++acc == G2_ACC) { acc = 0; acc_phase ^= 1; }
       }
+    }
     }
   } else {
     // ===================== epilogue (4 warps, both CTAs) =====================
@@ -342,11 +415,11 @@ static int encode_operand_map2(CUtensorMap* map, const void* ptr, int mn_major, 
   return encode_tmap_2d_bf16(map, ptr, dims, strides, box);
 }
 
-template <int A_MN, int B_MN, int SWIGLU = 0>
+template <int A_MN, int B_MN, int SWIGLU = 0, int UNI = 1>
 static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, int M, int N, int K, const GemmEpilogue& ep,
                         int* sched, cudaStream_t stream) {
   static bool attr_set = false;
-  auto kern = gemm2_bf16_kernel<A_MN, B_MN, SWIGLU>;
+  auto kern = gemm2_bf16_kernel<A_MN, B_MN, SWIGLU, UNI>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES);
     if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "cudaFuncSetAttribute(gemm2 smem): %s", cudaGetErrorString(e));
@@ -372,6 +445,15 @@ int gemm2_dispatch(const mla_gemm_args* g, const GemmEpilogue& ep, cudaStream_t 
   if (int rc = encode_operand_map2(&mb, g->b, g->b_mn_major, g->n, g->k, g->ldb)) return rc;
   const int M = int(g->m), N = int(g->n), K = int(g->k);
   int* sched = static_cast<int*>(g->sched_ws);
+  // MLA_GEMM_UNIFORM_ISSUE=0: the first-generation MMA issue path (A/B switch; default: warp-uniform issue)
+  static const bool uni = [] { const char* e = getenv("MLA_GEMM_UNIFORM_ISSUE"); return e ? atoi(e) != 0 : true; }();
+  if (!uni) {
+    if (ep.swiglu_f > 0) return launch_gemm2<0, 0, 1, 0>(ma, mb, M, N, K, ep, sched, stream);
+    if (!g->a_mn_major && !g->b_mn_major) return launch_gemm2<0, 0, 0, 0>(ma, mb, M, N, K, ep, sched, stream);
+    if (!g->a_mn_major && g->b_mn_major) return launch_gemm2<0, 1, 0, 0>(ma, mb, M, N, K, ep, sched, stream);
+    if (g->a_mn_major && !g->b_mn_major) return launch_gemm2<1, 0, 0, 0>(ma, mb, M, N, K, ep, sched, stream);
+    return launch_gemm2<1, 1, 0, 0>(ma, mb, M, N, K, ep, sched, stream);
+  }
   if (ep.swiglu_f > 0) return launch_gemm2<0, 0, 1>(ma, mb, M, N, K, ep, sched, stream);   // validated by the caller
   if (!g->a_mn_major && !g->b_mn_major) return launch_gemm2<0, 0>(ma, mb, M, N, K, ep, sched, stream);
   if (!g->a_mn_major && g->b_mn_major) return launch_gemm2<0, 1>(ma, mb, M, N, K, ep, sched, stream);
