@@ -442,6 +442,29 @@ def run_ours(args):
         except Exception as ex:
             sys.stderr.write(f"cfg3 measurement failed: {ex}\n")
             also = {"cfg3": {"error": str(ex)[:200]}}
+    busbw = None
+    if world > 1:
+        # measured NCCL all-reduce bus bandwidth at the message size the trainer uses (one decoder layer's flat fp32
+        # gradient arena, 810 MB), alone on the wire: the reference point for the exchange's share of the step
+        try:
+            buf = torch.zeros(3 * H * H + H * H + 2 * F * H + H * F + 2 * H, dtype=torch.float32, device="cuda")
+            for _ in range(2):
+                dist.all_reduce(buf)
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                dist.all_reduce(buf)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / 5], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            busbw = {"message_bytes": buf.numel() * 4, "ms": round(float(t.item()), 3),
+                     "busbw_gbs": round(2.0 * (world - 1) / world * buf.numel() * 4 / float(t.item()) / 1e6, 1)}
+            del buf
+        except Exception as ex:
+            busbw = {"error": str(ex)[:120]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -485,7 +508,8 @@ def run_ours(args):
         "reference_gpu": reference_gpu_record(),
     }
     if m["exchange"]:
-        out["gradient_exchange"] = m["exchange"]
+        out["gradient_exchange"] = dict(m["exchange"], allreduce_alone=busbw,
+                                        nccl_env={k: v for k, v in os.environ.items() if k.startswith("NCCL_")})
     if also:
         out["also"] = also
     print(json.dumps(out), flush=True)

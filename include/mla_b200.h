@@ -101,6 +101,9 @@ int mla_gemm_bf16(const mla_gemm_args* args, void* stream);
  * tile per 2-CTA cluster) for problems of at least 1024 rows (default), 2 = CTA pairs always.  Env MLA_GEMM_2CTA sets
  * the initial mode.  Both kernels honour sched_ws (dynamic tile claiming). */
 int mla_gemm_set_mode(int32_t mode);
+/* Tuning switch: M-tiles per rasterisation group of the CTA-pair kernel (0 = built-in heuristic from the K-panel size;
+ * env MLA_GEMM2_GROUP_M sets the initial value).  Results do not depend on it. */
+int mla_gemm_set_group_m(int32_t group_m);
 
 /* ---- RMSNorm ----------------------------------------------------------------------------------------------
  * y = w * bf16(x * rsqrt(mean(x^2) + eps))   (modeling_llama.py:85-90, LlamaRMSNorm; x,y,w bf16, stats f32).

@@ -65,26 +65,25 @@ __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, int64_t ld_o,
                      const float* __restrict__ lse, float* __restrict__ lse2, float* __restrict__ delta, int B, int S,
                      int H, int S_pad) {
-  const int64_t hw = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 4;     // half-warp index
+  // 32-bit index arithmetic throughout (B*H*S_pad < 2^31 is checked by the launcher): 64-bit div/mod are emulated in
+  // ~100 instructions each and made the first version of this kernel instruction-bound
+  const uint32_t hw = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;     // half-warp index
   const int l16 = threadIdx.x & 15;
-  const int64_t total = int64_t(B) * H * S_pad;
+  const uint32_t total = uint32_t(B) * H * S_pad;
   uint4 a[PREP_ROWS], c[PREP_ROWS];
-  int64_t w[PREP_ROWS];
   bool live[PREP_ROWS];
+  const uint32_t w0 = hw * PREP_ROWS;
+  // PREP_ROWS divides S_pad (a multiple of 128): the rows of one half-warp share (b, h)
+  const uint32_t bh = w0 / uint32_t(S_pad), s0 = w0 - bh * uint32_t(S_pad);
+  const uint32_t bb = bh / uint32_t(H), hh = bh - bb * uint32_t(H);
+  const int64_t base = (int64_t(bb) * S + s0) * ld_o + int64_t(hh) * BW_D + l16 * 8;
 #pragma unroll
   for (int u = 0; u < PREP_ROWS; ++u) {
-    w[u] = hw * PREP_ROWS + u;
     a[u] = c[u] = make_uint4(0, 0, 0, 0);
-    live[u] = false;
-    if (w[u] < total) {
-      const int s = int(w[u] % S_pad);
-      const int64_t bh = w[u] / S_pad;
-      if (s < S) {
-        const int64_t off = (int64_t(bh / H) * S + s) * ld_o + int(bh % H) * BW_D + l16 * 8;
-        a[u] = *reinterpret_cast<const uint4*>(o + off);
-        c[u] = *reinterpret_cast<const uint4*>(d_o + off);
-        live[u] = true;
-      }
+    live[u] = w0 + u < total && int(s0) + u < S;
+    if (live[u]) {
+      a[u] = *reinterpret_cast<const uint4*>(o + base + u * ld_o);
+      c[u] = *reinterpret_cast<const uint4*>(d_o + base + u * ld_o);
     }
   }
 #pragma unroll
@@ -99,14 +98,9 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* _
     }
 #pragma unroll
     for (int off = 8; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (l16 == 0 && w[u] < total) {
-      float l2 = INFINITY;
-      if (live[u]) {
-        const int s = int(w[u] % S_pad);
-        l2 = lse[(w[u] / S_pad) * S + s] * BW_LOG2E;
-      }
-      lse2[w[u]] = l2;
-      delta[w[u]] = acc;
+    if (l16 == 0 && w0 + u < total) {
+      lse2[w0 + u] = live[u] ? lse[bh * uint32_t(S) + s0 + u] * BW_LOG2E : INFINITY;
+      delta[w0 + u] = acc;
     }
   }
 }
@@ -115,6 +109,7 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* _
 int attn_bwd_prep_launch(const void* o, const void* d_o, int64_t ld_o, const void* lse, float* lse2, float* delta, int B,
                          int S, int H, int S_pad, cudaStream_t s) {
   const int64_t rows = int64_t(B) * H * S_pad;
+  if (rows >= (int64_t(1) << 31)) return set_error(MLA_ERR_ARG, "attn_bwd_prep: batch * heads * seq exceeds 2^31 rows");
   const int64_t threads = (rows + PREP_ROWS - 1) / PREP_ROWS * 16;
   attn_bwd_prep_kernel<<<unsigned((threads + 255) / 256), 256, 0, s>>>((const __nv_bfloat16*)o, (const __nv_bfloat16*)d_o,
                                                                         ld_o, (const float*)lse, lse2, delta, B, S, H, S_pad);

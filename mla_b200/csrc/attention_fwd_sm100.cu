@@ -249,14 +249,22 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       if (!edge) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
-      } else {
+      } else if (!use_mask) {
+        // causal / sequence-end tile without padding: column kv0 + i is visible iff i <= lim — one compare + select per
+        // element, no shared-memory mask, no branches
+        const int lim = min(row, S - 1) - kv0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const int c0 = kv0 + i, c1 = kv0 + 32 + i;
-          const bool vis0 = (c0 <= row) && (c0 < S) && (!use_mask || s_mask_tile[i]);
-          const bool vis1 = (c1 <= row) && (c1 < S) && (!use_mask || s_mask_tile[32 + i]);
-          if (!vis0) v0[i] = 0xff800000u;   // -inf
-          if (!vis1) v1[i] = 0xff800000u;
+          v0[i] = (i <= lim) ? v0[i] : 0xff800000u;   // -inf
+          v1[i] = (i + 32 <= lim) ? v1[i] : 0xff800000u;
+          mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+        }
+      } else {
+        const int lim = min(row, S - 1) - kv0;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v0[i] = ((i <= lim) && s_mask_tile[i]) ? v0[i] : 0xff800000u;
+          v1[i] = ((i + 32 <= lim) && s_mask_tile[32 + i]) ? v1[i] : 0xff800000u;
           mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
         }
       }

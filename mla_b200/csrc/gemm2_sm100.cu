@@ -401,6 +401,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
 }
 
+static int g_group_m_override = [] { const char* e = getenv("MLA_GEMM2_GROUP_M"); return e ? atoi(e) : 0; }();
+void gemm2_set_group_m(int g) { g_group_m_override = g; }
+
 static int encode_operand_map2(CUtensorMap* map, const void* ptr, int mn_major, int64_t rows_mn, int64_t k, int64_t ld) {
   uint64_t dims[2];
   uint64_t strides[1] = {uint64_t(ld) * 2};
@@ -430,6 +433,7 @@ static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, int M, int
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   int group_m = int((48ll << 20) / (int64_t(2 * G2_BM) * K * 2));
   group_m = group_m < 2 ? 2 : (group_m > 32 ? 32 : group_m);
+  if (g_group_m_override > 0) group_m = g_group_m_override;      // tuning switch (tools/bench_gemm_raster.py)
   kern<<<2 * clusters, G2_THREADS, G2_SMEM_BYTES, stream>>>(ma, mb, M, N, K, group_m, tiles > clusters ? sched : nullptr,
                                                             ep);
   cudaError_t e = cudaGetLastError();

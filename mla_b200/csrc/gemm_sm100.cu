@@ -290,6 +290,17 @@ static int g_gemm_mode = [] { const char* e = getenv("MLA_GEMM_2CTA"); return e 
 
 using namespace mla;
 
+namespace mla {
+void gemm2_set_group_m(int g);   // gemm2_sm100.cu
+}
+
+/* Rasterisation override of the CTA-pair kernel (M-tiles per group; 0 = the built-in heuristic): a tuning switch. */
+extern "C" int mla_gemm_set_group_m(int32_t group_m) {
+  if (group_m < 0 || group_m > 1024) return set_error(MLA_ERR_ARG, "gemm_set_group_m: out of range");
+  gemm2_set_group_m(group_m);
+  return MLA_OK;
+}
+
 extern "C" int mla_gemm_set_mode(int32_t mode) {
   if (mode < 0 || mode > 2) return set_error(MLA_ERR_ARG, "gemm_set_mode: mode must be 0, 1 or 2");
   g_gemm_mode = mode;
