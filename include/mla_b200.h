@@ -89,6 +89,9 @@ typedef struct mla_gemm_args {
    * swiglu_bwd_act is not NULL, the re-materialised act = bf16(bf16(silu(gate)) * up) (bf16 [M, f], the operand of the
    * down projection's weight gradient).  c is not written.  Bit-identical to the GEMM followed by mla_swiglu_bwd_act.
    * NULL swiglu_bwd_gu = off. */
+  /* Optional row -> rotary position table for the fused RoPE (int32 [M]; NULL: position = row % rope_seq): the
+   * shared-prefix layout repeats positions across the suffix groups of a sequence. */
+  const void* rope_pos;
   const void* swiglu_bwd_gu;
   int64_t ld_swiglu_bwd_gu;
   void* swiglu_bwd_dgu;
@@ -159,6 +162,12 @@ int mla_attn_bwd(const mla_attn_args* args, void* stream);
  * blocks, pitch ld_qkv); same outputs and semantics as mla_attn_fwd. */
 int mla_attn_fwd_sm100(const void* qkv, int64_t ld_qkv, void* o, int64_t ld_o, void* lse, const void* mask,
                        int32_t batch, int32_t seq, int32_t heads, float scale, void* stream);
+/* Shared-prefix attention (models/mla/model_mla.py:147-176 repeats every sample R times although only the
+ * [t | x | EOS] rows differ): sequence b = a causal prefix of prefix_len[b] rows followed by groups of `group` rows; a row
+ * of a group sees the whole prefix and, causally, its own group.  prefix_len: int32 [batch] on the device. */
+int mla_attn_fwd_sm100_grouped(const void* qkv, int64_t ld_qkv, void* o, int64_t ld_o, void* lse, const void* mask,
+                               const void* prefix_len, int32_t group, int32_t batch, int32_t seq, int32_t heads,
+                               float scale, void* stream);
 /* tcgen05/TMEM/TMA backward for head_dim 128 (dK/dV kernel + dQ kernel): dqkv has the layout of qkv (dq | dk | dv);
  * lse is the forward's [batch, heads, seq] output; workspace: mla_attn_bwd_sm100_workspace() bytes, 16-byte aligned. */
 size_t mla_attn_bwd_sm100_workspace(int32_t batch, int32_t seq, int32_t heads);
@@ -173,6 +182,12 @@ int mla_attn_bwd_sm100(const void* qkv, int64_t ld_qkv, const void* o, const voi
 int mla_attn_bwd2_sm100(const void* qkv, int64_t ld_qkv, const void* o, const void* d_o, int64_t ld_o, const void* lse,
                         const void* mask, void* dqkv, int64_t ld_dqkv, void* workspace, const void* rope_cos,
                         const void* rope_sin, int32_t batch, int32_t seq, int32_t heads, float scale, void* stream);
+/* Backward of mla_attn_fwd_sm100_grouped; rope_pos int32 [batch*seq] (or NULL) = rotary position of every row for the
+ * fused RoPE transpose. */
+int mla_attn_bwd2_sm100_grouped(const void* qkv, int64_t ld_qkv, const void* o, const void* d_o, int64_t ld_o,
+                                const void* lse, const void* mask, void* dqkv, int64_t ld_dqkv, void* workspace,
+                                const void* rope_cos, const void* rope_sin, const void* rope_pos, const void* prefix_len,
+                                int32_t group, int32_t batch, int32_t seq, int32_t heads, float scale, void* stream);
 /* How mla_attn_bwd2_sm100 hands P / dS to its accumulation MMAs: 1 (default; env MLA_ATTN_BWD_TS) = packed bf16 in
  * tensor memory, read as the A operand straight from TMEM (no shared-memory staging: the kernel is bound by
  * shared-memory operand bandwidth); 0 = staged in 128B-swizzled shared memory.  Same results bit for bit. */
@@ -242,6 +257,16 @@ int mla_splice_index(const void* input_ids, const void* attn_mask, const void* l
                      int32_t n_fused, int32_t n_ins, int32_t n_x, int64_t eos_id, int32_t text_base,
                      int32_t fused_base, int32_t ins_base, void* src_idx, void* mask_out, void* labels_out,
                      void* lti_out, void* head_rows, void* err_flag, void* stream);
+/* Shared-prefix splice (models/mla/model_mla.py:147-176 repeats each sample `repeats` times although only
+ * the [t | x] rows differ): sample b -> one packed sequence [prefix (prefix_len[b] rows) | repeats x (t | x.. | EOS)] of
+ * S' = n_fused + lt + repeats * (n_x + 2) rows (filler rows masked).  Row sources are offsets into one row table
+ * (text | fused | proprio [batch] | t [batch*repeats] | x [batch*repeats, n_x]); copy e = r * batch + b as `.repeat(R, ..)`
+ * orders them.  Outputs: src_idx, mask, rope_pos [batch, S'], prefix_len [batch], lti [batch*repeats], head_rows
+ * [batch*repeats, n_x] (flat packed rows of the noisy-action tokens, prismatic.py:1121-1124). */
+int mla_splice_index_shared(const void* input_ids, const void* attn_mask, int32_t batch, int32_t lt, int32_t n_fused,
+                            int32_t n_x, int32_t repeats, int64_t eos_id, int32_t text_base, int32_t fused_base,
+                            int32_t pr_base, int32_t t_base, int32_t x_base, void* src_idx, void* mask_out, void* rope_pos,
+                            void* prefix_len, void* lti_out, void* head_rows, void* err_flag, void* stream);
 
 /* ---- InfoNCE alignment losses (models/mla/fuser/contrastive.py) and patch correspondence ---------------------------
  * l2norm: F.normalize(p=2, dim=-1) (:192-193), fp32 math, bf16 out, norms f32 [rows] saved for backward.

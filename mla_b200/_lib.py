@@ -27,6 +27,7 @@ class GemmArgs(C.Structure):
         ("pre_act", C.c_void_p), ("ldp", C.c_int64), ("sched_ws", C.c_void_p),
         ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p), ("rope_seq", C.c_int32), ("rope_cols", C.c_int32),
         ("swiglu_out", C.c_void_p), ("ld_swiglu", C.c_int64),
+        ("rope_pos", C.c_void_p),
         ("swiglu_bwd_gu", C.c_void_p), ("ld_swiglu_bwd_gu", C.c_int64),
         ("swiglu_bwd_dgu", C.c_void_p), ("ld_swiglu_bwd_dgu", C.c_int64),
         ("swiglu_bwd_act", C.c_void_p), ("ld_swiglu_bwd_act", C.c_int64),

@@ -156,7 +156,10 @@ class LlamaForCausalLM(nn.Module):
                 return_dict=None, cache_position=None, pc_token_indices=None, img_token_indices=None,
                 tac_token_indices=None, patch_correspondence_indices=None, correspondence_valid_mask=None,
                 positive_pc_indices_for_tac=None, linear_positive_img_indices_for_tac=None,
-                compute_token_contrastive_loss: bool = False, compute_tactile_contrastive_loss: bool = False):
+                compute_token_contrastive_loss: bool = False, compute_tactile_contrastive_loss: bool = False,
+                prefix_len=None, suffix_group: int = 0, rope_pos=None):
+        """prefix_len / suffix_group / rope_pos (ours, not in the reference signature): the shared-prefix layout of
+        MLA.forward(share_diffusion_prefix) — see llama.LayerShape."""
         if past_key_values is not None or use_cache:
             raise NotImplementedError("KV-cache decoding is inference-only (out of the hot-path scope)")
         if (input_ids is None) == (inputs_embeds is None):
@@ -173,7 +176,7 @@ class LlamaForCausalLM(nn.Module):
         if attention_mask is not None:
             mask = attention_mask if attention_mask.dtype in (torch.bool, torch.uint8) else attention_mask != 0
             mask = mask.contiguous()
-        hs2d = self.model.run_layers(x.contiguous(), B, S, mask)
+        hs2d = self.model.run_layers(x.contiguous(), B, S, mask, prefix_len, suffix_group, rope_pos)
         h = self.config.hidden_size
         hidden_states = tuple(t.view(B, S, h) for t in hs2d)
 

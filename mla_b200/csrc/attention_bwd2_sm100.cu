@@ -54,6 +54,11 @@ struct Bw2Params {
   int64_t ld_dqkv;
   const __nv_bfloat16* rope_cos;   // bf16 [S, 64] or null: apply the transposed rotation to dq / dk in the epilogue
   const __nv_bfloat16* rope_sin;
+  // shared-prefix layout (see attention_fwd_sm100.cu): keys >= prefix_len[b] are visible to the `group` rows of their own
+  // group only; rope_pos (int32 [B*S] or null) maps a row to its rotary position (suffix groups repeat positions)
+  const int32_t* prefix_len;
+  int group;
+  const int32_t* rope_pos;
 };
 
 __device__ __forceinline__ void b2_named_bar_sync(int id, int nthreads) {
@@ -319,6 +324,7 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
       b2_named_bar_sync(1, 2 * B2_GROUP_WARPS * 32);
     }
     const bool use_mask = gmask && s_any_masked;
+    const int P = p.group > 0 ? p.prefix_len[b] : 0x3fffffff;     // keys >= P are visible to their own group only
     uint8_t* myT1 = sT1 + grp * B2_T_BYTES;
     uint8_t* myT2 = sT2 + grp * B2_T_BYTES;
     int it = 0;
@@ -329,6 +335,8 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
       const int orow = t * B2_OUT + r;        // key row (MODE 0) / query row (MODE 1) in the sequence
       float row_lse2 = 0.f, row_delta = 0.f;
       bool row_ok = true;
+      // MODE 1: first key of this query row's own group (prefix rows: 0 = nothing hidden by the group rule)
+      const int glo = (MODE == 1 && p.group > 0 && orow >= P) ? P + ((orow - P) / p.group) * p.group : 0;
       if (MODE == 1) {
         row_lse2 = p.lse2[int64_t(bh) * p.S_pad + orow];      // S_pad covers every row of every outer tile
         row_delta = p.delta[int64_t(bh) * p.S_pad + orow];
@@ -341,8 +349,9 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
         const int in0 = (i0 + j) * B2_IN + half * 32;   // first streamed column (sequence position) of this thread
         const uint32_t tS = tmem_base + lane_off + grp * 128 + half * 32;
         bool edge;
-        if (MODE == 0) edge = ((i0 + j) * B2_IN < t * B2_OUT + B2_OUT);                       // diagonal: query < key possible
-        else edge = ((i0 + j) * B2_IN + B2_IN - 1 > t * B2_OUT) || ((i0 + j + 1) * B2_IN > S) || use_mask;
+        if (MODE == 0) edge = ((i0 + j) * B2_IN < t * B2_OUT + B2_OUT) || (t * B2_OUT + B2_OUT > P);   // diagonal / suffix keys
+        else edge = ((i0 + j) * B2_IN + B2_IN - 1 > t * B2_OUT) || ((i0 + j + 1) * B2_IN > S) || use_mask ||
+                    ((i0 + j + 1) * B2_IN > P);
         mbar_wait(&sd_full[grp], (c >> 1) & 1);
         tc_fence_after();
         uint32_t vs[32], vp[32];
@@ -379,10 +388,12 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
             if (MASKED) {
               bool vis;
               if (MODE == 0) {
-                vis = row_ok && (!edge || orow <= in0 + cc);
+                const int col = in0 + cc;                      // query position; orow = key position
+                vis = row_ok && (!edge || orow <= col);
+                if (p.group > 0 && orow >= P) vis = vis && orow >= P + ((col - P) / p.group) * p.group;   // same group
               } else {
-                const int col = in0 + cc;
-                vis = (col <= orow) && (col < S) && (!use_mask || gmask[col]);
+                const int col = in0 + cc;                      // key position; orow = query position
+                vis = (col <= orow) && (col < S) && (col < P || col >= glo) && (!use_mask || gmask[col]);
               }
               x = vis ? x : -INFINITY;                                   // select, not a branch: ex2(-inf) = 0
             }
@@ -430,8 +441,9 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
       const bool rope = p.rope_cos != nullptr;
       float cs[16], sn[16];
       if (rope && store) {
-        const uint4* cp = reinterpret_cast<const uint4*>(p.rope_cos + int64_t(orow) * 64 + e4 * 16);
-        const uint4* sp = reinterpret_cast<const uint4*>(p.rope_sin + int64_t(orow) * 64 + e4 * 16);
+        const int pos = p.rope_pos ? p.rope_pos[row_base + orow] : orow;
+        const uint4* cp = reinterpret_cast<const uint4*>(p.rope_cos + int64_t(pos) * 64 + e4 * 16);
+        const uint4* sp = reinterpret_cast<const uint4*>(p.rope_sin + int64_t(pos) * 64 + e4 * 16);
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const uint4 cq = cp[q], sq = sp[q];
@@ -520,11 +532,30 @@ extern "C" int mla_attn_bwd2_set_ts(int32_t on) {
   return MLA_OK;
 }
 
+extern "C" int mla_attn_bwd2_sm100_grouped(const void* qkv, int64_t ld_qkv, const void* o, const void* d_o, int64_t ld_o,
+                                           const void* lse, const void* mask, void* dqkv, int64_t ld_dqkv, void* workspace,
+                                           const void* rope_cos, const void* rope_sin, const void* rope_pos,
+                                           const void* prefix_len, int32_t group, int32_t batch, int32_t seq,
+                                           int32_t heads, float scale, void* stream);
+
 extern "C" int mla_attn_bwd2_sm100(const void* qkv, int64_t ld_qkv, const void* o, const void* d_o, int64_t ld_o,
                                    const void* lse, const void* mask, void* dqkv, int64_t ld_dqkv, void* workspace,
                                    const void* rope_cos, const void* rope_sin, int32_t batch, int32_t seq, int32_t heads,
                                    float scale, void* stream) {
+  return mla_attn_bwd2_sm100_grouped(qkv, ld_qkv, o, d_o, ld_o, lse, mask, dqkv, ld_dqkv, workspace, rope_cos, rope_sin,
+                                     nullptr, nullptr, 0, batch, seq, heads, scale, stream);
+}
+
+// Shared-prefix variant (see mla_attn_fwd_sm100_grouped): prefix_len int32 [batch], group = rows per suffix group;
+// rope_pos int32 [batch*seq] (or NULL: position = row index within the sequence) for the fused RoPE transpose.
+extern "C" int mla_attn_bwd2_sm100_grouped(const void* qkv, int64_t ld_qkv, const void* o, const void* d_o, int64_t ld_o,
+                                           const void* lse, const void* mask, void* dqkv, int64_t ld_dqkv, void* workspace,
+                                           const void* rope_cos, const void* rope_sin, const void* rope_pos,
+                                           const void* prefix_len, int32_t group, int32_t batch, int32_t seq,
+                                           int32_t heads, float scale, void* stream) {
   if (int rc = device_check()) return rc;
+  if (group < 0 || (group > 0 && prefix_len == nullptr))
+    return set_error(MLA_ERR_ARG, "attn_bwd2_sm100: a shared-prefix layout needs prefix_len and group > 0");
   if (batch <= 0 || seq <= 0 || heads <= 0) return set_error(MLA_ERR_ARG, "attn_bwd2_sm100: empty problem");
   if ((ld_qkv & 7) || (ld_o & 7) || (ld_dqkv & 7) || (reinterpret_cast<uintptr_t>(qkv) & 15) ||
       (reinterpret_cast<uintptr_t>(d_o) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15) ||
@@ -564,6 +595,8 @@ extern "C" int mla_attn_bwd2_sm100(const void* qkv, int64_t ld_qkv, const void* 
   p.lse2 = lse2; p.delta = delta; p.mask = (const uint8_t*)mask;
   p.dqkv = (__nv_bfloat16*)dqkv; p.ld_dqkv = ld_dqkv;
   p.rope_cos = (const __nv_bfloat16*)rope_cos; p.rope_sin = (const __nv_bfloat16*)rope_sin;
+  p.prefix_len = group > 0 ? (const int32_t*)prefix_len : nullptr; p.group = group;
+  p.rope_pos = (const int32_t*)rope_pos;
   const int grid = batch * heads * 2;
   if (g_bwd2_ts) attn_bwd2_sm100_kernel<0, 1><<<grid, B2_THREADS, B2_SMEM, s>>>(m_qkv_fix, m_qkv_str, m_do_fix, m_do_str, p);
   else attn_bwd2_sm100_kernel<0, 0><<<grid, B2_THREADS, B2_SMEM, s>>>(m_qkv_fix, m_qkv_str, m_do_fix, m_do_str, p);

@@ -3,6 +3,8 @@
 // that each own one query row (= one TMEM lane).  Same semantics and rounding points as attention.cu (the mma.sync
 // implementation that still serves head_dim 32/64 and the backward): key j visible to query i iff j <= i and
 // mask[b,j]; masked-out query rows give zeros; P is rounded to bf16 before the PV product, statistics are fp32.
+// With a shared-prefix layout (FaParams::group > 0) key j is additionally hidden from query i when j lies in the
+// suffix region (j >= P_b) but in another group than i: the R diffusion repeats of a sample then share one prefix.
 //
 // Two CTAs per (batch, head) split that sequence's 128-row q tiles between them in a zig-zag (heaviest first, so both
 // get the same number of causal kv tiles) and walk them persistently: the TMEM allocation, barrier set-up and pipeline
@@ -38,6 +40,10 @@ struct FaParams {
   int64_t ld_o;
   float* lse;           // [B, H, S]
   const uint8_t* mask;  // [B, S] or null
+  // shared-prefix layout: rows [0, P_b) of sequence b are a causal prefix, rows from P_b on are groups of
+  // `group` rows that see the whole prefix and (causally) their own group only.  group = 0: plain causal attention.
+  const int32_t* prefix_len;   // [B] P_b, or null
+  int group;
 };
 
 __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -217,19 +223,22 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       named_bar_sync(1, 128);
     }
     const bool use_mask = gmask && s_any_masked;
+    const int P = p.group > 0 ? p.prefix_len[b] : 0x3fffffff;     // keys >= P are visible to their own group only
     int it = 0;
     for (int ti = 0;; ++ti) {
     const int t = my_tile(ti);
     if (t < 0) break;
     const int n_kv = kv_tiles(t);
     const int row = t * FA_BM + r;  // position in the sequence
+    // first key of this row's own group (rows of the prefix: 0, nothing is hidden by the group rule)
+    const int glo = (p.group > 0 && row >= P) ? P + ((row - P) / p.group) * p.group : 0;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       const int cur = it + j;
       const int s = cur & 1;
       const uint32_t ts = tmem_base + lane_off + s * FA_BN;
       const int kv0 = j * FA_BN;
-      const bool edge = (j >= 2 * t) || (kv0 + FA_BN > S) || use_mask;  // tile needs element-wise masking
+      const bool edge = (j >= 2 * t) || (kv0 + FA_BN > S) || use_mask || (kv0 + FA_BN > P);  // element-wise masking
       if (use_mask) {
         named_bar_sync(1, 128);  // previous tile's readers are done with s_mask_tile
         if (st < FA_BN) s_mask_tile[st] = (kv0 + st < S) ? gmask[kv0 + st] : 0;
@@ -253,18 +262,30 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         // causal / sequence-end tile without padding: column kv0 + i is visible iff i <= lim — one compare + select per
         // element, no shared-memory mask, no branches
         const int lim = min(row, S - 1) - kv0;
+        if (kv0 + FA_BN <= P) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v0[i] = (i <= lim) ? v0[i] : 0xff800000u;   // -inf
-          v1[i] = (i + 32 <= lim) ? v1[i] : 0xff800000u;
-          mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+          for (int i = 0; i < 32; ++i) {
+            v0[i] = (i <= lim) ? v0[i] : 0xff800000u;   // -inf
+            v1[i] = (i + 32 <= lim) ? v1[i] : 0xff800000u;
+            mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+          }
+        } else {
+          // tile reaches into the suffix region: columns in [P, glo) belong to other groups
+          const int pi = P - kv0, gi = glo - kv0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            v0[i] = ((i <= lim) && (i < pi || i >= gi)) ? v0[i] : 0xff800000u;
+            v1[i] = ((i + 32 <= lim) && (i + 32 < pi || i + 32 >= gi)) ? v1[i] : 0xff800000u;
+            mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
+          }
         }
       } else {
         const int lim = min(row, S - 1) - kv0;
+        const int pi = P - kv0, gi = glo - kv0;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          v0[i] = ((i <= lim) && s_mask_tile[i]) ? v0[i] : 0xff800000u;
-          v1[i] = ((i + 32 <= lim) && s_mask_tile[32 + i]) ? v1[i] : 0xff800000u;
+          v0[i] = ((i <= lim) && (i < pi || i >= gi) && s_mask_tile[i]) ? v0[i] : 0xff800000u;
+          v1[i] = ((i + 32 <= lim) && (i + 32 < pi || i + 32 >= gi) && s_mask_tile[32 + i]) ? v1[i] : 0xff800000u;
           mx = fmaxf(mx, fmaxf(__uint_as_float(v0[i]), __uint_as_float(v1[i])));
         }
       }
@@ -362,9 +383,22 @@ attn_fwd_sm100_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 using namespace mla;
 
 // Forward for head_dim 128 on the tcgen05 path; q/k/v must be the three column blocks of one [B*S, 3*H*128] buffer.
+extern "C" int mla_attn_fwd_sm100_grouped(const void* qkv, int64_t ld_qkv, void* o, int64_t ld_o, void* lse,
+                                          const void* mask, const void* prefix_len, int32_t group, int32_t batch,
+                                          int32_t seq, int32_t heads, float scale, void* stream);
+
 extern "C" int mla_attn_fwd_sm100(const void* qkv, int64_t ld_qkv, void* o, int64_t ld_o, void* lse, const void* mask,
                                   int32_t batch, int32_t seq, int32_t heads, float scale, void* stream) {
+  return mla_attn_fwd_sm100_grouped(qkv, ld_qkv, o, ld_o, lse, mask, nullptr, 0, batch, seq, heads, scale, stream);
+}
+
+// Shared-prefix variant: prefix_len int32 [batch] (device), group > 0 = rows per suffix group; group = 0 / NULL = causal.
+extern "C" int mla_attn_fwd_sm100_grouped(const void* qkv, int64_t ld_qkv, void* o, int64_t ld_o, void* lse,
+                                          const void* mask, const void* prefix_len, int32_t group, int32_t batch,
+                                          int32_t seq, int32_t heads, float scale, void* stream) {
   if (int rc = device_check()) return rc;
+  if (group < 0 || (group > 0 && prefix_len == nullptr))
+    return set_error(MLA_ERR_ARG, "attn_fwd_sm100: a shared-prefix layout needs prefix_len and group > 0");
   if (batch <= 0 || seq <= 0 || heads <= 0) return set_error(MLA_ERR_ARG, "attn_fwd_sm100: empty problem");
   if ((ld_qkv & 7) || (ld_o & 7) || (reinterpret_cast<uintptr_t>(qkv) & 15))
     return set_error(MLA_ERR_ARG, "attn_fwd_sm100: pitches must be multiples of 8 elements, base 16-byte aligned");
@@ -384,6 +418,7 @@ extern "C" int mla_attn_fwd_sm100(const void* qkv, int64_t ld_qkv, void* o, int6
   FaParams p;
   p.B = batch; p.S = seq; p.H = heads; p.scale = scale;
   p.o = (__nv_bfloat16*)o; p.ld_o = ld_o; p.lse = (float*)lse; p.mask = (const uint8_t*)mask;
+  p.prefix_len = group > 0 ? (const int32_t*)prefix_len : nullptr; p.group = group;
   attn_fwd_sm100_kernel<<<batch * heads * 2, FA_THREADS, FA_SMEM, (cudaStream_t)stream>>>(map_q, map_kv, p);
   MLA_CHECK_LAUNCH("attn_fwd_sm100");
   return MLA_OK;

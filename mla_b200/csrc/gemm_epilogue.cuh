@@ -26,6 +26,7 @@ struct GemmEpilogue {
   const __nv_bfloat16* rope_sin;
   int rope_seq;
   int rope_cols;                   // multiple of 256; 0 = off
+  const int32_t* rope_pos;         // int32 [M] row -> position, or null (position = row % rope_seq)
   // fused SwiGLU (CTA-pair kernel only): the tile holds 128 gate columns | the matching 128 up columns
   __nv_bfloat16* swiglu_out;       // bf16 [M, swiglu_f] = bf16(bf16(silu(gate)) * up)
   int64_t ld_swiglu;
@@ -59,7 +60,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // of the bf16 path: linear -> bf16, x*cos -> bf16, rotate_half(x)*sin -> bf16, sum -> bf16.
 __device__ __forceinline__ void gemm_store_tile_rope(const GemmEpilogue& ep, uint32_t taddr, int64_t row, int n0, int M) {
   const bool row_ok = row < M;
-  const int pos = int(row % ep.rope_seq);
+  const int pos = ep.rope_pos ? (row_ok ? ep.rope_pos[row] : 0) : int(row % ep.rope_seq);
 #pragma unroll 1
   for (int pair = 0; pair < 4; ++pair) {
     const int c1 = (pair >> 1) * 4 + (pair & 1);     // chunks 0,1 (head 0) and 4,5 (head 1): first halves

@@ -137,9 +137,90 @@ __global__ void splice_index_kernel(const int64_t* __restrict__ ids, const uint8
   }
 }
 
+// Shared-prefix variant of the splice: MLA.forward repeats every sample R times (model_mla.py:147-176) but
+// only the [t | x0..xT] rows differ between the copies.  Sample b becomes ONE packed sequence
+//   [ z[:lti] | proprio ]  (prefix, P_b = lti + 1 rows)  ++  R groups [ t_e | x_e,0..x_e,T | EOS ],  e = r*B + b,
+// padded with masked filler rows to the common length S' = F + Lt + R*(n_x + 2).  The rows the reference puts behind the
+// EOS (padding of a right-padded prompt) are masked keys and masked queries there and are simply left out.
+// Row sources: text rows at text_base + b*Lt + j, fused rows at fused_base + b*F + j, proprio rows at pr_base + b,
+// timestep rows at t_base + e, noisy-action rows at x_base + e*n_x + j.
+// Outputs: src_idx int32 [B,S'], mask uint8 [B,S'], rope_pos int32 [B,S'] (groups repeat the positions P_b ..),
+// prefix_len int32 [B], lti int32 [B*R], head_rows int32 [B*R, n_x] (flat packed rows of the x tokens of copy e).
+__global__ void splice_index_shared_kernel(const int64_t* __restrict__ ids, const uint8_t* __restrict__ amask, int B, int Lt,
+                                           int F, int n_x, int R, int64_t eos_id, int text_base, int fused_base,
+                                           int pr_base, int t_base, int x_base, int Sp, int32_t* __restrict__ src_idx,
+                                           uint8_t* __restrict__ mask_out, int32_t* __restrict__ rope_pos,
+                                           int32_t* __restrict__ prefix_len, int32_t* __restrict__ lti_out,
+                                           int32_t* __restrict__ head_rows, int32_t* __restrict__ err_flag) {
+  __shared__ int s_last;
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) s_last = -1;
+  __syncthreads();
+  for (int j = threadIdx.x; j < Lt; j += blockDim.x)
+    if (ids[int64_t(b) * Lt + j] == eos_id) atomicMax(&s_last, j);
+  __syncthreads();
+  int last = s_last;
+  if (last < 0) {
+    if (threadIdx.x == 0) atomicExch(err_flag, 1);  // the reference raises IndexError here
+    last = Lt - 1;
+  }
+  const int lti = last + F;       // position of the proprio row
+  const int P = lti + 1, n = n_x + 2;
+  if (threadIdx.x == 0) prefix_len[b] = P;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) lti_out[r * B + b] = lti;
+  for (int i = threadIdx.x; i < R * n_x; i += blockDim.x) {
+    const int r = i / n_x, j = i - r * n_x;
+    head_rows[(r * B + b) * n_x + j] = b * Sp + P + r * n + 1 + j;
+  }
+  for (int s = threadIdx.x; s < Sp; s += blockDim.x) {
+    int src, m = 1, pos = s;
+    if (s < lti) {
+      if (s >= 1 && s <= F) {
+        src = fused_base + b * F + (s - 1);
+      } else {
+        const int j = s == 0 ? 0 : s - F;
+        src = text_base + b * Lt + j;
+        m = amask ? (amask[int64_t(b) * Lt + j] != 0) : 1;
+      }
+    } else if (s == lti) {
+      src = pr_base + b;
+    } else if (s < P + R * n) {
+      const int q = s - P, r = q / n, k = q - r * n, e = r * B + b;
+      pos = P + k;
+      if (k == 0) src = t_base + e;
+      else if (k <= n_x) src = x_base + e * n_x + (k - 1);
+      else src = text_base + b * Lt + last;           // the EOS token's embedding
+    } else {
+      src = text_base + b * Lt;                       // filler row: masked key, masked query
+      m = 0;
+      pos = 0;
+    }
+    src_idx[int64_t(b) * Sp + s] = src;
+    mask_out[int64_t(b) * Sp + s] = uint8_t(m);
+    rope_pos[int64_t(b) * Sp + s] = pos;
+  }
+}
+
 }  // namespace mla
 
 using namespace mla;
+
+extern "C" int mla_splice_index_shared(const void* input_ids, const void* attn_mask, int32_t batch, int32_t lt,
+                                       int32_t n_fused, int32_t n_x, int32_t repeats, int64_t eos_id, int32_t text_base,
+                                       int32_t fused_base, int32_t pr_base, int32_t t_base, int32_t x_base, void* src_idx,
+                                       void* mask_out, void* rope_pos, void* prefix_len, void* lti_out, void* head_rows,
+                                       void* err_flag, void* stream) {
+  if (int rc = device_check()) return rc;
+  if (batch <= 0) return MLA_OK;
+  if (lt < 1 || n_fused < 0 || n_x < 1 || repeats < 1) return set_error(MLA_ERR_ARG, "splice_index_shared: bad sizes");
+  const int Sp = n_fused + lt + repeats * (n_x + 2);
+  splice_index_shared_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(
+      (const int64_t*)input_ids, (const uint8_t*)attn_mask, batch, lt, n_fused, n_x, repeats, eos_id, text_base, fused_base,
+      pr_base, t_base, x_base, Sp, (int32_t*)src_idx, (uint8_t*)mask_out, (int32_t*)rope_pos, (int32_t*)prefix_len,
+      (int32_t*)lti_out, (int32_t*)head_rows, (int32_t*)err_flag);
+  MLA_CHECK_LAUNCH("splice_index_shared");
+  return MLA_OK;
+}
 
 extern "C" int mla_patchify(const void* pixels, void* out, int32_t batch, int32_t c_total, int32_t himg, int32_t wimg,
                             int32_t patch, int32_t conv_stride, int32_t k_pad, void* stream) {

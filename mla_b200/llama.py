@@ -100,6 +100,15 @@ class LayerShape:
     mask: Optional[torch.Tensor]      # uint8 [B,S] or None
     cos: torch.Tensor                 # bf16 [S, D/2]
     sin: torch.Tensor
+    # shared-prefix layout: rows >= prefix_len[b] are `group`-row suffix groups (one per diffusion repeat)
+    # that see the prefix and their own group; rope_pos maps every row to its rotary position
+    prefix_len: Optional[torch.Tensor] = None     # int32 [B]
+    group: int = 0
+    rope_pos: Optional[torch.Tensor] = None       # int32 [B*S]
+
+    @property
+    def grouped(self):
+        return (self.prefix_len, self.group) if self.group else None
 
 
 class LlamaDecoderLayer(nn.Module):
@@ -196,11 +205,13 @@ class LlamaDecoderLayer(nn.Module):
         n1 = ops.rmsnorm_fwd(x, l1, self.eps)
         if sh.D == 128 and FUSE_ROPE["on"]:
             # RoPE in the projection's epilogue (q and k heads = the leading 2*H*D columns), no extra HBM pass
-            qkv = ops.gemm(n1, wqkv, rope=(sh.cos, sh.sin, sh.S, 2 * sh.H * sh.D))
+            qkv = ops.gemm(n1, wqkv, rope=(sh.cos, sh.sin, sh.S, 2 * sh.H * sh.D, sh.rope_pos))
         else:
+            if sh.group:
+                raise ops._lib.MlaError("the shared-prefix layout needs head_dim 128 with RoPE fused into the projection")
             qkv = ops.gemm(n1, wqkv)
             ops.rope_(qkv, 0, 2 * sh.H, sh.D, sh.S, sh.cos, sh.sin)      # q and k heads are contiguous
-        ctx, lse = ops.attn_fwd(qkv, sh.B, sh.S, sh.H, sh.D, sh.mask)
+        ctx, lse = ops.attn_fwd(qkv, sh.B, sh.S, sh.H, sh.D, sh.mask, grouped=sh.grouped)
         x_mid = ops.gemm(ctx, wo, residual=x)
         return n1, qkv, ctx, lse, x_mid
 
@@ -281,8 +292,11 @@ class LlamaDecoderLayer(nn.Module):
         dctx = ops.gemm(dx_mid, wo, b_mn=True)
         if ops.attn_bwd_fuses_rope(sh.D) and FUSE_ROPE["on"]:
             # the backward of RoPE rides in the attention kernel's epilogue (no extra pass over dq | dk)
-            dqkv = ops.attn_bwd(dctx, qkv, ctx, lse, sh.B, sh.S, sh.H, sh.D, sh.mask, rope=(sh.cos, sh.sin))
+            dqkv = ops.attn_bwd(dctx, qkv, ctx, lse, sh.B, sh.S, sh.H, sh.D, sh.mask, rope=(sh.cos, sh.sin),
+                                grouped=sh.grouped, rope_pos=sh.rope_pos)
         else:
+            if sh.group:
+                raise ops._lib.MlaError("the shared-prefix layout needs the pipelined attention backward (head_dim 128)")
             dqkv = ops.attn_bwd(dctx, qkv, ctx, lse, sh.B, sh.S, sh.H, sh.D, sh.mask)
             ops.rope_(dqkv, 0, 2 * sh.H, sh.D, sh.S, sh.cos, sh.sin, transpose=True)
         del dctx, ctx, qkv
@@ -389,11 +403,14 @@ class LlamaModel(nn.Module):
         for l in self.layers:
             l.mark_grads_fresh()
 
-    def run_layers(self, x: torch.Tensor, B: int, S: int, mask: Optional[torch.Tensor]) -> List[torch.Tensor]:
-        """x: bf16 [B*S, h].  Returns the list of hidden states (layer inputs + final normed), each [B*S, h]."""
+    def run_layers(self, x: torch.Tensor, B: int, S: int, mask: Optional[torch.Tensor],
+                   prefix_len: Optional[torch.Tensor] = None, group: int = 0,
+                   rope_pos: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+        """x: bf16 [B*S, h].  Returns the list of hidden states (layer inputs + final normed), each [B*S, h].
+        prefix_len / group / rope_pos: shared-prefix layout (see LayerShape)."""
         D = self.hidden_size // self.heads
         cos, sin = self.rope_tables(S, x.device)
-        sh = LayerShape(B, S, self.heads, D, mask, cos, sin)
+        sh = LayerShape(B, S, self.heads, D, mask, cos, sin, prefix_len, group, rope_pos)
         if self._anchor is None or self._anchor.device != x.device:
             self._anchor = torch.zeros(1, device=x.device, requires_grad=True)
         hs = []

@@ -14,6 +14,8 @@ autoregressive samplers (`predict_action_ar`, `_diff_ar`, `_batch`), `from_pretr
 """
 from __future__ import annotations
 
+import os
+
 from functools import partial
 from typing import Callable, Dict, List, Optional, Tuple
 
@@ -30,6 +32,10 @@ IGNORE_INDEX = -100
 
 class MLA(nn.Module):
     verbose = False
+    # SURVEY 8 f2 (opt-in, MLA_SHARE_PREFIX=1 or mla.share_diffusion_prefix = True): the R diffusion copies of a sample
+    # share one decoder prefix in training (image-only configurations: no per-copy randomness in front of the suffix).
+    # Same loss and gradients as the repeated batch, ~R x fewer decoder rows.
+    share_diffusion_prefix = os.environ.get("MLA_SHARE_PREFIX", "0") == "1"
 
     def __init__(self, vlm: PrismaticVLM, action_tokenizer=None, token_size: int = 4096, action_dim: int = 7,
                  future_action_window_size: int = 15, past_action_window_size: int = 0, use_ema: bool = False,
@@ -87,6 +93,8 @@ class MLA(nn.Module):
                                       "the MLA recipes (scripts/*_rlbench.sh) train the diffusion head")
         dev = self.vlm.llm_backbone.llm.lm_head.weight.device
         R = repeated_diffusion_steps
+        share = (self.share_diffusion_prefix and R > 1 and self.training and not (
+            self.use_pointcloud or self.use_tactile or self.use_contrastive or self.use_generation))
 
         def rep(v):
             v = v.to(dev, non_blocking=True)
@@ -107,13 +115,33 @@ class MLA(nn.Module):
         timestep = torch.randint(0, self.diffusion.num_timesteps, (actions_future.size(0),), device=actions.device)
         x = self.diffusion.q_sample(actions_future, timestep, noise)
 
-        output, noise_pred, generation_outputs, generation_losses = self.vlm(
+        if share:
+            # the R copies differ only in (t, x): run the decoder over ONE prefix per sample + R suffix
+            # groups (B * (S + (R-1)*(T+3)) rows instead of B * R * S) — identical loss and gradients
+            B0 = input_ids.shape[0] // R
+            output, noise_pred, generation_outputs, generation_losses = self.vlm.forward_shared_prefix(
+                x=x, t=timestep, proprio=proprio[:B0], input_ids=input_ids[:B0],
+                attention_mask=attention_mask[:B0] if attention_mask is not None else None, images=images,
+                camera_name=camera_name, repeats=R)
+        else:
+            output, noise_pred, generation_outputs, generation_losses = self._vlm_repeated(
+                input_ids, attention_mask, images, next_images, camera_name, point_cloud, next_point_cloud, tactile,
+                next_tactile, labels, x, timestep, proprio, gripper_xyz, inputs_embeds, past_key_values, use_cache,
+                output_attentions, output_hidden_states, return_dict, R)
+        return self._losses(output, noise_pred, noise, actions, timestep, generation_losses)
+
+    def _vlm_repeated(self, input_ids, attention_mask, images, next_images, camera_name, point_cloud, next_point_cloud,
+                      tactile, next_tactile, labels, x, timestep, proprio, gripper_xyz, inputs_embeds, past_key_values,
+                      use_cache, output_attentions, output_hidden_states, return_dict, R):
+        return self.vlm(
             input_ids=input_ids, attention_mask=attention_mask, images=images, next_images=next_images,
             camera_name=camera_name, point_cloud=point_cloud, next_point_cloud=next_point_cloud, tactile=tactile,
             next_tactile=next_tactile, labels=labels, x=x, t=timestep, proprio=proprio, gripper_xyz=gripper_xyz,
             inputs_embeds=inputs_embeds, past_key_values=past_key_values, use_cache=use_cache,
             output_attentions=output_attentions, output_hidden_states=output_hidden_states, return_dict=return_dict,
             use_diff=self.use_diff, image_repeat=R)
+
+    def _losses(self, output, noise_pred, noise, actions, timestep, generation_losses):
         assert noise_pred.shape == noise.shape == actions.shape
         zero = torch.tensor(0, dtype=torch.float32)
         loss_dict = {k: zero for k in ("total_loss", "img_pc_contrastive_loss", "tactile_contrastive_loss",

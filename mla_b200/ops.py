@@ -45,7 +45,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     """C = epilogue(alpha * A_op @ B_op).
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True);  b: [N,K] (b_mn=False, nn.Linear weight) or [K,N] (b_mn=True).
-    rope = (cos [S,64] bf16, sin [S,64] bf16, S, n_cols): rotate the leading n_cols columns (head_dim 128) in the epilogue.
+    rope = (cos [S,64] bf16, sin [S,64] bf16, S, n_cols[, pos int32 [M]]): rotate the leading n_cols columns (head_dim 128)
+    in the epilogue; position = row % S, or pos[row] when the table is given (shared-prefix layout).
     swiglu_out (see include/mla_b200.h): bf16 [M, N/2] receiving SwiGLU of the [gate | up] projection in
     the epilogue; with store_c=False the projection itself is not written (returns None).
     swiglu_bwd = (gu [M, 2N] bf16, dgu [M, 2N] bf16, act [M, N] bf16 or None): the product is d_act of a SwiGLU whose
@@ -90,7 +91,12 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
         g.ldp = _rowmajor_2d(pre_act, "pre_act")
     g.pre_act = _ptr(pre_act)
     if rope is not None:
-        cos_t, sin_t, seq, ncols = rope
+        cos_t, sin_t, seq, ncols = rope[:4]
+        if len(rope) > 4 and rope[4] is not None:
+            _req(rope[4], torch.int32, "rope pos")
+            if rope[4].numel() != M or not rope[4].is_contiguous():
+                raise _lib.MlaError("gemm: rope position table must be a contiguous int32 [M]")
+            g.rope_pos = rope[4].data_ptr()
         _req(cos_t, torch.bfloat16, "rope cos")
         _req(sin_t, torch.bfloat16, "rope sin")
         if tuple(cos_t.shape) != (seq, 64) or tuple(sin_t.shape) != (seq, 64) or not (cos_t.is_contiguous() and sin_t.is_contiguous()):
@@ -253,18 +259,36 @@ def _attn_args(qkv: torch.Tensor, B: int, S: int, H: int, D: int, mask: Optional
     return a
 
 
-def attn_fwd(qkv: torch.Tensor, B: int, S: int, H: int, D: int, mask: Optional[torch.Tensor] = None):
-    """qkv: fused projection [B*S, 3*H*D] (q | k | v, RoPE already applied). Returns (ctx [B*S, H*D], lse [B,H,S])."""
+def _grouped_args(grouped, B: int, name: str):
+    """(prefix_len int32 [B], group) of a shared-prefix layout -> (pointer, group) after validation."""
+    if grouped is None:
+        return None, 0
+    prefix_len, group = grouped
+    _req(prefix_len, torch.int32, f"{name}: prefix_len")
+    if prefix_len.numel() != B or not prefix_len.is_contiguous() or group <= 0:
+        raise _lib.MlaError(f"{name}: shared-prefix layout needs a contiguous int32 prefix_len [B] and group > 0")
+    return prefix_len, int(group)
+
+
+def attn_fwd(qkv: torch.Tensor, B: int, S: int, H: int, D: int, mask: Optional[torch.Tensor] = None,
+             grouped: Optional[tuple] = None):
+    """qkv: fused projection [B*S, 3*H*D] (q | k | v, RoPE already applied). Returns (ctx [B*S, H*D], lse [B,H,S]).
+    grouped = (prefix_len int32 [B], group): shared-prefix layout — rows from prefix_len[b] on are groups of `group` rows
+    that see the whole prefix and, causally, only their own group (tcgen05 kernel, head_dim 128)."""
     a = _attn_args(qkv, B, S, H, D, mask)
     ctx = torch.empty((B * S, H * D), dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty((B, H, S), dtype=torch.float32, device=qkv.device)
     a.o, a.ld_o, a.lse = ctx.data_ptr(), ctx.stride(0), lse.data_ptr()
+    pl, group = _grouped_args(grouped, B, "attention fwd")
     if D == 128 and ATTN_IMPL["fwd"] == "sm100":
         # tcgen05 / TMEM / TMA kernel (head_dim 128); the mma.sync kernel serves head_dim 32 / 64
-        check(_lib.lib().mla_attn_fwd_sm100(C.c_void_p(qkv.data_ptr()), C.c_int64(a.ld_qkv), C.c_void_p(a.o),
-                                            C.c_int64(a.ld_o), C.c_void_p(a.lse), C.c_void_p(a.mask), C.c_int32(B),
-                                            C.c_int32(S), C.c_int32(H), C.c_float(a.scale), _stream()))
+        check(_lib.lib().mla_attn_fwd_sm100_grouped(C.c_void_p(qkv.data_ptr()), C.c_int64(a.ld_qkv), C.c_void_p(a.o),
+                                                    C.c_int64(a.ld_o), C.c_void_p(a.lse), C.c_void_p(a.mask), _p(pl),
+                                                    C.c_int32(group), C.c_int32(B), C.c_int32(S), C.c_int32(H),
+                                                    C.c_float(a.scale), _stream()))
     else:
+        if group:
+            raise _lib.MlaError("attention fwd: the shared-prefix layout needs the tcgen05 kernel (head_dim 128)")
         check(_lib.lib().mla_attn_fwd(C.byref(a), _stream()))
     return ctx, lse
 
@@ -275,7 +299,8 @@ def attn_bwd_fuses_rope(D: int) -> bool:
 
 
 def attn_bwd(dctx: torch.Tensor, qkv: torch.Tensor, ctx: torch.Tensor, lse: torch.Tensor, B: int, S: int, H: int,
-             D: int, mask: Optional[torch.Tensor] = None, rope: Optional[tuple] = None) -> torch.Tensor:
+             D: int, mask: Optional[torch.Tensor] = None, rope: Optional[tuple] = None,
+             grouped: Optional[tuple] = None, rope_pos: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Returns d_qkv [B*S, 3*H*D] (dq | dk | dv) — gradients w.r.t. the post-RoPE q,k and v; with rope = (cos, sin)
     (bf16 [S, 64]; only where attn_bwd_fuses_rope) w.r.t. the PRE-RoPE q and k: the transposed rotation is applied in
     the kernel's epilogue."""
@@ -285,6 +310,13 @@ def attn_bwd(dctx: torch.Tensor, qkv: torch.Tensor, ctx: torch.Tensor, lse: torc
         raise _lib.MlaError("attention bwd: ctx / dctx must be contiguous")
     if rope is not None and not attn_bwd_fuses_rope(D):
         raise _lib.MlaError("attention bwd: fused RoPE transpose needs the pipelined tcgen05 kernel (head_dim 128)")
+    pl, group = _grouped_args(grouped, B, "attention bwd")
+    if group and not attn_bwd_fuses_rope(D):
+        raise _lib.MlaError("attention bwd: the shared-prefix layout needs the pipelined tcgen05 kernel (head_dim 128)")
+    if rope_pos is not None:
+        _req(rope_pos, torch.int32, "rope_pos")
+        if rope_pos.numel() != B * S or not rope_pos.is_contiguous():
+            raise _lib.MlaError("attention bwd: rope_pos must be a contiguous int32 [B*S]")
     dqkv = torch.empty_like(qkv, memory_format=torch.contiguous_format)
     if D == 128 and ATTN_IMPL["bwd"] in ("sm100", "sm100v2"):
         lib = _lib.lib()
@@ -300,10 +332,11 @@ def attn_bwd(dctx: torch.Tensor, qkv: torch.Tensor, ctx: torch.Tensor, lse: torc
                 if tuple(cos_t.shape) != (S, 64) or tuple(sin_t.shape) != (S, 64) or not (
                         cos_t.is_contiguous() and sin_t.is_contiguous()):
                     raise _lib.MlaError("attention bwd: fused RoPE needs contiguous [seq, 64] tables")
-            check(lib.mla_attn_bwd2_sm100(C.c_void_p(qkv.data_ptr()), C.c_int64(a.ld_qkv), _p(ctx), _p(dctx),
-                                          C.c_int64(ctx.stride(0)), _p(lse), C.c_void_p(a.mask), _p(dqkv),
-                                          C.c_int64(dqkv.stride(0)), _p(ws), _p(cos_t), _p(sin_t), C.c_int32(B),
-                                          C.c_int32(S), C.c_int32(H), C.c_float(a.scale), _stream()))
+            check(lib.mla_attn_bwd2_sm100_grouped(C.c_void_p(qkv.data_ptr()), C.c_int64(a.ld_qkv), _p(ctx), _p(dctx),
+                                                  C.c_int64(ctx.stride(0)), _p(lse), C.c_void_p(a.mask), _p(dqkv),
+                                                  C.c_int64(dqkv.stride(0)), _p(ws), _p(cos_t), _p(sin_t), _p(rope_pos),
+                                                  _p(pl), C.c_int32(group), C.c_int32(B), C.c_int32(S), C.c_int32(H),
+                                                  C.c_float(a.scale), _stream()))
             return dqkv
         check(lib.mla_attn_bwd_sm100(C.c_void_p(qkv.data_ptr()), C.c_int64(a.ld_qkv), _p(ctx), _p(dctx),
                                      C.c_int64(ctx.stride(0)), _p(lse), C.c_void_p(a.mask), _p(dqkv),

@@ -329,6 +329,78 @@ class PrismaticVLM(nn.Module):
                                F=F, h=h, n_x=n_x, n_ins=n_ins, fused=fused, patch_indices=patch_indices,
                                valid_mask=valid_mask, pos_pc=pos_pc, lin_img=lin_img, N_pc=N_pc, N_img=N_img, dev=dev)
 
+    def _fused_sequence_shared(self, x, t, proprio, input_ids, attention_mask, images, camera_name, repeats: int):
+        """Shared-prefix packing: the R = `repeats` diffusion copies of a sample (model_mla.py:147-176)
+        differ only in their [t | x] rows, so sample b becomes ONE sequence [prefix | R x (t_e | x_e.. | EOS)] and the
+        decoder runs B * S' rows instead of B * R * S.  x, t arrive per copy (B*R rows, copy e = r*B + b), everything
+        else per sample.  Exact for image-only training (no per-copy randomness in front of the suffix)."""
+        dev = self.llm_backbone.llm.lm_head.weight.device
+        h = self.token_size
+        fused, patch_indices, valid_mask, _, _, _ = self.get_fused_tokens(images, None, None, None, camera_name, 1)
+        B, F, _ = fused.shape
+        input_ids = input_ids.to(dev, non_blocking=True)
+        Lt = input_ids.shape[1]
+        R = repeats
+        text = self.llm_backbone.embed_input_ids(input_ids)                                   # [B, Lt, h]
+        pr = self.proprio_embedder(proprio.to(dev).to(torch.bfloat16))                         # [B, 1, h]
+        xe = self.x_embedder(x.to(dev).to(torch.bfloat16))                                    # [B*R, n_x, h]
+        te = self.t_embedder(t.to(dev)).unsqueeze(1)                                           # [B*R, 1, h]
+        n_x = xe.shape[1]
+        if pr.shape[1] != 1 or xe.shape[0] != B * R:
+            raise ValueError("shared-prefix packing expects one proprio token per sample and B*R noisy-action rows")
+        table = torch.cat([text.reshape(B * Lt, h), fused.reshape(B * F, h), pr.reshape(B, h), te.reshape(B * R, h),
+                           xe.reshape(B * R * n_x, h)], dim=0)
+        Sp = F + Lt + R * (n_x + 2)
+        src_idx = torch.empty((B, Sp), dtype=torch.int32, device=dev)
+        mask = torch.empty((B, Sp), dtype=torch.uint8, device=dev)
+        rope_pos = torch.empty((B, Sp), dtype=torch.int32, device=dev)
+        prefix_len = torch.empty(B, dtype=torch.int32, device=dev)
+        lti = torch.empty(B * R, dtype=torch.int32, device=dev)
+        head_rows = torch.empty((B * R, n_x), dtype=torch.int32, device=dev)
+        if self._err_flag is None or self._err_flag.device != dev:
+            self._err_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        am = None
+        if attention_mask is not None:
+            am = attention_mask.to(dev, non_blocking=True)
+            am = (am if am.dtype in (torch.bool, torch.uint8) else am != 0).contiguous()
+        eos_tag = 2 if self.training else 29871
+        check(_lib.lib().mla_splice_index_shared(
+            ops._p(input_ids.contiguous()), ops._p(am), C.c_int32(B), C.c_int32(Lt), C.c_int32(F), C.c_int32(n_x),
+            C.c_int32(R), C.c_int64(eos_tag), C.c_int32(0), C.c_int32(B * Lt), C.c_int32(B * Lt + B * F),
+            C.c_int32(B * Lt + B * F + B), C.c_int32(B * Lt + B * F + B + B * R), ops._p(src_idx), ops._p(mask),
+            ops._p(rope_pos), ops._p(prefix_len), ops._p(lti), ops._p(head_rows), ops._p(self._err_flag), ops._stream()))
+        embeds = ops.GatherRowsFn.apply(table, src_idx.view(-1))                              # [B*S', h]
+        return SimpleNamespace(embeds=embeds, mask=mask, lti=lti, head_rows=head_rows, B=B, S=Sp, F=F, h=h, n_x=n_x,
+                               prefix_len=prefix_len, rope_pos=rope_pos.view(-1), group=n_x + 2, fused=fused, dev=dev)
+
+    def forward_shared_prefix(self, x, t, proprio, input_ids, attention_mask, images, camera_name, repeats: int):
+        """Training forward of the diffusion head with the R copies of every sample packed behind one shared prefix
+        (see _fused_sequence_shared).  Same returns as forward() in train + diff mode; `output.hidden_states` are
+        [B, S', h] (packed rows), `noise_pred` is [B*R, T+1, action_dim] in the copy order of MLA.forward."""
+        if not (self.use_diff and self.training):
+            raise RuntimeError("forward_shared_prefix is the training path of the diffusion head")
+        if self.use_pointcloud or self.use_tactile or self.use_contrastive or self.use_generation:
+            raise NotImplementedError(
+                "shared-prefix training is exact only without per-copy randomness in front of the suffix: the point "
+                "tokenizer draws a fresh FPS start per copy (Point_PN.py:10), and the contrastive / generation heads "
+                "read per-copy rows")
+        if self.z_embedder.dropout_prob > 0:
+            raise NotImplementedError("class-dropout draws one mask per copy: the prefix is not shared")
+        if self.llm_backbone.llm.compute_lm_loss:
+            raise NotImplementedError("the vocabulary CE over packed rows is not defined; it is discarded in diffusion mode")
+        q = self._fused_sequence_shared(x, t, proprio, input_ids, attention_mask, images, camera_name, repeats)
+        output: CausalLMOutputWithPast = self.llm_backbone(
+            input_ids=None, attention_mask=q.mask, position_ids=None, past_key_values=None,
+            inputs_embeds=q.embeds.view(q.B, q.S, q.h), labels=None, use_cache=None, output_attentions=None,
+            output_hidden_states=True, return_dict=True, prefix_len=q.prefix_len, suffix_group=q.group,
+            rope_pos=q.rope_pos)
+        output.last_true_indices = q.lti
+        self._front_px = None
+        last = output.hidden_states[-1].reshape(q.B * q.S, q.h)
+        rows = ops.GatherRowsFn.apply(last, q.head_rows.view(-1))                             # [B*R*(T+1), h]
+        noise_pred = self.final_layer(rows).reshape(q.B * repeats, q.n_x, self.action_dim)
+        return output, noise_pred, {}, {}
+
     # ------------------------------------------------------------------ forward
     def forward(self, x=None, t=None, z=None, proprio=None, gripper_xyz=None, input_ids=None, attention_mask=None,
                 images=None, camera_name=None, point_cloud=None, tactile=None, labels=None, inputs_embeds=None,
