@@ -286,7 +286,7 @@ def reference_gpu_record():
         return None
 
 
-def measure_ours(args, workload: str, world: int, rank: int, local: int, with_breakdown: bool):
+def measure_ours(args, workload: str, world: int, rank: int, local: int, with_breakdown: bool, share_prefix: bool = False):
     """Builds the drop-in module for `workload`, runs warm-up + timed steps (device-resident and end-to-end), frees it.
     Returns the measurements of this workload (identical on every rank: times are max-reduced over ranks)."""
     import torch.distributed as dist
@@ -298,13 +298,15 @@ def measure_ours(args, workload: str, world: int, rank: int, local: int, with_br
     B, R, Lt, T = (args.batch or DEFAULT_BATCH.get(workload, 8)), 4, 32, 0
     views = EXTRA_VIEWS.get(workload, 0)
     mla = build_model(workload, T, args.stage)
+    mla.share_diffusion_prefix = share_prefix
     trainer = DataParallelTrainer(mla, lr=2e-5, weight_decay=0.0, max_grad_norm=1.0)
     S = 1 + 256 + 256 * (1 + views) + 1 + (Lt - 1) + 1 + 1 + (T + 1)
     tokens = B * R * S
+    decoder_rows = B * (S + (R - 1) * (T + 3)) if share_prefix else tokens
     # stage pretrain keeps the tokenizers' pre-BatchNorm activations through the decoder (7.6 GB for 32 clouds); their
     # backward transients come after the decoder's activations are gone
     reserve = 10.0 + (9.0 if args.stage == "pretrain" else 0.0)
-    levels = [args.save_level] * L if args.save_level != "auto" else plan_save_levels(mla, tokens, reserve_gb=reserve)
+    levels = [args.save_level] * L if args.save_level != "auto" else plan_save_levels(mla, decoder_rows, reserve_gb=reserve)
     mla.vlm.llm_backbone.llm.model.set_save_levels(levels)
 
     host = make_batch(B, Lt, T, 672, 1024, seed=1234 + rank, use_pointcloud=use_pc, use_tactile=use_tac, pin=True,
@@ -400,7 +402,8 @@ def measure_ours(args, workload: str, world: int, rank: int, local: int, with_br
     clocks = sampler.stop() if rank == 0 else None
     mla.vlm.check_errors()
     exch = trainer.exchange_stats() if hasattr(trainer, "exchange_stats") else None
-    res = dict(workload=workload, desc=desc, B=B, R=R, S=S, tokens=tokens, levels=levels, ms_dev=ms_dev, ms_e2e=ms_e2e,
+    res = dict(workload=workload, desc=desc, B=B, R=R, S=S, tokens=tokens, decoder_rows=decoder_rows, levels=levels,
+               ms_dev=ms_dev, ms_e2e=ms_e2e,
                last_loss=last_loss, launches=int(launches), ms_fwd=ms_fwd, ms_fwd_bwd=ms_fwd_bwd, clocks=clocks,
                mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, h2d=batch_bytes(host), exchange=exch,
                unused_params=sum(1 for p in mla.parameters() if p.requires_grad and id(p) not in layer_ids
@@ -428,7 +431,7 @@ def run_ours(args):
     _lib.check(_lib.lib().mla_device_check())
 
     workload = args.workload or ("cfg2" if world == 1 else "cfg4")
-    m = measure_ours(args, workload, world, rank, local, with_breakdown=True)
+    m = measure_ours(args, workload, world, rank, local, with_breakdown=True, share_prefix=args.share_prefix)
     also = None
     if world == 1 and not args.workload and not args.no_also:
         try:        # BASELINE configs[2] on the same GPU in the same run (secondary: must never take the headline down)
@@ -442,6 +445,19 @@ def run_ours(args):
         except Exception as ex:
             sys.stderr.write(f"cfg3 measurement failed: {ex}\n")
             also = {"cfg3": {"error": str(ex)[:200]}}
+        try:        # the same cfg2 step with the 4 diffusion copies sharing one decoder prefix per sample
+            a = measure_ours(args, "cfg2", world, rank, local, with_breakdown=False, share_prefix=True)
+            also["cfg2_shared_prefix"] = {
+                "workload": "cfg2 with MLA.share_diffusion_prefix: same loss and gradients as the repeated batch "
+                            "(tests/test_shared_prefix_gpu.py); the decoder runs one prefix per sample + 4 suffix groups",
+                "ms_per_step": round(a["ms_dev"], 2), "value": round(a["tokens"] / a["ms_dev"] * 1e3, 1),
+                "unit": "tokens/s (the step's 17,536 logical tokens)", "decoder_rows_per_step": a["decoder_rows"],
+                "e2e_value": round(a["tokens"] / a["ms_e2e"] * 1e3, 1), "e2e_ms_per_step": round(a["ms_e2e"], 2),
+                "gpu_launches": a["launches"], "last_loss": a["last_loss"], "peak_mem_gb": round(a["mem_gb"], 1),
+                "note": "reported apart from the headline: the algorithmic-FLOP roofline counts the repeated batch"}
+        except Exception as ex:
+            sys.stderr.write(f"shared-prefix measurement failed: {ex}\n")
+            also["cfg2_shared_prefix"] = {"error": str(ex)[:200]}
     busbw = None
     if world > 1:
         # measured NCCL all-reduce bus bandwidth at the message size the trainer uses (one decoder layer's flat fp32
@@ -493,7 +509,9 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_dev, 2),
         "fwd_ms": m["ms_fwd"], "fwd_bwd_ms": m["ms_fwd_bwd"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{workload}: {m['desc']}", "per_gpu_batch": m["B"], "repeated_diffusion_steps": m["R"],
+        "config": {"workload": f"{workload}: {m['desc']}" + (" [shared decoder prefix across the diffusion copies]"
+                                                             if args.share_prefix else ""),
+                   "per_gpu_batch": m["B"], "repeated_diffusion_steps": m["R"], "decoder_rows_per_gpu_step": m["decoder_rows"],
                    "seq_len": S, "tokens_per_gpu_step": tokens, "global_batch": m["B"] * world, "parallelism": f"dp{world}",
                    "stage": ("pretrain (vision tokenizers trained)" if args.stage == "pretrain" else
                              "post-training (generation heads on)" if workload in GENERATION
@@ -551,7 +569,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 8; 1 for cfg5)")
     ap.add_argument("--save-level", default="auto", choices=["auto", "layer", "mlp", "none"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-also", action="store_true", help="single GPU: skip the secondary cfg3 measurement")
+    ap.add_argument("--no-also", action="store_true", help="single GPU: skip the secondary cfg3 / shared-prefix measurements")
+    ap.add_argument("--share-prefix", action="store_true", help="headline run with MLA.share_diffusion_prefix (cfg2 only)")
     ap.add_argument("--layers-cpu", type=int, default=32, help="reference arm: decoder layers of the CPU sample (32 = full model)")
     ap.add_argument("--stage", default="", choices=["", "pretrain", "finetune", "post-training"],
                     help="freeze_backbones stage (default: finetune; post-training for cfg5)")

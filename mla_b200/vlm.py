@@ -369,7 +369,10 @@ class PrismaticVLM(nn.Module):
             C.c_int32(R), C.c_int64(eos_tag), C.c_int32(0), C.c_int32(B * Lt), C.c_int32(B * Lt + B * F),
             C.c_int32(B * Lt + B * F + B), C.c_int32(B * Lt + B * F + B + B * R), ops._p(src_idx), ops._p(mask),
             ops._p(rope_pos), ops._p(prefix_len), ops._p(lti), ops._p(head_rows), ops._p(self._err_flag), ops._stream()))
-        embeds = ops.GatherRowsFn.apply(table, src_idx.view(-1))                              # [B*S', h]
+        # the EOS embedding row feeds every group (and the filler rows all point at one row): the gather is not
+        # injective here, its backward accumulates (fp32) instead of permuting
+        from .contrastive import _GatherDupFn
+        embeds = _GatherDupFn.apply(table, src_idx.view(-1))                                  # [B*S', h]
         return SimpleNamespace(embeds=embeds, mask=mask, lti=lti, head_rows=head_rows, B=B, S=Sp, F=F, h=h, n_x=n_x,
                                prefix_len=prefix_len, rope_pos=rope_pos.view(-1), group=n_x + 2, fused=fused, dev=dev)
 
