@@ -19,8 +19,12 @@
 //   * the transpose of the rotary embedding (the backward of RoPE on dq and dk) is applied in the epilogue while the
 //     accumulators leave TMEM, bit-identical to the separate in-place pass it replaces (rope_kernel, sign = -1).
 // Per CTA (1 per SM, 576 threads): warp 0 TMA loader, warp 1 MMA issuer, warps 2-9 math group 0, warps 10-17 group 1
-// (two threads per TMEM lane and group, 32 score columns each).  Two CTAs per (batch, head) take that sequence's outer
-// tiles in a zig-zag and walk them persistently.
+// (two threads per TMEM lane and group, 32 score columns each).  Work item = one half of a (batch, head): the sequence's
+// outer tiles are dealt to the two halves in a zig-zag.  The CTAs are PERSISTENT (one per SM, items round-robin): the
+// barriers, the TMEM allocation and the TMA / MMA / math pipelines stay alive across items, the loader runs ahead into
+// the next item, and (TMEM hand-over variant) the fixed operands are double-buffered, so the next outer tile's K_j | V_j
+// (Q_t | dO_t) arrive while the current one computes — at 548-token sequences an outer tile only has ~5 streamed tiles,
+// and the launch / fill / drain of one-CTA-per-item used to cost as much as the steady state.
 // TMEM (512 cols): [S0|dP0|S1|dP1] 4 x 64, accumulators @256 (dV or dQ) and @384 (dK).
 // smem: fixed 2x32 KB | streamed 3 slots x (16+16) KB | 2 x (P^T 16 KB + dS^T 16 KB) | barriers | per-column lse/delta.
 #include <cstdlib>
@@ -59,6 +63,7 @@ struct Bw2Params {
   const int32_t* prefix_len;
   int group;
   const int32_t* rope_pos;
+  const int32_t* batch_masked;   // int32 [B]: 1 when mask[b, :] has a zero (computed by the launcher's flag kernel), or null
 };
 
 __device__ __forceinline__ void b2_named_bar_sync(int id, int nthreads) {
@@ -121,31 +126,46 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
                        Bw2Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* sF1 = smem;                                   // MODE 0: K_j   MODE 1: Q_t
-  uint8_t* sF2 = smem + B2_FIX_BYTES;                    // MODE 0: V_j   MODE 1: dO_t
+  // fixed operands (MODE 0: K_j | V_j, MODE 1: Q_t | dO_t): buffer 0 here, buffer 1 (TS only: the next outer tile is
+  // prefetched while the current one computes) in the P / dS staging area the TS variant does not need
+  uint8_t* sFix0 = smem;
   uint8_t* sX = smem + 2 * B2_FIX_BYTES;                 // 3 slots  MODE 0: Q_i   MODE 1: K_j
   uint8_t* sY = sX + B2_SLOTS * B2_STR_BYTES;            // 3 slots  MODE 0: dO_i  MODE 1: V_j
   uint8_t* sT1 = sY + B2_SLOTS * B2_STR_BYTES;           // 2 buffers: P^T (MODE 0 only)
   uint8_t* sT2 = sT1 + 2 * B2_T_BYTES;                   // 2 buffers: dS^T / dS
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + B2_TILES_BYTES);
-  uint64_t *fix_full = bars, *fix_empty = bars + 1, *in_full = bars + 2 /*3*/, *in_empty = bars + 5 /*3*/,
-           *sd_full = bars + 8 /*2*/, *sd_empty = bars + 10 /*2*/, *ds_full = bars + 12 /*2*/, *acc_done = bars + 14 /*2*/,
-           *acc_full = bars + 16, *acc_empty = bars + 17;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-  int& s_any_masked = *reinterpret_cast<int*>(bars + 19);
+  uint64_t *fix_full = bars /*2*/, *fix_empty = bars + 2 /*2*/, *in_full = bars + 4 /*3*/, *in_empty = bars + 7 /*3*/,
+           *sd_full = bars + 10 /*2*/, *sd_empty = bars + 12 /*2*/, *ds_full = bars + 14 /*2*/, *acc_done = bars + 16 /*2*/,
+           *acc_full = bars + 18, *acc_empty = bars + 19;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  constexpr int NFIX = TS ? 2 : 1;
+  uint8_t* sFix1 = TS ? sT1 : sFix0;
+  auto fix_buf = [&](int ti) -> uint8_t* { return (NFIX == 2 && (ti & 1)) ? sFix1 : sFix0; };
+  auto fix_idx = [&](int ti) { return NFIX == 2 ? (ti & 1) : 0; };
+  auto fix_par = [&](int ti) -> uint32_t { return NFIX == 2 ? ((ti >> 1) & 1) : (ti & 1); };
   float* s_stat = reinterpret_cast<float*>(smem + B2_TILES_BYTES + 256);   // [slot][lse2|delta][64]
 
   const int warp = int(warp_idx_uniform()), lane = threadIdx.x & 31;     // warp-uniform role index (see ptx.cuh)
   const int S = p.S;
   const int n_out = (S + B2_OUT - 1) / B2_OUT;
   const int n_in = (S + B2_IN - 1) / B2_IN;
-  const int half_id = blockIdx.x & 1;
-  const int bh = blockIdx.x >> 1;
-  const int b = bh / p.H, hd = bh % p.H;
   const int HD = p.H * B2_D;
-  const int row_base = b * S;
+  // Persistent CTAs: work item w = (batch, head, half); a CTA walks items blockIdx.x, + gridDim.x, ... with its barriers,
+  // TMEM allocation and pipelines alive across items (the loader runs ahead into the next item).  The halves of
+  // consecutive rounds are swapped so that every CTA alternates between the heavier and the lighter half.
+  const int n_items = p.B * p.H * 2;
+  struct Item { int half_id, bh, b, hd, row_base, col_q, col_k, col_v, col_do; };
+  auto item_of = [&](int w) {
+    Item I;
+    I.half_id = (w & 1) ^ ((w / int(gridDim.x)) & 1);
+    I.bh = w >> 1;
+    I.b = I.bh / p.H; I.hd = I.bh % p.H;
+    I.row_base = I.b * S;
+    I.col_q = I.hd * B2_D; I.col_k = HD + I.hd * B2_D; I.col_v = 2 * HD + I.hd * B2_D; I.col_do = I.hd * B2_D;
+    return I;
+  };
   // outer tiles in order of decreasing work are dealt A B B A A B B A ...
-  auto my_tile = [&](int k) -> int {
+  auto my_tile = [&](int half_id, int k) -> int {
     const int pos = half_id == 0 ? (k == 0 ? 0 : 4 * ((k + 1) >> 1) - ((k & 1) ? 1 : 0)) : (4 * (k >> 1) + 1 + (k & 1));
     if (pos >= n_out) return -1;
     return MODE == 0 ? pos : n_out - 1 - pos;      // dK/dV: key tile 0 sees every query; dQ: the last query tile sees every key
@@ -156,14 +176,13 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_qkv_fix); tma_prefetch_desc(&map_qkv_str);
     tma_prefetch_desc(&map_do_fix); tma_prefetch_desc(&map_do_str);
-    mbar_init(fix_full, 1); mbar_init(fix_empty, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&fix_full[i], 1); mbar_init(&fix_empty[i], 1); }
     for (int i = 0; i < B2_SLOTS; ++i) { mbar_init(&in_full[i], 1); mbar_init(&in_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sd_full[i], 1); mbar_init(&sd_empty[i], B2_GROUP_WARPS);
       mbar_init(&ds_full[i], B2_GROUP_WARPS); mbar_init(&acc_done[i], 1);
     }
     mbar_init(acc_full, 1); mbar_init(acc_empty, 2 * B2_GROUP_WARPS);
-    s_any_masked = 0;
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -176,29 +195,33 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_acc0 = tmem_base + 256, tmem_acc1 = tmem_base + 384;
 
-  // column blocks of the fused [q | k | v] buffer
-  const int col_q = hd * B2_D, col_k = HD + hd * B2_D, col_v = 2 * HD + hd * B2_D, col_do = hd * B2_D;
-
   if (warp == 0) {
     // ================================ TMA loader ================================
     if (lane == 0) {
-      int c = 0;
-      for (int ti = 0;; ++ti) {
-        const int t = my_tile(ti);
+      int c = 0, tg = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const Item I = item_of(w);
+      const int bh = I.bh, row_base = I.row_base, col_q = I.col_q, col_k = I.col_k, col_v = I.col_v, col_do = I.col_do;
+      for (int k = 0;; ++k) {
+        const int t = my_tile(I.half_id, k);
         if (t < 0) break;
-        mbar_wait(fix_empty, (ti & 1) ^ 1);
-        mbar_arrive_expect_tx(fix_full, 2 * B2_FIX_BYTES);
+        const int ti = tg++;
+        uint64_t* ff = &fix_full[fix_idx(ti)];
+        uint8_t* sF1 = fix_buf(ti);
+        uint8_t* sF2 = sF1 + B2_FIX_BYTES;
+        mbar_wait(&fix_empty[fix_idx(ti)], fix_par(ti) ^ 1);
+        mbar_arrive_expect_tx(ff, 2 * B2_FIX_BYTES);
         const int r0 = row_base + t * B2_OUT;
         if (MODE == 0) {
-          tma_load_2d(sF1, &map_qkv_fix, fix_full, col_k, r0);
-          tma_load_2d(sF1 + B2_FIX_BYTES / 2, &map_qkv_fix, fix_full, col_k + 64, r0);
-          tma_load_2d(sF2, &map_qkv_fix, fix_full, col_v, r0);
-          tma_load_2d(sF2 + B2_FIX_BYTES / 2, &map_qkv_fix, fix_full, col_v + 64, r0);
+          tma_load_2d(sF1, &map_qkv_fix, ff, col_k, r0);
+          tma_load_2d(sF1 + B2_FIX_BYTES / 2, &map_qkv_fix, ff, col_k + 64, r0);
+          tma_load_2d(sF2, &map_qkv_fix, ff, col_v, r0);
+          tma_load_2d(sF2 + B2_FIX_BYTES / 2, &map_qkv_fix, ff, col_v + 64, r0);
         } else {
-          tma_load_2d(sF1, &map_qkv_fix, fix_full, col_q, r0);
-          tma_load_2d(sF1 + B2_FIX_BYTES / 2, &map_qkv_fix, fix_full, col_q + 64, r0);
-          tma_load_2d(sF2, &map_do_fix, fix_full, col_do, r0);
-          tma_load_2d(sF2 + B2_FIX_BYTES / 2, &map_do_fix, fix_full, col_do + 64, r0);
+          tma_load_2d(sF1, &map_qkv_fix, ff, col_q, r0);
+          tma_load_2d(sF1 + B2_FIX_BYTES / 2, &map_qkv_fix, ff, col_q + 64, r0);
+          tma_load_2d(sF2, &map_do_fix, ff, col_do, r0);
+          tma_load_2d(sF2 + B2_FIX_BYTES / 2, &map_do_fix, ff, col_do + 64, r0);
         }
         for (int i = in_begin(t); i < in_end(t); ++i, ++c) {
           const int s = c % B2_SLOTS;
@@ -224,6 +247,7 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
           }
         }
       }
+      }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
@@ -232,7 +256,9 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
     {
       constexpr uint32_t idesc_sd = umma_idesc_bf16(B2_OUT, B2_IN, 0, 0);    // 128 x 64,  K = d
       constexpr uint32_t idesc_acc = umma_idesc_bf16(B2_OUT, B2_D, 0, 1);    // 128 x 128, K = 64 streamed rows, B MN-major
-      const uint64_t dF1 = umma_smem_desc_sw128(smem_u32(sF1), 16, 1024), dF2 = umma_smem_desc_sw128(smem_u32(sF2), 16, 1024);
+      const uint64_t dFix0 = umma_smem_desc_sw128(smem_u32(sFix0), 16, 1024);
+      const uint64_t dFix1 = umma_smem_desc_sw128(smem_u32(sFix1), 16, 1024);
+      uint64_t dF1 = dFix0, dF2 = umma_desc_advance(dFix0, B2_FIX_BYTES);     // set per outer tile
       const uint64_t dX0 = umma_smem_desc_sw128(smem_u32(sX), 16, 1024), dY0 = umma_smem_desc_sw128(smem_u32(sY), 16, 1024);
       // the same streamed tiles read MN-major by the accumulation products (LBO = the other 64-column chunk)
       const uint64_t dXm0 = umma_smem_desc_sw128(smem_u32(sX), B2_STR_BYTES / 2, 1024);
@@ -259,15 +285,21 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
         }
         umma_commit_elect(&sd_full[g]);
       };
-      int it = 0;
-      for (int ti = 0;; ++ti) {
-        const int t = my_tile(ti);
+      int it = 0, tg = 0;
+      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      const Item I = item_of(w);
+      for (int k = 0;; ++k) {
+        const int t = my_tile(I.half_id, k);
         if (t < 0) break;
+        const int ti = tg++;
         const int n = in_end(t) - in_begin(t);
-        mbar_wait(fix_full, ti & 1);
+        uint64_t* fe = &fix_empty[fix_idx(ti)];
+        dF1 = (NFIX == 2 && (ti & 1)) ? dFix1 : dFix0;
+        dF2 = umma_desc_advance(dF1, B2_FIX_BYTES);
+        mbar_wait(&fix_full[fix_idx(ti)], fix_par(ti));
         issue_sd(it);
         if (n > 1) issue_sd(it + 1);
-        else umma_commit_elect(fix_empty);
+        else umma_commit_elect(fe);
         for (int j = 0; j < n; ++j) {
           const int c = it + j;
           const int s = c % B2_SLOTS, g = c & 1;
@@ -301,9 +333,10 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
           if (j == n - 1) umma_commit_elect(acc_full);
           // keep the score products two tiles ahead of the accumulation products
           if (j + 2 < n) issue_sd(c + 2);
-          else if (j + 2 == n) umma_commit_elect(fix_empty);       // every score product of this outer tile has been issued
+          else if (j + 2 == n) umma_commit_elect(fe);              // every score product of this outer tile has been issued
         }
         it += n;
+      }
       }
     }
   } else {
@@ -315,22 +348,19 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
     const int r = quarter * 32 + lane;        // row of the outer tile == TMEM lane
     const uint32_t lane_off = uint32_t(quarter * 32) << 16;
     const float sl2 = p.scale * B2_LOG2E;
-    const uint8_t* gmask = p.mask ? p.mask + int64_t(b) * S : nullptr;
-    const int st = threadIdx.x - 64;          // 0..511
-    if (gmask) {
-      int bad = 0;
-      for (int i = st; i < S; i += 2 * B2_GROUP_WARPS * 32) bad |= (gmask[i] == 0);
-      if (bad) atomicOr(&s_any_masked, 1);
-      b2_named_bar_sync(1, 2 * B2_GROUP_WARPS * 32);
-    }
-    const bool use_mask = gmask && s_any_masked;
-    const int P = p.group > 0 ? p.prefix_len[b] : 0x3fffffff;     // keys >= P are visible to their own group only
     uint8_t* myT1 = sT1 + grp * B2_T_BYTES;
     uint8_t* myT2 = sT2 + grp * B2_T_BYTES;
-    int it = 0;
-    for (int ti = 0;; ++ti) {
-      const int t = my_tile(ti);
+    int it = 0, tg = 0;
+    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+    const Item I = item_of(w);
+    const int bh = I.bh, b = I.b, row_base = I.row_base, col_q = I.col_q, col_k = I.col_k, col_v = I.col_v;
+    const uint8_t* gmask = p.mask ? p.mask + int64_t(b) * S : nullptr;
+    const bool use_mask = gmask && (p.batch_masked == nullptr || p.batch_masked[b] != 0);
+    const int P = p.group > 0 ? p.prefix_len[b] : 0x3fffffff;     // keys >= P are visible to their own group only
+    for (int k = 0;; ++k) {
+      const int t = my_tile(I.half_id, k);
       if (t < 0) break;
+      const int ti = tg++;
       const int i0 = in_begin(t), n = in_end(t) - i0;
       const int orow = t * B2_OUT + r;        // key row (MODE 0) / query row (MODE 1) in the sequence
       float row_lse2 = 0.f, row_delta = 0.f;
@@ -502,6 +532,7 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
       if (lane == 0) mbar_arrive(acc_empty);
       it += n;
     }
+    }
   }
 
   tc_fence_before();
@@ -510,6 +541,14 @@ attn_bwd2_sm100_kernel(const __grid_constant__ CUtensorMap map_qkv_fix, const __
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+// flags[b] = 1 when mask[b, :] contains a zero (one CTA per batch row)
+__global__ void attn_mask_flags_kernel(const uint8_t* __restrict__ mask, int S, int32_t* __restrict__ flags) {
+  int bad = 0;
+  for (int i = threadIdx.x; i < S; i += blockDim.x) bad |= (mask[int64_t(blockIdx.x) * S + i] == 0);
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) flags[blockIdx.x] = bad ? 1 : 0;
 }
 
 // defined in attention_bwd_sm100.cu: lse2 = lse * log2(e) and delta = rowsum(dO o O), padded to S_pad per (b, h)
@@ -569,6 +608,12 @@ extern "C" int mla_attn_bwd2_sm100_grouped(const void* qkv, int64_t ld_qkv, cons
   float* lse2 = (float*)workspace;
   float* delta = lse2 + size_t(batch) * heads * s_pad;
   if (int rc = attn_bwd_prep_launch(o, d_o, ld_o, lse, lse2, delta, batch, seq, heads, s_pad, s)) return rc;
+  int32_t* flags = nullptr;
+  if (mask != nullptr) {
+    flags = reinterpret_cast<int32_t*>(delta + size_t(batch) * heads * s_pad);
+    attn_mask_flags_kernel<<<batch, 256, 0, s>>>((const uint8_t*)mask, seq, flags);
+    MLA_CHECK_LAUNCH("attn_mask_flags");
+  }
   CUtensorMap m_qkv_fix, m_qkv_str, m_do_fix, m_do_str;
   const uint64_t dims_qkv[2] = {uint64_t(3) * heads * B2_D, uint64_t(batch) * seq};
   const uint64_t dims_do[2] = {uint64_t(heads) * B2_D, uint64_t(batch) * seq};
@@ -597,7 +642,11 @@ extern "C" int mla_attn_bwd2_sm100_grouped(const void* qkv, int64_t ld_qkv, cons
   p.rope_cos = (const __nv_bfloat16*)rope_cos; p.rope_sin = (const __nv_bfloat16*)rope_sin;
   p.prefix_len = group > 0 ? (const int32_t*)prefix_len : nullptr; p.group = group;
   p.rope_pos = (const int32_t*)rope_pos;
-  const int grid = batch * heads * 2;
+  p.batch_masked = flags;
+  // persistent CTAs, one per SM (an even count: the two halves of a (batch, head) never straddle a round)
+  const int items = batch * heads * 2;
+  int grid = num_sms() & ~1;
+  if (grid > items) grid = items;
   if (g_bwd2_ts) attn_bwd2_sm100_kernel<0, 1><<<grid, B2_THREADS, B2_SMEM, s>>>(m_qkv_fix, m_qkv_str, m_do_fix, m_do_str, p);
   else attn_bwd2_sm100_kernel<0, 0><<<grid, B2_THREADS, B2_SMEM, s>>>(m_qkv_fix, m_qkv_str, m_do_fix, m_do_str, p);
   MLA_CHECK_LAUNCH("attn_bwd2_sm100_dkv");

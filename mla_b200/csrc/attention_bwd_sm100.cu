@@ -433,7 +433,8 @@ using namespace mla;
 
 extern "C" size_t mla_attn_bwd_sm100_workspace(int32_t batch, int32_t seq, int32_t heads) {
   const size_t s_pad = size_t((seq + 127) / 128) * 128;
-  return 2 * sizeof(float) * size_t(batch) * heads * s_pad;
+  // lse2 | delta ([batch, heads, s_pad] f32 each) | per-batch "has padding" flags (int32 [batch], pipelined generation)
+  return 2 * sizeof(float) * size_t(batch) * heads * s_pad + (size_t(batch) * 4 + 15) / 16 * 16;
 }
 
 // Backward for head_dim 128 on the tcgen05 path.  qkv / dqkv: fused [B*S, 3*H*128] buffers (q | k | v column blocks).

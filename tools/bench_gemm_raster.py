@@ -34,21 +34,31 @@ def main():
         "wgrad down (h,f,T)": (lambda: ops.gemm(x, xf, a_mn=True, b_mn=True, out=g[2]), 2.0 * T * H * F),
     }
     res = {}
+    gms = (0, 2, 3, 4, 6, 8, 12, 16, 24, 32, 69)
+    # the part is power-capped and its clock wanders over ~100 ms: every setting is timed over 25 launches, the settings are
+    # interleaved and the whole sweep is repeated 3 times; the median of the three is reported
+    for _ in range(20):
+        ops.gemm(x, wgu)                      # bring the chip to its sustained clocks first
     for name, (fn, fl) in shapes.items():
+        samples = {gm: [] for gm in gms}
+        for rnd in range(3):
+            for gm in gms:
+                lib.mla_gemm_set_group_m(C.c_int32(gm))
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(25):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                samples[gm].append(e0.elapsed_time(e1) / 25)
         row = {}
-        for gm in (0, 2, 3, 4, 6, 8, 12, 16, 24, 32, 69):
-            lib.mla_gemm_set_group_m(C.c_int32(gm))
-            for _ in range(2):
-                fn()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(6):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / 6
-            row["heuristic" if gm == 0 else gm] = {"ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)}
+        for gm in gms:
+            ms = sorted(samples[gm])[1]
+            row["heuristic" if gm == 0 else gm] = {"ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1),
+                                                   "spread": round(max(samples[gm]) / min(samples[gm]), 3)}
         lib.mla_gemm_set_group_m(C.c_int32(0))
         res[name] = row
         print(name, {k: v["tflops"] for k, v in row.items()}, file=sys.stderr, flush=True)
