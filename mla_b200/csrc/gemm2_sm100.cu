@@ -431,8 +431,11 @@ static int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, int M, int
   const int tiles = ((M + 2 * G2_BM - 1) / (2 * G2_BM)) * (SWIGLU ? ep.swiglu_f / G2_BNH : (N + G2_BN - 1) / G2_BN);
   const int max_clusters = num_sms() / 2;
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  int group_m = int((48ll << 20) / (int64_t(2 * G2_BM) * K * 2));
-  group_m = group_m < 2 ? 2 : (group_m > 32 ? 32 : group_m);
+  // M-tiles per rasterisation group: ~64 MB of A panels (256 rows x K) per group, between 6 and 24 — from the sweep of
+  // tools/bench_gemm_raster.py (profiles/r02_gemm_raster.json): K = 4096 is flat from 12 to 24, the K >= 16 K shapes
+  // (weight gradients, gate|up dgrad) peak at 6-8 and lose 10 % at 24
+  int group_m = int((64ll << 20) / (int64_t(2 * G2_BM) * K * 2));
+  group_m = group_m < 6 ? 6 : (group_m > 24 ? 24 : group_m);
   if (g_group_m_override > 0) group_m = g_group_m_override;      // tuning switch (tools/bench_gemm_raster.py)
   kern<<<2 * clusters, G2_THREADS, G2_SMEM_BYTES, stream>>>(ma, mb, M, N, K, group_m, tiles > clusters ? sched : nullptr,
                                                             ep);
