@@ -127,6 +127,53 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_reg_kernel(const __nv_bfloat1
   }
 }
 
+// Warp-per-row variant (h a multiple of 256, h <= 4096): a warp keeps its whole row in registers (NV 16-byte vectors per
+// lane), so there is no block barrier at all, and with 16 warps resident per SM ~128 KB of loads are in flight per SM —
+// the block-per-row kernels above top out at 0.57 of the HBM peak because only ~48 KB are.
+template <int NV>
+__global__ void __launch_bounds__(256, 2) rmsnorm_fwd_warp_kernel(const __nv_bfloat16* __restrict__ x,
+                                                               const __nv_bfloat16* __restrict__ w,
+                                                               __nv_bfloat16* __restrict__ y, float* __restrict__ rstd_out,
+                                                               int64_t rows, int h, int64_t ldx, int64_t ldy, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+    const __nv_bfloat16* xr = x + row * ldx;
+    uint4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const uint4*>(xr + (i * 32 + lane) * 8);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float f[8];
+      unpack8(v[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / float(h) + eps);
+    if (lane == 0 && rstd_out) rstd_out[row] = rstd;
+    __nv_bfloat16* yr = y + row * ldy;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float f[8], g[8];
+      // opaque to the optimiser: unpack again here instead of keeping the 8*NV floats of the first pass alive (spills)
+      asm volatile("" : "+r"(v[i].x), "+r"(v[i].y), "+r"(v[i].z), "+r"(v[i].w));
+      unpack8(v[i], f);
+      // weights: 8 KB, L1-resident; the volatile asm keeps the compiler from hoisting all NV weight loads above the loop
+      // (that would double the live registers and spill)
+      uint4 wq;
+      asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wq.x), "=r"(wq.y), "=r"(wq.z), "=r"(wq.w)
+                   : "l"(w + (i * 32 + lane) * 8));
+      unpack8(wq, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = g[j] * bf16_round(f[j] * rstd);
+      *reinterpret_cast<uint4*>(yr + (i * 32 + lane) * 8) = pack8(f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ RMSNorm bwd
 // dn = dy*w ; dx = rstd*(dn - n*mean(dn*n)) (+ dres) ; dw += sum_rows dy*n.   Each CTA walks rows blockIdx.x,
 // +gridDim.x, ... keeping its dw partial in registers, then does one fp32 atomicAdd per column.
@@ -326,6 +373,27 @@ extern "C" int mla_rmsnorm_fwd(const void* x, const void* w, void* y, void* rstd
   if (rows <= 0) return MLA_OK;
   if (h <= 0 || (h & 7) || (ldx & 7) || (ldy & 7)) return set_error(MLA_ERR_ARG, "rmsnorm_fwd: h, ldx, ldy must be multiples of 8");
   if (mode != 0 && mode != 1) return set_error(MLA_ERR_ARG, "rmsnorm_fwd: mode must be 0 (mean-square) or 1 (variance)");
+  if (mode == 0 && (h & 255) == 0 && h <= 4096 && rows >= 4096) {
+    // large token counts (the decoder's norms): warp-per-row
+    auto s_ = (cudaStream_t)stream;
+    const int64_t want = (rows + 7) / 8;
+    const int grid = int(want < int64_t(num_sms()) * 2 ? want : int64_t(num_sms()) * 2);
+#define LAUNCH_RW(NV_)                                                                                            \
+  rmsnorm_fwd_warp_kernel<NV_><<<grid, 256, 0, s_>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w,            \
+                                                     (__nv_bfloat16*)y, (float*)rstd, rows, h, ldx, ldy, eps)
+    switch (h / 256) {
+      case 1: LAUNCH_RW(1); break;
+      case 2: LAUNCH_RW(2); break;
+      case 4: LAUNCH_RW(4); break;
+      case 8: LAUNCH_RW(8); break;
+      case 16: LAUNCH_RW(16); break;
+      default: goto generic;
+    }
+#undef LAUNCH_RW
+    MLA_CHECK_LAUNCH("rmsnorm_fwd");
+    return MLA_OK;
+  }
+generic:
   int block = (h / 8 + 31) / 32 * 32;
   block = block > 256 ? 256 : block;
   const int vpt = (h / 8 + block - 1) / block;
