@@ -18,8 +18,9 @@ def main():
     B = int(os.environ.get("B", 8))
     use_pc, use_tac, _, _ = bench.WORKLOADS[workload]
     mla = bench.build_model(workload)
+    mla.share_diffusion_prefix = os.environ.get("SHARE", "0") == "1"       # SURVEY 8 f2 (cfg2 only)
     trainer = DataParallelTrainer(mla)
-    tokens = B * 4 * 548
+    tokens = B * (548 + 3 * 3) if mla.share_diffusion_prefix else B * 4 * 548
     mla.vlm.llm_backbone.llm.model.set_save_levels(plan_save_levels(mla, tokens))
     b = map_tensors(make_batch(B, 32, 0, use_pointcloud=use_pc, use_tactile=use_tac), lambda t: t.cuda())
 
@@ -64,7 +65,7 @@ def main():
            "idle_before_kernel_ms_per_step": {k: [v[0] // n_steps, round(v[1] / 1e3 / n_steps, 3)]
                                               for k, v in sorted(gap_by.items(), key=lambda kv: -kv[1][1])[:15]}}
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open("gpurun_out/timeline.json", "w"), indent=1)
+    json.dump(out, open(os.environ.get("OUT", "gpurun_out/timeline.json"), "w"), indent=1)
     print(json.dumps(out, indent=1))
 
 
