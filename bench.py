@@ -126,7 +126,7 @@ def GEMM_SHAPES(T):
 def ncu_gemm_traffic():
     """Mean DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (None if absent)."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")))["gemm"]
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_gemm12_summary.json")))["gemm"]
         return round(sum((r["dram_read_MB"] + r["dram_write_MB"]) * 1e6 for r in d) / len(d))
     except Exception:
         return None
@@ -170,7 +170,7 @@ def gemm_roofline(tokens: int, peak_tf: float, iters: int = 5):
     ach = flops / ms / 1e9
     return {"bound": "tensor", "achieved": round(ach, 1), "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach / peak_tf, 4),
             "traffic": ncu_gemm_traffic(), "traffic_unit": "bytes per launch (dram read+write, ncu --set full, mean of "
-            "the same 12 launches: profiles/r01_ncu_full_summary.json)",
+            "the same 12 launches: profiles/r02_ncu_gemm12_summary.json)",
             "algorithmic_bytes_per_launch": round(sum(2.0 * (m * k + n * k) + (2.0 if i < 8 else 4.0) * m * n
                                                       for i, (m, n, k) in enumerate(GEMM_SHAPES(T))) / 12),
             "kernel": "gemm2_bf16_kernel (tcgen05 cta_group::2, 12 GEMM shapes of one decoder layer fwd+bwd)",
