@@ -98,6 +98,10 @@ typedef struct mla_gemm_args {
   int64_t ld_swiglu_bwd_dgu;
   void* swiglu_bwd_act;
   int64_t ld_swiglu_bwd_act;
+  /* fp32 outputs (weight gradients) only: *sumsq (f32, device) += sum of squares of the values WRITTEN (after the optional
+   * accumulate) — the global gradient norm of clip_grad_norm_ (training/strategies/fsdp.py:310) comes out of the
+   * weight-gradient GEMMs instead of a second pass over 27.8 GB of gradients.  NULL = off. */
+  void* sumsq;
 } mla_gemm_args;
 int mla_gemm_bf16(const mla_gemm_args* args, void* stream);
 /* Kernel selection for mla_gemm_bf16: 0 = one CTA per 128x256 tile, 1 = CTA pairs (tcgen05.mma.cta_group::2, 256x256

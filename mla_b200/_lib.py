@@ -31,6 +31,7 @@ class GemmArgs(C.Structure):
         ("swiglu_bwd_gu", C.c_void_p), ("ld_swiglu_bwd_gu", C.c_int64),
         ("swiglu_bwd_dgu", C.c_void_p), ("ld_swiglu_bwd_dgu", C.c_int64),
         ("swiglu_bwd_act", C.c_void_p), ("ld_swiglu_bwd_act", C.c_int64),
+        ("sumsq", C.c_void_p),
     ]
 
 

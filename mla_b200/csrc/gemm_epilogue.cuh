@@ -27,6 +27,8 @@ struct GemmEpilogue {
   int rope_seq;
   int rope_cols;                   // multiple of 256; 0 = off
   const int32_t* rope_pos;         // int32 [M] row -> position, or null (position = row % rope_seq)
+  float* sumsq;                    // fp32 outputs only: += sum of squares of the values written (the global gradient norm
+                                   // of clip_grad_norm_ without re-reading the gradients), or null
   // fused SwiGLU (CTA-pair kernel only): the tile holds 128 gate columns | the matching 128 up columns
   __nv_bfloat16* swiglu_out;       // bf16 [M, swiglu_f] = bf16(bf16(silu(gate)) * up)
   int64_t ld_swiglu;
@@ -211,6 +213,7 @@ __device__ __forceinline__ void gemm_store_tile(const GemmEpilogue& ep, uint32_t
     return;
   }
   const bool row_ok = row < M;
+  float ss = 0.f;                  // sum of squares of this thread's fp32 outputs (ep.sumsq)
 #pragma unroll 1
   for (int c = 0; c < BN / 32; ++c) {
     const int col0 = n0 + c * 32;
@@ -235,11 +238,16 @@ __device__ __forceinline__ void gemm_store_tile(const GemmEpilogue& ep, uint32_t
             o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
           }
           *reinterpret_cast<float4*>(crow + j) = o;
+          ss += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
         }
       } else {
         #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (col0 + j < N) crow[j] = ep.accumulate ? crow[j] + v[j] : v[j];
+          if (col0 + j < N) {
+            const float o = ep.accumulate ? crow[j] + v[j] : v[j];
+            crow[j] = o;
+            ss += o * o;
+          }
       }
       continue;
     }
@@ -299,6 +307,11 @@ __device__ __forceinline__ void gemm_store_tile(const GemmEpilogue& ep, uint32_t
       for (int j = 0; j < 32; ++j)
         if (col0 + j < N) crow[j] = __float2bfloat16_rn(v[j]);
     }
+  }
+  if (ep.sumsq != nullptr) {       // kernel-uniform; every lane of the (converged) epilogue warp takes part
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0 && ss != 0.f) atomicAdd(ep.sumsq, ss);
   }
 }
 

@@ -335,6 +335,8 @@ extern "C" int mla_gemm_bf16(const mla_gemm_args* g, void* stream_) {
   ep.rope_sin = static_cast<const __nv_bfloat16*>(g->rope_sin);
   ep.rope_seq = g->rope_seq; ep.rope_cols = g->rope_cols;
   ep.rope_pos = static_cast<const int32_t*>(g->rope_pos);
+  ep.sumsq = static_cast<float*>(g->sumsq);
+  if (g->sumsq != nullptr && g->c_dtype != 1) return set_error(MLA_ERR_ARG, "gemm: sumsq applies to fp32 outputs");
   ep.swiglu_out = static_cast<__nv_bfloat16*>(g->swiglu_out); ep.ld_swiglu = g->ld_swiglu;
   ep.swiglu_f = g->swiglu_out ? int(g->n / 2) : 0;
   ep.sb_gu = static_cast<const __nv_bfloat16*>(g->swiglu_bwd_gu); ep.ld_sb_gu = g->ld_swiglu_bwd_gu;

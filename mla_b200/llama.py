@@ -39,6 +39,9 @@ FUSE_SWIGLU = {"on": os.environ.get("MLA_FUSE_SWIGLU", "1") == "1"}
 # SwiGLU BACKWARD inside the epilogue of the down projection's input-gradient GEMM (d_act is never written): same bits
 # as the GEMM followed by swiglu_bwd_act.  MLA_FUSE_SWIGLU_BWD=0 restores the separate pass.
 FUSE_SWIGLU_BWD = {"on": os.environ.get("MLA_FUSE_SWIGLU_BWD", "1") == "1"}
+# Sum of squares of a layer's weight gradients accumulated by the weight-gradient GEMM epilogues themselves (single
+# replica: the trainer then skips its 27.8 GB norm pass).  MLA_FUSE_GRAD_NORM=0 restores the separate pass.
+FUSE_GRAD_NORM = {"on": os.environ.get("MLA_FUSE_GRAD_NORM", "1") == "1"}
 
 
 def side_stream(device) -> "torch.cuda.Stream":
@@ -126,6 +129,9 @@ class LlamaDecoderLayer(nn.Module):
         self._gflat = None
         self._grads_fresh = True
         self._grad_ready_cb = None   # set by the data-parallel trainer: called when this layer's arenas are final
+        self._gnorm2 = None          # f32 [1]: sum of squares of the four weight-gradient matrices (written by the wgrad GEMMs)
+        self._gnorm2_valid = False   # True when _gnorm2 describes what the arenas hold now
+        self._want_gnorm2 = False    # set by the trainer on a single replica
         self._weights_ready = None   # CUDA event: the optimizer's side-stream update of this layer has landed
 
     # ------------------------------------------------------------------ parameter plumbing
@@ -198,6 +204,7 @@ class LlamaDecoderLayer(nn.Module):
     def mark_grads_fresh(self):
         """Next backward overwrites the arenas instead of accumulating (cheaper than zeroing 0.8 GB per layer)."""
         self._grads_fresh = True
+        self._gnorm2_valid = False
 
     # ------------------------------------------------------------------ compute
     def _attn_half(self, x: torch.Tensor, sh: LayerShape, keep: bool):
@@ -257,11 +264,21 @@ class LlamaDecoderLayer(nn.Module):
         overlap = OVERLAP["wgrad"] and dy.is_cuda
         main = torch.cuda.current_stream() if overlap else None
         side = side_stream(dy.device) if overlap else None
+        ss = None
+        if self._want_gnorm2 and FUSE_GRAD_NORM["on"] and not overlap:
+            # the four weight-gradient GEMMs below leave the sum of squares of what they write (the final values, also
+            # when accumulating onto an earlier micro-batch) in _gnorm2
+            if self._gnorm2 is None or self._gnorm2.device != dy.device:
+                self._gnorm2 = torch.zeros(1, dtype=torch.float32, device=dy.device)
+            else:
+                self._gnorm2.zero_()
+            ss = self._gnorm2
+        self._gnorm2_valid = False
 
         def wgrad(d, a, out):
             """out (+)= d^T a.  With overlap: on the side stream, ordered after everything issued so far."""
             if not overlap:
-                ops.gemm(d, a, a_mn=True, b_mn=True, out=out, accumulate=acc)
+                ops.gemm(d, a, a_mn=True, b_mn=True, out=out, accumulate=acc, sumsq=ss)
                 return
             side.wait_stream(main)
             with torch.cuda.stream(side):
@@ -305,6 +322,7 @@ class LlamaDecoderLayer(nn.Module):
         del dqkv, n1
         dx = ops.rmsnorm_bwd(dn1, x, l1, self.eps, dres=dx_mid, dw=g1)
         self._grads_fresh = False
+        self._gnorm2_valid = ss is not None
         if self._grad_ready_cb is not None:
             if overlap:
                 # the arenas are final once BOTH streams are done: issue the exchange behind the side stream

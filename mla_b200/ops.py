@@ -41,7 +41,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, residual: Optional[torch.Tensor] = None,
          pre_act: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = False,
          rope: Optional[tuple] = None, swiglu_out: Optional[torch.Tensor] = None,
-         store_c: bool = True, swiglu_bwd: Optional[tuple] = None) -> torch.Tensor:
+         store_c: bool = True, swiglu_bwd: Optional[tuple] = None, sumsq: Optional[torch.Tensor] = None) -> torch.Tensor:
     """C = epilogue(alpha * A_op @ B_op).
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True);  b: [N,K] (b_mn=False, nn.Linear weight) or [K,N] (b_mn=True).
@@ -120,6 +120,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
             if tuple(act_t.shape) != (M, N):
                 raise _lib.MlaError(f"gemm: swiglu_bwd act must be [{M}, {N}]")
             g.swiglu_bwd_act, g.ld_swiglu_bwd_act = act_t.data_ptr(), _rowmajor_2d(act_t, "swiglu_bwd act")
+    if sumsq is not None:       # fp32 outputs: *sumsq += sum of squares of what this launch writes
+        _req(sumsq, torch.float32, "sumsq")
+        g.sumsq = sumsq.data_ptr()
     if DYNAMIC_TILES["on"]:
         g.sched_ws = _sched_ws(a.device).data_ptr()
     check(_lib.lib().mla_gemm_bf16(C.byref(g), _stream()))

@@ -69,6 +69,8 @@ class DataParallelTrainer:
                 layer_params.add(id(p))
             if self.world > 1:
                 l._grad_ready_cb = self._layer_grads_ready
+            else:
+                l._want_gnorm2 = True     # single replica: the wgrad GEMMs accumulate the gradient norm themselves
         import os
         if self.world > 1 and torch.cuda.is_available() and os.environ.get("MLA_FORCE_DYN", "1") != "0":
             # the all-reduces share the SMs with backward: let the persistent GEMMs claim tiles dynamically so that
@@ -207,7 +209,14 @@ class DataParallelTrainer:
             if l._grads_fresh:
                 continue          # no backward reached this layer since the last step
             g = l._gflat
-            check(lib.mla_sumsq_f32(ops._p(g), C.c_int64(g.numel()), ops._p(self._sumsq), s))
+            if self.world == 1 and l._gnorm2_valid:
+                # the four weight-gradient matrices were normed by the GEMM epilogues that wrote them; only the two
+                # RMSNorm weight gradients (the arena's tail, accumulated atomically) are left
+                self._sumsq.add_(l._gnorm2)
+                tail = g[g.numel() - 2 * l.hidden_size:]
+                check(lib.mla_sumsq_f32(ops._p(tail), C.c_int64(tail.numel()), ops._p(self._sumsq), s))
+            else:
+                check(lib.mla_sumsq_f32(ops._p(g), C.c_int64(g.numel()), ops._p(self._sumsq), s))
         for _, p, _ in self.other:
             if p.grad is not None:
                 g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()

@@ -114,3 +114,35 @@ def test_stream_overlap_is_bit_identical(cuda_lib, level):
     _, _, _, n3a = _run(3, False, False, level=level)
     _, _, _, n3b = _run(3, True, True, level=level)
     assert abs(n3a - n3b) <= 2e-3 * abs(n3a)
+
+
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_gradient_norm_from_the_wgrad_epilogues(cuda_lib, accumulate):
+    """Single replica: the global gradient norm clip_grad_norm_ needs is accumulated by the weight-gradient GEMM epilogues
+    (sum of squares of the values they write) instead of a pass over every gradient — same norm, same update, also when
+    a second micro-batch accumulates onto the first."""
+    from mla_b200 import llama, trainer as T
+    res = {}
+    for fused in (False, True):
+        llama.FUSE_GRAD_NORM["on"] = fused
+        try:
+            m = _model()
+            m.set_save_levels("none")
+            tr = T.DataParallelTrainer(m, lr=1e-2, weight_decay=0.0, max_grad_norm=0.5)
+            torch.manual_seed(9)
+            B, S, h = 2, 150, 128
+            for _ in range(2):
+                for _mb in range(2 if accumulate else 1):
+                    x = (torch.randn(B * S, h, device="cuda") * 0.5).to(torch.bfloat16).requires_grad_(True)
+                    g = torch.randn(B * S, h, device="cuda").to(torch.bfloat16)
+                    m.run_layers(x, B, S, None)[-1].backward(g)
+                assert all(l._gnorm2_valid == fused for l in m.layers)
+                tr.step()
+            torch.cuda.synchronize()
+            res[fused] = (float(tr.grad_norm()), {n: p.detach().clone() for n, p in m.named_parameters()})
+        finally:
+            llama.FUSE_GRAD_NORM["on"] = True
+    (n0, p0), (n1, p1) = res[False], res[True]
+    assert abs(n0 - n1) <= 1e-5 * n0, (n0, n1)
+    for k in p0:
+        assert torch.allclose(p0[k], p1[k], rtol=0, atol=1e-6 + 1e-5 * float(p0[k].abs().max())), k
