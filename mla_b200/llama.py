@@ -44,6 +44,25 @@ FUSE_SWIGLU_BWD = {"on": os.environ.get("MLA_FUSE_SWIGLU_BWD", "1") == "1"}
 FUSE_GRAD_NORM = {"on": os.environ.get("MLA_FUSE_GRAD_NORM", "1") == "1"}
 
 
+# NVTX ranges per decoder layer and phase (MLA_NVTX=1): nsys / ncu --nvtx can then attribute kernels to
+# layer.N.fwd / layer.N.bwd.mlp / layer.N.bwd.attn.  Off by default (two host calls per range).
+NVTX = {"on": os.environ.get("MLA_NVTX", "0") == "1"}
+
+
+class _Range:
+    def __init__(self, name: str):
+        self.name = name
+
+    def __enter__(self):
+        if NVTX["on"]:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if NVTX["on"]:
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def side_stream(device) -> "torch.cuda.Stream":
     key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
     st = _SIDE_STREAMS.get(key)
@@ -235,8 +254,9 @@ class LlamaDecoderLayer(nn.Module):
         return n2, gu, act, y
 
     def forward_impl(self, x: torch.Tensor, sh: LayerShape, save_level: str):
-        n1, qkv, ctx, lse, x_mid = self._attn_half(x, sh, True)
-        n2, gu, act, y = self._mlp_half(x_mid)
+        with _Range(f"layer.{self.layer_idx}.fwd"):
+            n1, qkv, ctx, lse, x_mid = self._attn_half(x, sh, True)
+            n2, gu, act, y = self._mlp_half(x_mid)
         if save_level == "layer":
             saved = (x,)
         elif save_level == "mlp":
@@ -246,6 +266,10 @@ class LlamaDecoderLayer(nn.Module):
         return y, saved
 
     def backward_impl(self, dy: torch.Tensor, saved: Tuple[torch.Tensor, ...], sh: LayerShape, save_level: str):
+        with _Range(f"layer.{self.layer_idx}.bwd"):
+            return self._backward_impl(dy, saved, sh, save_level)
+
+    def _backward_impl(self, dy: torch.Tensor, saved: Tuple[torch.Tensor, ...], sh: LayerShape, save_level: str):
         wqkv, wo, wgu, wd, l1, l2 = self.compute_weights()
         x = saved[0]
         if save_level == "layer":

@@ -81,3 +81,28 @@ def test_predict_action_diff_keeps_existing_tag_and_rejects_unbuilt_modes():
         mla.predict_action_diff(image=object(), instruction="x", unnorm_key="rlbench", use_ddim=False)
     with pytest.raises(AssertionError):
         mla.predict_action_diff(image=object(), instruction="x", unnorm_key="nope")
+
+
+def test_bench_reference_arm_runs_the_unmodified_reference_on_cpu():
+    """`bench.py --impl reference` (the driver's reference arm, also the cpu_baseline leg) drives the UNMODIFIED reference's
+    MLA.forward + backward on the host cores and prints the contract's JSON line; here with one decoder layer so the CPU
+    suite stays short (the GPU box runs all 32).  Skipped where no reference tree is installed."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import pytest
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip("no reference tree (/root/reference or baseline/_ref)")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--layers-cpu", "1"], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES="", RANK="0", WORLD_SIZE="1"))
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "multimodal_tokens_per_sec" and line["unit"] == "tokens/s"
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["layers_cpu"] == 1
+    assert line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["config"]["workload"].startswith("cfg2")
