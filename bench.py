@@ -6,10 +6,11 @@
 
 A step = forward + backward + gradient all-reduce (N>1) + clip + AdamW of one synthetic batch, per-GPU batch 8 x 4
 diffusion repeats = 32 sequences of 548 tokens (17,536 multimodal tokens per GPU per step), random-init weights.
-Default workload: N = 1 -> "cfg2" = BASELINE configs[1] (Llama-2-7B MLA, image-only tokens + 32 text tokens) as the
-headline, with BASELINE configs[2] ("cfg3": + point cloud + tactile + both InfoNCE losses) measured in the same run
-and reported under "also"; N > 1 -> "cfg4" = BASELINE configs[3], the full configuration under DDP (cfg3's flags,
-global batch 8 N).  `--workload` overrides.
+Default workload: the FULL configuration at every N, so that the 1/2/4/8-GPU series BASELINE.json's metric names is one
+weak-scaling series — N = 1 -> "cfg3" = BASELINE configs[2] (image + point cloud + tactile + both InfoNCE losses +
+diffusion head, per-GPU batch 8), N > 1 -> "cfg4" = BASELINE configs[3] (the same flags and per-GPU batch under DDP,
+global batch 8 N).  On one GPU the same run also measures BASELINE configs[1] ("cfg2": image-only) and cfg2 with the
+shared decoder prefix and reports them under "also".  `--workload` overrides (e.g. `--workload cfg2`).
 `value` is timed with the batch already resident in HBM; `e2e` times the same step through the public module call
 with the batch in pinned host memory (H2D inside the timed region) and a D2H read of the loss every step.
 """
@@ -198,6 +199,9 @@ def reference_cpu(steps: int, warmup: int, layers_cpu: int = 32, threads: int = 
     from oracle.ref_model import build_reference_7b, ref_call
     from mla_b200.synthetic import make_batch
     use_pc = WORKLOADS[workload][0]
+    if use_pc and layers_cpu < 9:
+        raise SystemExit("the full configuration's InfoNCE loss reads hidden_states[8] (modeling_llama.py:1274): "
+                         "--layers-cpu must be at least 9 (or pass --workload cfg2)")
     quiet = contextlib.redirect_stdout(io.StringIO())        # the reference prints its loss dict every forward
     t0 = time.perf_counter()
     with quiet, contextlib.redirect_stderr(io.StringIO()):
@@ -268,16 +272,19 @@ def cpu_baseline_subprocess(workload: str):
     raise RuntimeError((r.stderr or r.stdout)[-300:])
 
 
-def reference_gpu_record():
-    """R-GPU: the unmodified reference (PyTorch + flash-attn 2.8.3) on one B200, measured by tools/ref_gpu.py this round
-    and committed under profiles/ — a recorded number, not re-measured in this run."""
+def reference_gpu_record(workload: str = "cfg3"):
+    """R-GPU: the unmodified reference (PyTorch + flash-attn 2.8.3) on one B200 at the same per-GPU workload, measured by
+    tools/ref_gpu.py this round and committed under profiles/ — a recorded number, not re-measured in this run."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r02_ref_gpu_cfg2.json")))
+        name = f"r02_ref_gpu_{workload}.json"
+        if not os.path.exists(os.path.join(ROOT, "profiles", name)):
+            name = "r02_ref_gpu_cfg2.json"
+        d = json.load(open(os.path.join(ROOT, "profiles", name)))
         runs = {r["variant"].split(":")[0].split(",")[0] + (" ckpt" if r.get("activation_checkpointing") else " no-ckpt"): r
                 for r in d["runs"]}
         full = next(r for r in d["runs"] if "step_ms" in r)
         fb = next(r for r in d["runs"] if "fwd_bwd_ms" in r and r["activation_checkpointing"])
-        return {"source": "profiles/r02_ref_gpu_cfg2.json (tools/ref_gpu.py step, recorded, same B200 pool)",
+        return {"source": f"profiles/{name} (tools/ref_gpu.py step, recorded, same B200 pool)",
                 "workload": d["workload"], "attn": f"flash_attn {d['flash_attn']}", "step_ms": full["step_ms"],
                 "tokens_per_s": full["tokens_per_s"], "fwd_ms": fb["fwd_ms"], "fwd_bwd_ms_checkpointed": fb["fwd_bwd_ms"],
                 "fwd_bwd_ms_no_checkpointing": next((r["fwd_bwd_ms"] for r in d["runs"] if "fwd_bwd_ms" in r
@@ -430,21 +437,21 @@ def run_ours(args):
     from mla_b200 import _lib
     _lib.check(_lib.lib().mla_device_check())
 
-    workload = args.workload or ("cfg2" if world == 1 else "cfg4")
+    workload = args.workload or ("cfg3" if world == 1 else "cfg4")
     m = measure_ours(args, workload, world, rank, local, with_breakdown=True, share_prefix=args.share_prefix)
     also = None
     if world == 1 and not args.workload and not args.no_also:
-        try:        # BASELINE configs[2] on the same GPU in the same run (secondary: must never take the headline down)
-            a = measure_ours(args, "cfg3", world, rank, local, with_breakdown=False)
-            also = {"cfg3": {"workload": f"cfg3: {a['desc']}", "ms_per_step": round(a["ms_dev"], 2),
+        try:        # BASELINE configs[1] on the same GPU in the same run (secondary: must never take the headline down)
+            a = measure_ours(args, "cfg2", world, rank, local, with_breakdown=False)
+            also = {"cfg2": {"workload": f"cfg2: {a['desc']}", "ms_per_step": round(a["ms_dev"], 2),
                              "value": round(a["tokens"] / a["ms_dev"] * 1e3, 1), "unit": "tokens/s",
                              "e2e_value": round(a["tokens"] / a["ms_e2e"] * 1e3, 1), "e2e_ms_per_step": round(a["ms_e2e"], 2),
                              "h2d_bytes_per_step": a["h2d"], "gpu_launches": a["launches"], "last_loss": a["last_loss"],
                              "peak_mem_gb": round(a["mem_gb"], 1),
                              "step_frac_of_peak": round(step_flops(a["tokens"], a["S"]) / a["ms_dev"] / 1e9 / peaks()[2], 4)}}
         except Exception as ex:
-            sys.stderr.write(f"cfg3 measurement failed: {ex}\n")
-            also = {"cfg3": {"error": str(ex)[:200]}}
+            sys.stderr.write(f"cfg2 measurement failed: {ex}\n")
+            also = {"cfg2": {"error": str(ex)[:200]}}
         try:        # the same cfg2 step with the 4 diffusion copies sharing one decoder prefix per sample
             a = measure_ours(args, "cfg2", world, rank, local, with_breakdown=False, share_prefix=True)
             also["cfg2_shared_prefix"] = {
@@ -523,7 +530,7 @@ def run_ours(args):
         "e2e": {"value": round(world * tokens / ms_e2e * 1e3, 1), "unit": "tokens/s", "ms_per_step": round(ms_e2e, 2),
                 "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": 4, "last_loss": m["last_loss"]},
         "gpu_launches": m["launches"], "clocks": m["clocks"], "roofline": roof, "cpu_baseline": cpu,
-        "reference_gpu": reference_gpu_record(),
+        "reference_gpu": reference_gpu_record("cfg2" if workload == "cfg2" else "cfg3"),
     }
     if m["exchange"]:
         out["gradient_exchange"] = dict(m["exchange"], allreduce_alone=busbw,
@@ -543,7 +550,7 @@ def run_reference(args):
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    workload = args.workload or ("cfg2" if world == 1 else "cfg4")
+    workload = args.workload or ("cfg3" if world == 1 else "cfg4")
     res = reference_cpu(args.steps, args.warmup, layers_cpu=args.layers_cpu, workload=workload)
     desc = WORKLOADS[workload][3]
     out = {"impl": "reference", "metric": "multimodal_tokens_per_sec", "value": res["value"], "unit": "tokens/s",
@@ -565,7 +572,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="", choices=[""] + sorted(WORKLOADS),
-                    help="default: cfg2 (+ cfg3 under 'also') on one GPU, cfg4 (the full configuration) under DDP")
+                    help="default: the full configuration (cfg3 on one GPU, + cfg2 under 'also'; cfg4 under DDP)")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: 8; 1 for cfg5)")
     ap.add_argument("--save-level", default="auto", choices=["auto", "layer", "mlp", "none"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -85,8 +85,9 @@ def test_predict_action_diff_keeps_existing_tag_and_rejects_unbuilt_modes():
 
 def test_bench_reference_arm_runs_the_unmodified_reference_on_cpu():
     """`bench.py --impl reference` (the driver's reference arm, also the cpu_baseline leg) drives the UNMODIFIED reference's
-    MLA.forward + backward on the host cores and prints the contract's JSON line; here with one decoder layer so the CPU
-    suite stays short (the GPU box runs all 32).  Skipped where no reference tree is installed."""
+    MLA.forward + backward on the host cores and prints the contract's JSON line; here with one decoder layer of the image-only
+    workload so the CPU suite stays short (the GPU box runs all 32 layers of the full configuration; its InfoNCE loss reads
+    hidden_states[8], so that one needs at least 9).  Skipped where no reference tree is installed."""
     import json
     import os
     import subprocess
@@ -98,7 +99,7 @@ def test_bench_reference_arm_runs_the_unmodified_reference_on_cpu():
     if not ref_shim.available():
         pytest.skip("no reference tree (/root/reference or baseline/_ref)")
     r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                        "--layers-cpu", "1"], capture_output=True, text=True, timeout=600,
+                        "--layers-cpu", "1", "--workload", "cfg2"], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, CUDA_VISIBLE_DEVICES="", RANK="0", WORLD_SIZE="1"))
     assert r.returncode == 0, r.stderr[-500:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
