@@ -39,6 +39,8 @@ const char* mla_last_error(void);
 int mla_device_check(void);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches counter). */
 int64_t mla_launch_count(void);
+/* TMA descriptors (CUtensorMap) are cached per host thread by (pointer, dims, strides, box): hits / driver encodes so far. */
+void mla_tmap_cache_stats(int64_t* hits, int64_t* misses);
 
 /* ---- GEMM (tcgen05 + TMA) --------------------------------------------------------------------------------
  * C[M,N] = epilogue(alpha * A_op[M,K] . B_op[K,N]).
@@ -387,6 +389,35 @@ int mla_gemv_fused(const mla_gemv_args* a, void* stream);
  * the previous kernel's tail; consumers griddepcontrol.wait before touching activations).  0 turns it off (env
  * MLA_DECODE_PDL=0 does the same). */
 int mla_decode_set_pdl(int32_t on);
+/* decode_stack: the n suffix rows per sample (batch*n <= 2) through ALL decoder layers in ONE persistent launch
+ * (csrc/decode_stack.cu) — replaces layers x [gemv_fused, decode_attn_rope, gemv_fused, gemv_fused, gemv_fused]
+ * (LlamaModel.decode; modeling_llama.py:405-597 per layer on the suffix rows of MLA.predict_action_diff,
+ * model_mla.py:592-775).  One CTA per SM: a producer thread streams every layer's weights through a shared-memory ring
+ * without ever waiting for activations, the consumer warps walk the five phases of each layer separated by a grid
+ * barrier.  Bit-identical to the per-op path with split-K attention.
+ *   w_qkv / w_o / w_gate_up / w_down / ln1 / ln2 / kv_cache: DEVICE arrays of `layers` device pointers (bf16, contiguous:
+ *   [3h,h] [h,h] [2*ffn,h] [h,ffn] [h] [h] and the head-major prefix cache [batch, 2, heads, prefix, head_dim]).
+ *   x bf16 [batch*n, h]: layer-0 input on entry, last layer's output on return (final norm not applied).
+ *   qkv [batch*n, 3h], ctx / x_mid [batch*n, h], gate_up [batch*n, 2*ffn]: bf16 scratch.
+ *   cos_t / sin_t bf16 [n, head_dim/2]: RoPE table rows of positions prefix..prefix+n-1.
+ *   workspace: mla_decode_stack_workspace(...) bytes, ZEROED once before the first launch (arrival counters and the
+ *   grid barrier re-arm themselves).  head_dim in {32, 64, 128}; h, ffn multiples of 8 and <= 12288. */
+typedef struct mla_decode_stack_args {
+  const void* const* w_qkv;
+  const void* const* w_o;
+  const void* const* w_gate_up;
+  const void* const* w_down;
+  const void* const* ln1;
+  const void* const* ln2;
+  const void* const* kv_cache;
+  void *x, *qkv, *ctx, *x_mid, *gate_up;
+  const void *cos_t, *sin_t;
+  void* workspace;
+  int32_t layers, batch, n, prefix, heads, head_dim, ffn;
+  float eps, scale;
+} mla_decode_stack_args;
+int mla_decode_stack(const mla_decode_stack_args* a, void* stream);
+size_t mla_decode_stack_workspace(int32_t batch, int32_t n, int32_t prefix, int32_t heads, int32_t head_dim);
 /* rope_cache: the n new rows per sample of a packed q|k|v projection bf16 [batch*n, 3*heads*head_dim] at positions
  * prefix..prefix+n-1: RoPE (modeling_llama.py:184-208) on q in place and on k into cache row (b*(prefix+n) + prefix + i),
  * v copied beside it; cache bf16 [batch*(prefix+n), 2*heads*head_dim] = k | v; cos/sin bf16 [n, head_dim/2]. */

@@ -59,6 +59,13 @@ def launch_count() -> int:
     return int(lib().mla_launch_count())
 
 
+def tmap_cache_stats() -> tuple:
+    """(hits, misses) of the TMA-descriptor cache inside the library."""
+    h, m = C.c_int64(0), C.c_int64(0)
+    lib().mla_tmap_cache_stats(C.byref(h), C.byref(m))
+    return int(h.value), int(m.value)
+
+
 class AttnArgs(C.Structure):
     _fields_ = [
         ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("ld_qkv", C.c_int64),
@@ -104,4 +111,17 @@ class GemvArgs(C.Structure):
         ("m", C.c_int32), ("n", C.c_int32), ("k", C.c_int32),
         ("ldx", C.c_int64), ("ldw", C.c_int64), ("ldo", C.c_int64), ("ldr", C.c_int64),
         ("prologue", C.c_int32), ("eps", C.c_float),
+    ]
+
+
+class DecodeStackArgs(C.Structure):
+    """mla_decode_stack_args (include/mla_b200.h)."""
+    _fields_ = [
+        ("w_qkv", C.c_void_p), ("w_o", C.c_void_p), ("w_gate_up", C.c_void_p), ("w_down", C.c_void_p),
+        ("ln1", C.c_void_p), ("ln2", C.c_void_p), ("kv_cache", C.c_void_p),
+        ("x", C.c_void_p), ("qkv", C.c_void_p), ("ctx", C.c_void_p), ("x_mid", C.c_void_p), ("gate_up", C.c_void_p),
+        ("cos_t", C.c_void_p), ("sin_t", C.c_void_p), ("workspace", C.c_void_p),
+        ("layers", C.c_int32), ("batch", C.c_int32), ("n", C.c_int32), ("prefix", C.c_int32), ("heads", C.c_int32),
+        ("head_dim", C.c_int32), ("ffn", C.c_int32),
+        ("eps", C.c_float), ("scale", C.c_float),
     ]

@@ -2,6 +2,7 @@
 // through the driver entry point (so the .so links against nothing but the static CUDA runtime and still loads
 // on a box without libcuda — the C-ABI export test runs there).
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "mla_internal.cuh"
@@ -58,8 +59,57 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// Descriptor cache: a CUtensorMap is a pure function of (pointer, rank, dims, strides, box) — it holds no reference to
+// the memory's contents — and the training step asks for the same few hundred of them every step (the per-layer weight,
+// activation and gradient buffers keep their addresses).  Direct-mapped, per host thread, so there is no lock on the
+// launch path; a miss costs one driver encode (~1-2 us), a hit a 72-byte compare.
+struct TmapKey {
+  const void* ptr;
+  uint64_t dims[3], strides[2];
+  uint32_t box[3], rank;
+};
+struct TmapEntry {
+  TmapKey key;
+  CUtensorMap map;
+  bool valid;
+};
+constexpr int kTmapCacheSize = 2048;
+static std::atomic<int64_t> g_tmap_hits{0}, g_tmap_misses{0};
+
+static int encode_nd_uncached(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
+                              const uint32_t* box);
+
 static int encode_nd(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
                      const uint32_t* box) {
+  static thread_local TmapEntry* cache = nullptr;
+  if (!cache) cache = static_cast<TmapEntry*>(calloc(kTmapCacheSize, sizeof(TmapEntry)));
+  if (!cache || rank > 3) return encode_nd_uncached(map, ptr, rank, dims, strides, box);
+  TmapKey k;
+  memset(&k, 0, sizeof(k));
+  k.ptr = ptr;
+  k.rank = uint32_t(rank);
+  for (int i = 0; i < rank; ++i) k.dims[i] = dims[i], k.box[i] = box[i];
+  for (int i = 0; i < rank - 1; ++i) k.strides[i] = strides[i];
+  uint64_t h = reinterpret_cast<uint64_t>(ptr) >> 8;
+  h = (h ^ (k.dims[0] * 0x9E3779B97F4A7C15ull) ^ (k.dims[1] * 0xC2B2AE3D27D4EB4Full) ^ (uint64_t(k.box[0]) << 17) ^
+       (uint64_t(k.box[1]) << 29) ^ (k.strides[0] * 0x165667B19E3779F9ull)) *
+      0xD6E8FEB86659FD93ull;
+  TmapEntry& e = cache[(h >> 32) & (kTmapCacheSize - 1)];
+  if (e.valid && memcmp(&e.key, &k, sizeof(k)) == 0) {
+    *map = e.map;
+    g_tmap_hits.fetch_add(1, std::memory_order_relaxed);
+    return MLA_OK;
+  }
+  if (int rc = encode_nd_uncached(map, ptr, rank, dims, strides, box)) return rc;
+  e.key = k;
+  e.map = *map;
+  e.valid = true;
+  g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
+  return MLA_OK;
+}
+
+static int encode_nd_uncached(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
+                              const uint32_t* box) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return set_error(MLA_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t d[5];
@@ -97,4 +147,8 @@ int encode_tmap_3d_bf16(CUtensorMap* map, const void* ptr, const uint64_t dims[3
 extern "C" const char* mla_version(void) { return "mla_b200 0.1.0 (sm_100a)"; }
 extern "C" const char* mla_last_error(void) { return mla::g_err; }
 extern "C" int mla_device_check(void) { return mla::device_check(); }
+extern "C" void mla_tmap_cache_stats(int64_t* hits, int64_t* misses) {
+  if (hits) *hits = mla::g_tmap_hits.load(std::memory_order_relaxed);
+  if (misses) *misses = mla::g_tmap_misses.load(std::memory_order_relaxed);
+}
 extern "C" int64_t mla_launch_count(void) { return mla::g_launches.load(std::memory_order_relaxed); }

@@ -47,6 +47,8 @@ FUSE_GRAD_NORM = {"on": os.environ.get("MLA_FUSE_GRAD_NORM", "1") == "1"}
 # NVTX ranges per decoder layer and phase (MLA_NVTX=1): nsys / ncu --nvtx can then attribute kernels to
 # layer.N.fwd / layer.N.bwd.mlp / layer.N.bwd.attn.  Off by default (two host calls per range).
 NVTX = {"on": os.environ.get("MLA_NVTX", "0") == "1"}
+# inference: all decoder layers of a denoise step in ONE persistent launch (csrc/decode_stack.cu) when batch*rows <= 2
+DECODE_STACK = os.environ.get("MLA_DECODE_STACK", "1") == "1"
 
 
 class _Range:
@@ -483,6 +485,30 @@ class LlamaModel(nn.Module):
         """n suffix rows per sample (x bf16 [B*n, h]) at positions P..P+n-1 -> final-norm hidden states [B*n, h]."""
         cos, sin = self.rope_tables(P + n, x.device)
         cs, sn = cos[P:P + n].contiguous(), sin[P:P + n].contiguous()
-        for layer, cache in zip(self.layers, caches):
-            x = layer.decode(x, cache, B, P, n, cs, sn)
+        D = self.hidden_size // self.heads
+        f = self.layers[0].inter
+        if DECODE_STACK and ops.decode_stack_supported(B * n, self.hidden_size, f, D):
+            x = self._decode_stack(x, caches, B, P, n, cs, sn)
+        else:
+            for layer, cache in zip(self.layers, caches):
+                x = layer.decode(x, cache, B, P, n, cs, sn)
         return ops.rmsnorm_fwd(x, ops.bf16_of(self.norm.weight), self.eps)
+
+    def _decode_stack(self, x, caches, B, P, n, cs, sn):
+        """One persistent launch for all layers (csrc/decode_stack.cu).  The per-layer pointer table and the workspace
+        are built on the first (eager) call for a set of buffers and re-used afterwards — a CUDA-graph capture of the
+        DDIM loop therefore has to be preceded by an eager pass, which VLM.denoise_session does."""
+        ws = [layer.compute_weights() for layer in self.layers]       # refreshes the bf16 copies if a master changed
+        ptrs = tuple(t.data_ptr() for w in ws for t in w) + tuple(c.data_ptr() for c in caches)
+        st = self.__dict__.get("_stack_state")
+        if st is None or st[0] != ptrs:
+            L = len(self.layers)
+            rows = [[w[i].data_ptr() for w in ws] for i in range(6)] + [[c.data_ptr() for c in caches]]
+            table = torch.tensor(rows, dtype=torch.int64).to(x.device)
+            st = (ptrs, table, {})
+            self.__dict__["_stack_state"] = st
+        key = (B, n, P)
+        if key not in st[2]:
+            st[2][key] = ops.decode_stack_workspace(B, n, P, self.heads, self.hidden_size // self.heads, x.device)
+        return ops.decode_stack(x, st[1], cs, sn, st[2][key], B, n, P, self.heads, self.hidden_size // self.heads,
+                                self.layers[0].inter, self.eps)

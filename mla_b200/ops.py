@@ -745,6 +745,47 @@ def decode_attn_rope(qkv: torch.Tensor, kv: torch.Tensor, cos_t: torch.Tensor, s
     return ctx
 
 
+def decode_stack_supported(rows: int, h: int, f: int, D: int) -> bool:
+    """Shapes the one-launch decoder stack (csrc/decode_stack.cu) takes: activations of <= 2 rows live in registers."""
+    return rows <= 2 and D in (32, 64, 128) and h % 8 == 0 and f % 8 == 0 and h <= 12288 and f <= 12288
+
+
+def decode_stack_workspace(B: int, n: int, P: int, H: int, D: int, device) -> torch.Tensor:
+    """Zeroed once; the kernel's arrival counters and grid barrier re-arm themselves."""
+    lib = _lib.lib()
+    lib.mla_decode_stack_workspace.restype = C.c_size_t
+    nbytes = lib.mla_decode_stack_workspace(C.c_int32(B), C.c_int32(n), C.c_int32(P), C.c_int32(H), C.c_int32(D))
+    return torch.zeros(nbytes, dtype=torch.uint8, device=device)
+
+
+def decode_stack(x: torch.Tensor, table: torch.Tensor, cos_t: torch.Tensor, sin_t: torch.Tensor, workspace: torch.Tensor,
+                 B: int, n: int, P: int, H: int, D: int, f: int, eps: float) -> torch.Tensor:
+    """All decoder layers over the n suffix rows per sample in ONE persistent launch (see mla_decode_stack).
+    x bf16 [B*n, h] (not modified); table int64 [7, L] on the device = per-layer pointers of w_qkv, w_o, w_gate_up,
+    w_down, ln1, ln2, kv_cache; returns the last layer's output bf16 [B*n, h] (final norm not applied)."""
+    _req(x, torch.bfloat16, "x")
+    h, M, L = H * D, B * n, table.shape[1]
+    if tuple(x.shape) != (M, h):
+        raise _lib.MlaError(f"decode_stack: x must be [{M}, {h}]")
+    if table.dtype != torch.int64 or table.shape[0] != 7 or not table.is_contiguous():
+        raise _lib.MlaError("decode_stack: the pointer table must be contiguous int64 [7, layers]")
+    dev = x.device
+    xb = x.contiguous().clone()
+    qkv = torch.empty((M, 3 * h), dtype=torch.bfloat16, device=dev)
+    ctx = torch.empty((M, h), dtype=torch.bfloat16, device=dev)
+    xmid = torch.empty((M, h), dtype=torch.bfloat16, device=dev)
+    gu = torch.empty((M, 2 * f), dtype=torch.bfloat16, device=dev)
+    a = _lib.DecodeStackArgs()
+    base = table.data_ptr()
+    a.w_qkv, a.w_o, a.w_gate_up, a.w_down, a.ln1, a.ln2, a.kv_cache = (base + 8 * L * i for i in range(7))
+    a.x, a.qkv, a.ctx, a.x_mid, a.gate_up = xb.data_ptr(), qkv.data_ptr(), ctx.data_ptr(), xmid.data_ptr(), gu.data_ptr()
+    a.cos_t, a.sin_t, a.workspace = cos_t.data_ptr(), sin_t.data_ptr(), workspace.data_ptr()
+    a.layers, a.batch, a.n, a.prefix, a.heads, a.head_dim, a.ffn = L, B, n, P, H, D, f
+    a.eps, a.scale = float(eps), float(D ** -0.5)
+    check(_lib.lib().mla_decode_stack(C.byref(a), _stream()))
+    return xb
+
+
 def ddim_step(x: torch.Tensor, eps: torch.Tensor, coef: torch.Tensor) -> torch.Tensor:
     """x_{t-1} = ddim_sample(x_t, eps) with eta = 0 (see mla_ddim_step); x f32, eps bf16/f32, coef f32 [4] on device."""
     _req(x, torch.float32, "x")

@@ -67,7 +67,8 @@ def test_ctypes_structs_match_header(tmp_path):
     if gcc is None:
         pytest.skip("no C compiler")
     pairs = {"mla_gemm_args": _lib.GemmArgs, "mla_attn_args": _lib.AttnArgs, "mla_mha_args": _lib.MhaArgs,
-             "mla_gen_image_args": _lib.GenImageArgs, "mla_gemv_args": _lib.GemvArgs}
+             "mla_gen_image_args": _lib.GenImageArgs, "mla_gemv_args": _lib.GemvArgs,
+             "mla_decode_stack_args": _lib.DecodeStackArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "mla_b200.h")}"',
              'int main(void) {']
     for cname, ct in pairs.items():

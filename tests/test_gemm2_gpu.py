@@ -149,3 +149,25 @@ def test_fused_swiglu_backward_epilogue_matches_unfused(cuda_lib, M, f, K, mode)
         assert torch.equal(dgu2, dgu_ref)
     finally:
         cuda_lib.mla_gemm_set_mode(C.c_int32(1))
+
+
+def test_tma_descriptor_cache(cuda_lib):
+    """The same operands at the same addresses re-use their encoded TMA descriptors (no driver call on the launch path);
+    an operand of a different shape at a re-used address gets its own descriptor."""
+    from mla_b200 import _lib, ops
+    torch.manual_seed(11)
+    a, b, ref = _mk(512, 512, 256, False, False)
+    out = torch.empty(512, 512, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, out=out)
+    h0, m0 = _lib.tmap_cache_stats()
+    first = out.clone()
+    for _ in range(5):
+        ops.gemm(a, b, out=out)
+    h1, m1 = _lib.tmap_cache_stats()
+    assert m1 == m0 and h1 >= h0 + 10, (h0, m0, h1, m1)
+    assert torch.equal(out, first)
+    # same base address, different logical shape: must not alias the cached descriptor
+    a2 = a.view(-1)[: 256 * 256].view(256, 256)
+    got = ops.gemm(a2, b[:, :256].contiguous())
+    want = a2.float() @ b[:, :256].float().t()
+    assert rel_err(got, want) < 4e-3
