@@ -394,14 +394,14 @@ int mla_decode_set_pdl(int32_t on);
  * (LlamaModel.decode; modeling_llama.py:405-597 per layer on the suffix rows of MLA.predict_action_diff,
  * model_mla.py:592-775).  One CTA per SM: a producer thread streams every layer's weights through a shared-memory ring
  * without ever waiting for activations, the consumer warps walk the five phases of each layer separated by a grid
- * barrier.  Bit-identical to the per-op path with split-K attention.
+ * barrier.  Bit-identical to the per-op path.
  *   w_qkv / w_o / w_gate_up / w_down / ln1 / ln2 / kv_cache: DEVICE arrays of `layers` device pointers (bf16, contiguous:
  *   [3h,h] [h,h] [2*ffn,h] [h,ffn] [h] [h] and the head-major prefix cache [batch, 2, heads, prefix, head_dim]).
  *   x bf16 [batch*n, h]: layer-0 input on entry, last layer's output on return (final norm not applied).
  *   qkv [batch*n, 3h], ctx / x_mid [batch*n, h], gate_up [batch*n, 2*ffn]: bf16 scratch.
  *   cos_t / sin_t bf16 [n, head_dim/2]: RoPE table rows of positions prefix..prefix+n-1.
- *   workspace: mla_decode_stack_workspace(...) bytes, ZEROED once before the first launch (arrival counters and the
- *   grid barrier re-arm themselves).  head_dim in {32, 64, 128}; h, ffn multiples of 8 and <= 12288. */
+ *   workspace: mla_decode_stack_workspace(...) bytes, ZEROED once before the first launch (the grid barrier's
+ *   counters re-arm themselves).  head_dim in {32, 64, 128}; h, ffn multiples of 8 and <= 12288. */
 typedef struct mla_decode_stack_args {
   const void* const* w_qkv;
   const void* const* w_o;
@@ -415,9 +415,20 @@ typedef struct mla_decode_stack_args {
   void* workspace;
   int32_t layers, batch, n, prefix, heads, head_dim, ffn;
   float eps, scale;
+  void* trace; /* null, or int64 [SMs][layers][5][3]: globaltimer ns per CTA at phase entry / work done / barrier passed */
 } mla_decode_stack_args;
 int mla_decode_stack(const mla_decode_stack_args* a, void* stream);
 size_t mla_decode_stack_workspace(int32_t batch, int32_t n, int32_t prefix, int32_t heads, int32_t head_dim);
+/* Profiling only (results become meaningless): 1 = consumers release the ring slots without doing the math, 2 = no grid
+ * barriers, 4 = no attention phase.  0 restores the product behaviour. */
+int mla_decode_stack_set_debug(int32_t flags);
+/* How many weight groups (32-44 KB each, per SM) the producer's L2 prefetch runs in front of its shared-memory ring
+ * (default 12 = ~57 MB chip-wide; env MLA_DECODE_STACK_AHEAD); 0 = no run-ahead. */
+int mla_decode_stack_set_ahead(int32_t groups);
+/* Cap the shared-memory ring (KB; 0 = as large as fits, 192 KB): tuning / profiling. */
+int mla_decode_stack_set_ring_kb(int32_t kb);
+/* Weight rows per ring slot where K > 4096 (the down projection): 1 or 2 (default 2); tuning. */
+int mla_decode_stack_set_rows_per_slot_big(int32_t rows);
 /* rope_cache: the n new rows per sample of a packed q|k|v projection bf16 [batch*n, 3*heads*head_dim] at positions
  * prefix..prefix+n-1: RoPE (modeling_llama.py:184-208) on q in place and on k into cache row (b*(prefix+n) + prefix + i),
  * v copied beside it; cache bf16 [batch*(prefix+n), 2*heads*head_dim] = k | v; cos/sin bf16 [n, head_dim/2]. */

@@ -124,4 +124,5 @@ class DecodeStackArgs(C.Structure):
         ("layers", C.c_int32), ("batch", C.c_int32), ("n", C.c_int32), ("prefix", C.c_int32), ("heads", C.c_int32),
         ("head_dim", C.c_int32), ("ffn", C.c_int32),
         ("eps", C.c_float), ("scale", C.c_float),
+        ("trace", C.c_void_p),
     ]

@@ -43,6 +43,7 @@ struct GemvParams {
   float eps;
   int stages;          // ring depth
   uint32_t pitch;      // bytes per weight row in the ring (K*2 rounded up to 128)
+  int one_copy;        // the rows of a slot are contiguous in global memory and in the ring: one bulk copy per slot
 };
 
 
@@ -81,9 +82,16 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_ring_kernel(GemvParams p) 
         const int n0 = g * RPI;
         const int valid = p.N - n0 < RPI ? p.N - n0 : RPI;
         mbar_arrive_expect_tx(&full_bar[s], row_bytes * valid);
-        for (int r = 0; r < valid; ++r)
-          bulk_load_row(ring + size_t(s) * slot_bytes + size_t(r) * p.pitch, p.w + int64_t(n0 + r) * p.ldw, row_bytes,
-                        &full_bar[s]);
+        if (p.one_copy) {
+          // the rows of a slot are contiguous in global memory (ldw = K) and, with an unpadded pitch, in the ring: ONE bulk
+          // copy.  The producer is a single thread — every instruction it spends per slot is serial latency in front of
+          // the memory pipe (profiles/r02_decode_stack_trace_*.json: issuing row by row cost ~5 % of the streaming rate)
+          bulk_load_row(ring + size_t(s) * slot_bytes, p.w + int64_t(n0) * p.ldw, row_bytes * valid, &full_bar[s]);
+        } else {
+          for (int r = 0; r < valid; ++r)
+            bulk_load_row(ring + size_t(s) * slot_bytes + size_t(r) * p.pitch, p.w + int64_t(n0 + r) * p.ldw, row_bytes,
+                          &full_bar[s]);
+        }
       }
     }
     return;
@@ -165,10 +173,15 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_ring_kernel(GemvParams p) 
   for (int g = blockIdx.x; g < groups; g += gridDim.x, ++it) {
     const int s = it % p.stages;
     const uint32_t ph = (it / p.stages) & 1;
-    mbar_wait(&full_bar[s], ph);
-    const uint8_t* slot = ring + size_t(s) * slot_bytes;
     const int n0 = g * RPI;
     const int passes = GEN ? (p.M + MB - 1) / MB : 1;
+    // fast path: the residual element this thread adds in the slot's epilogue is requested BEFORE the wait for the
+    // weights — otherwise its L2 round trip is paid once per slot by all 512 threads at the next named barrier
+    float resv = 0.f;
+    if (!GEN && p.res && tid < RPI * MB && n0 + tid / MB < p.N && tid % MB < p.M)
+      resv = __bfloat162float(p.res[int64_t(tid % MB) * p.ldr + n0 + tid / MB]);
+    mbar_wait(&full_bar[s], ph);
+    const uint8_t* slot = ring + size_t(s) * slot_bytes;
     for (int pass = 0; pass < passes; ++pass) {
       const int m0 = pass * MB;
       float acc[RPI][MB];
@@ -237,7 +250,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) gemv_ring_kernel(GemvParams p) 
 #pragma unroll
           for (int w2 = 0; w2 < GV_CWARPS; ++w2) t += partial[pb][w2][tid];
           float v = bf16_round(t);
-          if (p.res) v += __bfloat162float(p.res[int64_t(m) * p.ldr + n]);
+          if (p.res) v += GEN ? __bfloat162float(p.res[int64_t(m) * p.ldr + n]) : resv;
           p.out[int64_t(m) * p.ldo + n] = __float2bfloat16_rn(v);
         }
       }
@@ -533,6 +546,14 @@ extern "C" int mla_gemv_fused(const mla_gemv_args* a, void* stream) {
   p.ln_w = (const __nv_bfloat16*)a->ln_weight; p.out = (__nv_bfloat16*)a->out;
   p.M = M; p.N = N; p.K = K; p.ldx = a->ldx; p.ldw = a->ldw; p.ldo = a->ldo; p.ldr = a->ldr; p.eps = a->eps;
   p.pitch = (uint32_t(K) * 2u + 127u) & ~127u;
+  {
+    static int one = -1;
+    if (one < 0) {
+      const char* e = getenv("MLA_GEMV_ONE_COPY");
+      one = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.one_copy = one && a->ldw == K && p.pitch == uint32_t(K) * 2u;
+  }
   const int rpi = small_k ? 4 : 2;
   const size_t slot = size_t(p.pitch) * rpi;
   int stages = int(GV_RING_BYTES / slot);

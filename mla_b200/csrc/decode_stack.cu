@@ -11,24 +11,26 @@
 //     slot: weights do not depend on activations, so it runs ahead across operator and layer boundaries and the HBM
 //     queue stays full while the consumers synchronise;
 //   * the 16 consumer warps go through the five phases of a layer — RMSNorm+QKV, attention, O-proj+residual,
-//     RMSNorm+gate|up, SwiGLU+down+residual — separated by a grid barrier (sense-reversing counter in global memory:
-//     ~1 us, hidden behind the ring's ~3 us of buffered weights);
-//   * attention runs split-K over all SMs (item = (sample, head, 128-key split), last arrival merges), the prefix
-//     K/V of the layer having been pulled into L2 by a bulk prefetch the producer issues one phase earlier.
+//     RMSNorm+gate|up, SwiGLU+down+residual — separated by a grid barrier (arrival counter in global memory: one
+//     L2 round trip, hidden behind the ring's ~3 us of buffered weights);
+//   * attention: one CTA per (sample, head) serves all query rows from one pass over the keys, the prefix K/V of the
+//     layer having been pulled into L2 by a bulk prefetch the producer issues one phase earlier; the other CTAs' rings
+//     fill with the output projection's weights meanwhile.
 // The arithmetic of every phase is the per-op kernels' (same thread -> k-chunk mapping, same reduction trees, same
-// rounding points; attention = decode_attn_kernel<.,ROPE=1> with split-K), so the result is BIT-IDENTICAL to
-// LlamaDecoderLayer.decode run with split-K attention — that is what tests/test_decode_stack_gpu.py asserts.
+// rounding points; attention = decode_attn_kernel<.,ROPE=1>), so the result is BIT-IDENTICAL to
+// LlamaDecoderLayer.decode — that is what tests/test_decode_stack_gpu.py asserts.
 // Activations written by other CTAs inside this launch are read with ld.global.cg (L2): L1 is not coherent.
 // Limits: B*n <= 2 suffix rows (activations live in registers), h <= 12288, f <= 12288, head_dim in {32, 64, 128}.
 #include <cstdlib>
+#include <type_traits>
 
 #include "decode_common.cuh"
 
 namespace mla {
 
 constexpr int ST_MAX_STAGES = 8;
-constexpr int ST_ATTN_UN = 8;                       // keys per warp and split: 16 warps x 8 = 128 keys per item
-constexpr int ST_SPLIT_KEYS = DEC_WARPS * ST_ATTN_UN;
+constexpr int ST_THREADS = GV_CONSUMERS + 64;        // 16 consumer warps | producer warp | finisher warp
+constexpr int ST_ATTN_UN = 8;                       // keys per warp in flight: 16 warps x 8 = 128 keys per pass
 
 struct StackParams {
   const __nv_bfloat16* const* wqkv;     // [L] device pointers: [3h, h]
@@ -40,13 +42,15 @@ struct StackParams {
   const __nv_bfloat16* const* cache;    // [B, 2, H, P, D] rotated prefix keys | values (head-major)
   __nv_bfloat16 *x, *qkv, *ctx, *xmid, *gu;     // [M,h] (in/out) | [M,3h] | [M,h] | [M,h] | [M,2f]
   const __nv_bfloat16 *cos, *sin;       // [n, D/2]: table rows of positions P..P+n-1
-  float* attn_ws;                       // [B*H*n, S, D+2] split-K partials
-  int* attn_cnt;                        // [B*H] arrival counters (zero on entry, left zero)
-  unsigned* bar;                        // [2] grid barrier: arrivals, generation (zero-initialised once)
+  unsigned* bar;                        // [3] grid barrier: two alternating arrival counters + selector (zeroed once)
+  long long* trace;                     // null, or [grid][L][5 phases][3] globaltimer ns: phase entry, work done, barrier passed
   int L, B, n, P, H, D, h, f;
   float eps, scale;
   int stages;
   uint32_t slot_bytes;
+  int rpi_big;    // weight rows per ring slot where K > 4096 (1 or 2)
+  int ahead;      // weight groups the L2 prefetch cursor runs in front of the ring (0 = no run-ahead)
+  int dbg;        // profiling only (mla_decode_stack_set_debug): 1 = consumers skip the math, 2 = no grid barriers, 4 = no attention
 };
 
 __device__ __forceinline__ uint4 ld_cg16(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
@@ -75,35 +79,56 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-// All consumer threads of all CTAs.  Sense-reversing: bar[0] counts arrivals and is reset by the last one, bar[1] is the
-// generation everybody else spins on — no host-side reset between launches.
-__device__ __forceinline__ void grid_barrier(unsigned* bar, int tid) {
-  consumers_sync();
+// Grid barrier for the consumer threads of all CTAs: a monotonic arrival counter — one fire-and-forget red.add per CTA,
+// then everybody polls until the count reaches (k+1) * grid for the k-th barrier of the launch: one L2 round trip after
+// the last arrival.  Two counters alternate between launches (bar[2] = which one this launch uses): CTA 0 clears the
+// idle one at its start and flips the selector after the first barrier, when every CTA is known to have read it — so
+// nothing has to be reset from the host.
+struct GridBar {
+  unsigned* ctr;
+  unsigned target;
+};
+// consumers + the finisher warp (whose output stores must be ordered before the arrival)
+__device__ __forceinline__ void cta_workers_sync() { asm volatile("bar.sync 2, %0;" ::"n"(GV_CONSUMERS + 32) : "memory"); }
+__device__ __forceinline__ void grid_barrier(GridBar& gb, int tid, int dbg = 0) {
+  if (dbg & 2) { cta_workers_sync(); return; }
+  cta_workers_sync();
   if (tid == 0) {
-    const unsigned gen = ld_acquire_u32(bar + 1);
-    __threadfence();
-    if (atomicAdd(bar, 1u) == gridDim.x - 1) {
-      bar[0] = 0u;
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
-    } else {
-      while (ld_acquire_u32(bar + 1) == gen) {
-      }
+    gb.target += gridDim.x;
+    __threadfence();                                  // this CTA's writes (seen through the bar.sync) before the arrival
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(gb.ctr) : "memory");
+    while (ld_acquire_u32(gb.ctr) < gb.target) {
     }
-    __threadfence();
   }
-  consumers_sync();
+  cta_workers_sync();
 }
 
+// Fixed-size ring slots (the largest group of any phase: 2 rows x 22 KB for the down projection at 7B width; the
+// K = 4096 phases use 32 KB of each).  A byte-granular ring that packed six 32 KB slots into the same space was tried
+// and streamed no faster: what bounds the rate is not the bytes in flight but the work per slot on both sides — above
+// all the PRODUCER thread's own instruction path (one thread, ~1000 cycles per slot with the generic cursor logic),
+// which is why the per-slot bookkeeping below is a handful of adds.
 struct Ring {
   uint8_t* base;
   uint64_t *full_bar, *empty_bar;
   int stages;
   uint32_t slot_bytes;
+};
+struct RingPos {        // a role's position in the slot sequence: stage index and the parity of its current round
+  int s;
+  uint32_t par;
+  __device__ __forceinline__ void next(int stages) {
+    if (++s == stages) { s = 0; par ^= 1u; }
+  }
 };
 
 // the linear phases of a layer, in order: which weight, how many output rows, contraction length
@@ -119,7 +144,7 @@ __device__ __forceinline__ PhaseW phase_weights(const StackParams& p, int l, int
     default: return {p.wd[l], p.h, p.f};
   }
 }
-__device__ __forceinline__ int rows_per_slot(int K) { return K <= GV_CONSUMERS * 8 ? 4 : 2; }
+__device__ __forceinline__ int rows_per_slot(int K, int rpi_big) { return K <= GV_CONSUMERS * 8 ? 4 : rpi_big; }
 
 // group g of a phase goes to CTA (off + g) % grid, where off continues the round-robin of the previous phase: the CTAs
 // that get one group more than the others are different ones in every phase
@@ -129,32 +154,86 @@ struct Deal {
   __device__ __forceinline__ void next(int groups, int grid) { off = (off + groups) % grid; }
 };
 
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait_a(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+
 // ---------------------------------------------------------------------------------------------- producer
+// One thread.  Everything it does per slot is serial latency in front of the memory pipe, so the inner loop is: wait for
+// the stage to be free, arm its barrier, ONE bulk copy (the rows of a group are contiguous in global memory and, with an
+// unpadded row pitch, in the ring too), a few adds.
 __device__ void stack_producer(const StackParams& p, const Ring& r) {
-  int it = 0;
-  Deal deal{0};
   const int grid = gridDim.x, cta = blockIdx.x;
+  RingPos pos{0, 0u};
+  Deal deal{0};
+  long long wait_cycles = 0, slots = 0;
+  const long long t_begin = p.trace ? clock64() : 0;
   for (int l = 0; l < p.L; ++l) {
     for (int ph = 0; ph < 4; ++ph) {
       const PhaseW w = phase_weights(p, l, ph);
-      const int rpi = rows_per_slot(w.K);
+      const int rpi = rows_per_slot(w.K, p.rpi_big);
       const uint32_t row_bytes = uint32_t(w.K) * 2u, pitch = (row_bytes + 127u) & ~127u;
       const int groups = (w.N + rpi - 1) / rpi;
-      for (int g = deal.first(cta, grid); g < groups; g += grid, ++it) {
-        const int s = it % r.stages;
-        const uint32_t par = (it / r.stages) & 1;
-        mbar_wait(&r.empty_bar[s], par ^ 1);
-        const int n0 = g * rpi;
-        const int valid = w.N - n0 < rpi ? w.N - n0 : rpi;
-        mbar_arrive_expect_tx(&r.full_bar[s], row_bytes * valid);
-        for (int rr = 0; rr < valid; ++rr)
-          bulk_load_row(r.base + size_t(s) * r.slot_bytes + size_t(rr) * pitch, w.w + int64_t(n0 + rr) * w.K, row_bytes,
-                        &r.full_bar[s]);
+      const uint32_t group_bytes = row_bytes * uint32_t(rpi);
+      const int g0 = deal.first(cta, grid);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(w.w) + size_t(g0) * group_bytes;
+      const size_t stride = size_t(grid) * group_bytes;
+      const int full_groups = w.N / rpi;                   // groups with all rpi rows
+      for (int g = g0; g < groups; g += grid, src += stride) {
+        const uint32_t bar_e = smem_u32(&r.empty_bar[pos.s]), bar_f = smem_u32(&r.full_bar[pos.s]);
+        if (p.trace) {
+          const long long t0 = clock64();
+          mbar_wait_a(bar_e, pos.par ^ 1u);
+          wait_cycles += clock64() - t0;
+          ++slots;
+        } else {
+          mbar_wait_a(bar_e, pos.par ^ 1u);
+        }
+        uint8_t* dst = r.base + size_t(pos.s) * r.slot_bytes;
+        const uint32_t bytes = g < full_groups ? group_bytes : row_bytes * uint32_t(w.N - g * rpi);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_f), "r"(bytes) : "memory");
+        if (p.dbg & 32) {               // profiling: no memory traffic at all — how fast are the consumers on their own?
+          asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar_f), "r"(bytes) : "memory");
+        } else if (pitch == row_bytes) {
+          bulk_load_row(dst, src, bytes, &r.full_bar[pos.s]);
+        } else {
+          for (uint32_t o = 0, q = 0; o < bytes; o += row_bytes, q += pitch) bulk_load_row(dst + q, src + o, row_bytes, &r.full_bar[pos.s]);
+        }
+        pos.next(r.stages);
       }
       deal.next(groups, grid);
       if (ph == 0) {
-        // this layer's prefix K/V -> L2 while the QKV projection is still being consumed: the attention phase that
-        // follows then pays L2, not DRAM, latency.  Each CTA asks for its 1/grid of the cache in 16 KB pieces.
+        // the QKV weights of this layer are all requested: pull the layer's prefix K/V into L2, so the attention phase
+        // that follows pays L2, not DRAM, latency.  Each CTA asks for its 1/grid of the cache in 16 KB pieces.
         const size_t total = size_t(p.B) * 2 * p.H * p.P * p.D * 2;
         const size_t per = ((total + grid - 1) / grid + 15) & ~size_t(15);
         size_t beg = per * cta;
@@ -164,21 +243,79 @@ __device__ void stack_producer(const StackParams& p, const Ring& r) {
       }
     }
   }
+  if (p.trace) {          // behind the phase stamps: [grid][4] = producer wait / total cycles, slots, (consumer wait, written there)
+    long long* st = p.trace + size_t(gridDim.x) * p.L * 15 + size_t(blockIdx.x) * 4;
+    st[0] = wait_cycles;
+    st[1] = clock64() - t_begin;
+    st[2] = slots;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- linear phase (consumers)
-// out[m, n] = bf16( bf16(sum_k x'[m,k] w[n,k]) + res[m,n] ): the fast path of gemv_ring_kernel (XF = 1) with coherent
-// activation loads and the ring / deal state carried across phases.
+// out[m, n] = bf16( bf16(sum_k x'[m,k] w[n,k]) + res[m,n] ): the arithmetic of gemv_ring_kernel's fast path (XF = 1;
+// same thread -> k-chunk mapping, same reduction trees), with coherent activation loads and the ring / deal state
+// carried across phases.
+//
+// The 16 consumer warps are NOT synchronised per slot.  Each one takes its k-slice of the slot's rows, reduces its V
+// partial sums inside the warp, leaves them in shared memory and arrives on the slot's `part` mbarrier (arrive /
+// try_wait are release / acquire at CTA scope — no fence, no atomic counter).  A dedicated FINISHER warp waits for that
+// barrier, adds the 16 partials in warp order (so the result does not depend on timing), rounds, adds the residual,
+// stores, and hands the slot back to the producer.  Consumer warps drift apart by up to a ring's worth of slots, so one
+// slot's reduction latency overlaps the next slots' dot products.
+// Partials are indexed by slot mod 16 = 2 * ST_MAX_STAGES: the ring never holds more than ST_MAX_STAGES slots between
+// the finisher and the fastest consumer.
+struct LinArgs {          // by value: each instantiation is a real function with its own register allocation
+  uint32_t ring_base;     // shared-space byte address of the ring
+  uint32_t slot_bytes;
+  int stages;
+  uint32_t full_bar, empty_bar, part_bar;   // shared-space addresses of the barrier arrays
+  uint32_t partial;       // shared-space address: float [16 slots][16 warps][8]
+  float* red_ss;
+  const __nv_bfloat16 *x, *ln_w, *res;
+  __nv_bfloat16* out;
+  int64_t ldx, ldr, ldo;
+  int M, N, K;
+  float eps;
+  int dbg;
+  int deal_off;
+  RingPos pos;
+  int it;
+  long long* wait_acc;    // profiling: cycles thread 0 spent waiting for weights
+};
+// two fp32 FMAs per instruction (FFMA2, sm_100): the dot products are issue-bound on the CUDA cores
+__device__ __forceinline__ void ffma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long pack_f32x2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long bf16x2_to_f32x2(uint32_t v) {      // (lo, hi) bf16 -> (lo, hi) fp32
+  unsigned long long r;
+  asm("{\n\t.reg .b32 l, h;\n\tshl.b32 l, %1, 16;\n\tand.b32 h, %1, 0xffff0000;\n\tmov.b64 %0, {l, h};\n\t}" : "=l"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ float sum_f32x2(unsigned long long v) {
+  float lo, hi;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo + hi;
+}
+
+// MB activation rows (registers), CPT k-chunks (8 bf16) per thread, RPI weight rows per slot.
+struct LinRet {
+  RingPos pos;
+  int it;
+};
 template <int MB, int CPT, int RPI, int PRO>
-__device__ __forceinline__ void stack_linear(const Ring& r, int& it, int& pb, const Deal& deal, float* partial /*[2][16][8]*/,
-                                             float* red_ss /*[16][2]*/, const __nv_bfloat16* x, int64_t ldx,
-                                             const __nv_bfloat16* ln_w, const __nv_bfloat16* res, int64_t ldr,
-                                             __nv_bfloat16* out, int64_t ldo, int M, int N, int K, float eps) {
+__device__ __noinline__ LinRet stack_linear(const LinArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = a.M, N = a.N, K = a.K;
   const int chunks = K >> 3;
   const uint32_t pitch = (uint32_t(K) * 2u + 127u) & ~127u;
   const int groups = (N + RPI - 1) / RPI;
-  float xf[MB][CPT][8];
+  // activations of this thread's k-chunks as fp32 pairs (element 2i, 2i+1): thread t always meets the same chunks
+  unsigned long long xp[MB][CPT][4];
   {
     uint4 xr[MB][CPT];
     float ss[MB];
@@ -193,13 +330,13 @@ __device__ __forceinline__ void stack_linear(const Ring& r, int& it, int& pb, co
         if (m < M && c < chunks) {
           if (PRO == GV_PRO_SWIGLU) {
             float g[8], u[8], o[8];
-            unpack8(ld_cg16(x + int64_t(m) * ldx + 8 * c), g);
-            unpack8(ld_cg16(x + int64_t(m) * ldx + K + 8 * c), u);
+            unpack8(ld_cg16(a.x + int64_t(m) * a.ldx + 8 * c), g);
+            unpack8(ld_cg16(a.x + int64_t(m) * a.ldx + K + 8 * c), u);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = bf16_round(g[e] * (1.f / (1.f + __expf(-g[e])))) * u[e];
             v = pack8f(o);
           } else {
-            v = ld_cg16(x + int64_t(m) * ldx + 8 * c);
+            v = ld_cg16(a.x + int64_t(m) * a.ldx + 8 * c);
             if (PRO == GV_PRO_RMSNORM) {
               float f[8];
               unpack8(v, f);
@@ -215,107 +352,171 @@ __device__ __forceinline__ void stack_linear(const Ring& r, int& it, int& pb, co
 #pragma unroll
       for (int m = 0; m < MB; ++m) {
         const float t = d_wsum(ss[m]);
-        if (lane == 0) red_ss[warp * 2 + m] = t;
+        if (lane == 0) a.red_ss[warp * 2 + m] = t;
       }
       consumers_sync();
 #pragma unroll
       for (int m = 0; m < MB; ++m) {
         float t = 0.f;
 #pragma unroll
-        for (int w2 = 0; w2 < GV_CWARPS; ++w2) t += red_ss[w2 * 2 + m];
-        const float rstd = rsqrtf(t / float(K) + eps);
+        for (int w2 = 0; w2 < GV_CWARPS; ++w2) t += a.red_ss[w2 * 2 + m];
+        const float rstd = rsqrtf(t / float(K) + a.eps);
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
           const int c = tid + j * GV_CONSUMERS;
           if (c < chunks) {
             float f[8], g[8], o[8];
             unpack8(xr[m][j], f);
-            unpack8(__ldg(reinterpret_cast<const uint4*>(ln_w + 8 * c)), g);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(a.ln_w + 8 * c)), g);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = g[e] * bf16_round(f[e] * rstd);
             xr[m][j] = pack8f(o);
           }
         }
       }
+      consumers_sync();                 // red_ss is re-used by the next RMSNorm phase
     }
 #pragma unroll
     for (int m = 0; m < MB; ++m)
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) unpack8(xr[m][j], xf[m][j]);
+      for (int j = 0; j < CPT; ++j) {
+        xp[m][j][0] = bf16x2_to_f32x2(xr[m][j].x);
+        xp[m][j][1] = bf16x2_to_f32x2(xr[m][j].y);
+        xp[m][j][2] = bf16x2_to_f32x2(xr[m][j].z);
+        xp[m][j][3] = bf16x2_to_f32x2(xr[m][j].w);
+        // opaque: keep the fp32 pairs in registers instead of re-deriving them from the packed bf16 in every slot
+        asm volatile("" : "+l"(xp[m][j][0]), "+l"(xp[m][j][1]), "+l"(xp[m][j][2]), "+l"(xp[m][j][3]));
+      }
   }
 
   constexpr int V = RPI * MB;
-  for (int g = deal.first(blockIdx.x, gridDim.x); g < groups; g += gridDim.x, ++it) {
-    const int s = it % r.stages;
-    const uint32_t par = (it / r.stages) & 1;
-    mbar_wait(&r.full_bar[s], par);
-    const uint8_t* slot = r.base + size_t(s) * r.slot_bytes;
-    const int n0 = g * RPI;
-    float acc[RPI][MB];
+  constexpr int LPV = 32 / V;
+  constexpr int NBUF = 2 * ST_MAX_STAGES;
+  const uint32_t lane_off = 16u * uint32_t(tid);
+  RingPos pos = a.pos;
+  int it = a.it;                        // slots so far: picks the finisher warp and the partial buffer
+  int g = int(blockIdx.x) - a.deal_off;
+  if (g < 0) g += gridDim.x;
+  for (; g < groups; g += gridDim.x, ++it, pos.next(a.stages)) {
+    const int s = pos.s;
+    const uint32_t par = pos.par;
+    {
+      const long long t0 = (a.wait_acc && tid == 0) ? clock64() : 0;
+      mbar_wait_a(a.full_bar + 8u * s, par);
+      if (a.wait_acc && tid == 0) *a.wait_acc += clock64() - t0;
+    }
+    const uint32_t part = a.partial + uint32_t(it % NBUF) * (GV_CWARPS * 8 * 4);
+    if (!(a.dbg & 1)) {
+      const uint32_t slot = a.ring_base + uint32_t(s) * a.slot_bytes + lane_off;
+      unsigned long long acc[RPI][MB];          // (sum over even elements, sum over odd elements)
 #pragma unroll
-    for (int rr = 0; rr < RPI; ++rr)
+      for (int rr = 0; rr < RPI; ++rr)
 #pragma unroll
-      for (int m = 0; m < MB; ++m) acc[rr][m] = 0.f;
+        for (int m = 0; m < MB; ++m) acc[rr][m] = 0ull;
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      const int c = tid + j * GV_CONSUMERS;
-      if (c < chunks) {
+      for (int j = 0; j < CPT; ++j) {
+        if (tid + j * GV_CONSUMERS < chunks) {
+          uint4 wv[RPI];
 #pragma unroll
-        for (int rr = 0; rr < RPI; ++rr) {
-          const uint4 wv = *reinterpret_cast<const uint4*>(slot + size_t(rr) * pitch + 16 * c);
-          float wf[8];
-          unpack8(wv, wf);
+          for (int rr = 0; rr < RPI; ++rr) wv[rr] = lds128(slot + uint32_t(rr) * pitch + uint32_t(j) * (16u * GV_CONSUMERS));
 #pragma unroll
-          for (int m = 0; m < MB; ++m)
+          for (int rr = 0; rr < RPI; ++rr) {
+            const unsigned long long w0 = bf16x2_to_f32x2(wv[rr].x), w1 = bf16x2_to_f32x2(wv[rr].y),
+                                     w2 = bf16x2_to_f32x2(wv[rr].z), w3 = bf16x2_to_f32x2(wv[rr].w);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[rr][m] = fmaf(wf[e], xf[m][j][e], acc[rr][m]);
+            for (int m = 0; m < MB; ++m) {
+              ffma2(acc[rr][m], w0, xp[m][j][0]);
+              ffma2(acc[rr][m], w1, xp[m][j][1]);
+              ffma2(acc[rr][m], w2, xp[m][j][2]);
+              ffma2(acc[rr][m], w3, xp[m][j][3]);
+            }
+          }
         }
       }
+      float flat[V];
+#pragma unroll
+      for (int rr = 0; rr < RPI; ++rr)
+#pragma unroll
+        for (int m = 0; m < MB; ++m) flat[rr * MB + m] = sum_f32x2(acc[rr][m]);
+      warp_reduce_many<V>(flat, lane);
+      if (lane % LPV == 0) sts32(part + uint32_t(warp * V + lane / LPV) * 4u, flat[0]);
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&r.empty_bar[s]);      // this warp no longer reads the slot
-    float flat[V];
-#pragma unroll
-    for (int rr = 0; rr < RPI; ++rr)
-#pragma unroll
-      for (int m = 0; m < MB; ++m) flat[rr * MB + m] = acc[rr][m];
-    warp_reduce_many<V>(flat, lane);
-    constexpr int LPV = 32 / V;
-    float* part = partial + pb * (GV_CWARPS * 8);
-    if (lane % LPV == 0) part[warp * V + lane / LPV] = flat[0];
-    consumers_sync();
-    if (tid < V) {
-      const int rr = tid / MB, m = tid % MB;
-      const int n = n0 + rr;
-      if (n < N && m < M) {
-        float t = 0.f;
-#pragma unroll
-        for (int w2 = 0; w2 < GV_CWARPS; ++w2) t += part[w2 * V + tid];
-        float v = bf16_round(t);
-        if (res) v += ld_cg_bf16(res + int64_t(m) * ldr + n);
-        out[int64_t(m) * ldo + n] = __float2bfloat16_rn(v);
-      }
-    }
-    pb ^= 1;
+    if (lane == 0) mbar_arrive_a(a.part_bar + 8u * s);        // this warp is done with the slot and its partials are published
   }
+  LinRet ret{pos, it};
+  return ret;
+}
+
+// The finisher warp's side of a linear phase: for every slot, once the 16 consumer warps have published their partial
+// sums (part_bar), add them in warp order, round, add the residual (requested while waiting), store, and only then hand
+// the slot back to the producer (empty_bar, one arrival).  The consumer warps therefore never wait for each other: with
+// a consumer warp doing this job in turn (first decoupled version) every slot's last step sat on the critical path of
+// the next slot, and the consumers ran at 2000 cycles per slot with an IPC of 0.3.
+template <int MB, int RPI>
+__device__ __forceinline__ LinRet stack_finish(const LinArgs& a) {
+  const int lane = threadIdx.x & 31;
+  const int M = a.M, N = a.N;
+  const int groups = (N + RPI - 1) / RPI;
+  constexpr int V = RPI * MB;
+  constexpr int NBUF = 2 * ST_MAX_STAGES;
+  RingPos pos = a.pos;
+  int it = a.it;
+  int g = int(blockIdx.x) - a.deal_off;
+  if (g < 0) g += gridDim.x;
+  const int rr = lane / MB, m = lane % MB;
+  for (; g < groups; g += gridDim.x, ++it, pos.next(a.stages)) {
+    const int n = g * RPI + rr;
+    const bool live = lane < V && n < N && m < M;
+    float resv = 0.f;
+    if (live && a.res) resv = ld_cg_bf16(a.res + int64_t(m) * a.ldr + n);
+    mbar_wait_a(a.part_bar + 8u * pos.s, pos.par);
+    if (live && !(a.dbg & 1)) {
+      const uint32_t part = a.partial + uint32_t(it % NBUF) * (GV_CWARPS * 8 * 4);
+      float t = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < GV_CWARPS; ++w2) t += lds32(part + uint32_t(w2 * V + lane) * 4u);
+      float v = bf16_round(t);
+      if (a.res) v += resv;
+      a.out[int64_t(m) * a.ldo + n] = __float2bfloat16_rn(v);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_a(a.empty_bar + 8u * pos.s);
+  }
+  LinRet ret{pos, it};
+  return ret;
+}
+template <int MB>
+__device__ __forceinline__ LinRet stack_finish_k(const LinArgs& a, int rpi_big) {
+  if (a.K <= GV_CONSUMERS * 8) return stack_finish<MB, 4>(a);
+  if (rpi_big == 2) return stack_finish<MB, 2>(a);
+  return stack_finish<MB, 1>(a);
 }
 
 // ---------------------------------------------------------------------------------------------- attention phase
-// decode_attn_kernel<EPL, ROPE = 1> with split-K, every item (b, h, split) serving all n <= NQ query rows of the sample
-// from ONE load of the keys / values.  Per query the arithmetic is that kernel's: warp w takes keys jbeg + w + 16 u in
-// order, the 16 warps are merged in order, the splits are merged in order by the last CTA to arrive.
+// decode_attn_kernel<EPL, ROPE = 1> (un-split), one CTA per (sample, head) serving all n <= NQ query rows from ONE load
+// of the keys / values.  Per query the arithmetic is that kernel's: warp w folds keys w, w + 16, ... in ascending order
+// into its online softmax, the 16 warps are merged in order.  No partials in global memory, no atomics: the phase is
+// five L2 round trips (the producer pulled this layer's K/V into L2 during the QKV phase) plus a shared-memory merge,
+// while the other CTAs' rings fill with the output projection's weights.
+struct AttnArgsDev {      // by value: a reference to the kernel parameters would force a local-memory copy of them
+  const __nv_bfloat16 *qkv, *cos, *sin;
+  __nv_bfloat16* ctx;
+  int B, n, P, H;
+  float scale;
+};
 template <int EPL, int NQ>
-__device__ __forceinline__ void stack_attention(const StackParams& p, const __nv_bfloat16* cache, float* s_m /*[NQ][16]*/,
-                                                float* s_l, float* s_acc /*[NQ][16][D]*/, int* s_last) {
+__device__ __noinline__ void stack_attention(const AttnArgsDev p, const __nv_bfloat16* cache, float* s_m /*[NQ][16]*/,
+                                             float* s_l, float* s_acc /*[NQ][16][D]*/) {
   constexpr int D = 32 * EPL;
+  constexpr int UN = ST_ATTN_UN;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = p.n, P = p.P, H = p.H, hdim = H * D;
   const int Lk = P + n;
-  const int S = (Lk + ST_SPLIT_KEYS - 1) / ST_SPLIT_KEYS;
-  const int items = p.B * H * S;
+  const int items = p.B * H;
   const int64_t ldq = 3 * int64_t(hdim);
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    const int sp = item % S, h = (item / S) % H, b = item / (S * H);
+    const int h = item % H, b = item / H;
     float qf[NQ][EPL], acc[NQ][EPL], m[NQ], l[NQ];
 #pragma unroll
     for (int i = 0; i < NQ; ++i) {
@@ -332,57 +533,57 @@ __device__ __forceinline__ void stack_attention(const StackParams& p, const __nv
     }
     const __nv_bfloat16* kc = cache + (int64_t(b) * 2 * H + h) * int64_t(P) * D + lane * EPL;
     const __nv_bfloat16* vc = kc + int64_t(H) * P * D;
-    const int jbeg = sp * ST_SPLIT_KEYS;
-    const int jend = Lk < jbeg + ST_SPLIT_KEYS ? Lk : jbeg + ST_SPLIT_KEYS;     // keys any query of the sample may see
-    RawEpl<EPL> kr[ST_ATTN_UN], vr[ST_ATTN_UN];
+    for (int j0 = warp; j0 < Lk; j0 += DEC_WARPS * UN) {
+      RawEpl<EPL> kr[UN], vr[UN];
 #pragma unroll
-    for (int u = 0; u < ST_ATTN_UN; ++u) {
-      const int j = jbeg + warp + u * DEC_WARPS;
+      for (int u = 0; u < UN; ++u) {
+        const int j = j0 + u * DEC_WARPS;
 #pragma unroll
-      for (int w2 = 0; w2 < (EPL + 1) / 2; ++w2) { kr[u].w[w2] = 0u; vr[u].w[w2] = 0u; }
-      if (j < jend) {
-        if (j >= P) {
-          const __nv_bfloat16* row = p.qkv + (int64_t(b) * n + (j - P)) * ldq + int64_t(h) * D + lane * EPL;
-          kr[u] = ld_raw_cg<EPL>(row + hdim);
-          vr[u] = ld_raw_cg<EPL>(row + 2 * hdim);
-        } else {
-          kr[u] = ld_raw<EPL>(kc + int64_t(j) * D);
-          vr[u] = ld_raw<EPL>(vc + int64_t(j) * D);
+        for (int w2 = 0; w2 < (EPL + 1) / 2; ++w2) { kr[u].w[w2] = 0u; vr[u].w[w2] = 0u; }
+        if (j < Lk) {
+          if (j >= P) {
+            const __nv_bfloat16* row = p.qkv + (int64_t(b) * n + (j - P)) * ldq + int64_t(h) * D + lane * EPL;
+            kr[u] = ld_raw_cg<EPL>(row + hdim);
+            vr[u] = ld_raw_cg<EPL>(row + 2 * hdim);
+          } else {
+            kr[u] = ld_raw<EPL>(kc + int64_t(j) * D);
+            vr[u] = ld_raw<EPL>(vc + int64_t(j) * D);
+          }
         }
       }
-    }
-    float s[NQ][ST_ATTN_UN];
+      float s[NQ][UN];
 #pragma unroll
-    for (int u = 0; u < ST_ATTN_UN; ++u) {
-      const int j = jbeg + warp + u * DEC_WARPS;
-      float kf[EPL];
-      cvt_raw<EPL>(kr[u], kf);
-      if (j >= P && j < jend) rope_lanes<EPL>(kf, p.cos + int64_t(j - P) * (D / 2), p.sin + int64_t(j - P) * (D / 2), lane);
+      for (int u = 0; u < UN; ++u) {
+        const int j = j0 + u * DEC_WARPS;
+        float kf[EPL];
+        cvt_raw<EPL>(kr[u], kf);
+        if (j >= P && j < Lk) rope_lanes<EPL>(kf, p.cos + int64_t(j - P) * (D / 2), p.sin + int64_t(j - P) * (D / 2), lane);
 #pragma unroll
-      for (int i = 0; i < NQ; ++i) {
-        s[i][u] = 0.f;
+        for (int i = 0; i < NQ; ++i) {
+          s[i][u] = 0.f;
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) s[i][u] = fmaf(qf[i][e], kf[e], s[i][u]);
+          for (int e = 0; e < EPL; ++e) s[i][u] = fmaf(qf[i][e], kf[e], s[i][u]);
+        }
       }
-    }
 #pragma unroll
-    for (int i = 0; i < NQ; ++i)
+      for (int i = 0; i < NQ; ++i)
 #pragma unroll
-      for (int u = 0; u < ST_ATTN_UN; ++u) s[i][u] = d_wsum(s[i][u]);
+        for (int u = 0; u < UN; ++u) s[i][u] = d_wsum(s[i][u]);
 #pragma unroll
-    for (int u = 0; u < ST_ATTN_UN; ++u) {
-      const int j = jbeg + warp + u * DEC_WARPS;
-      float vf[EPL];
-      cvt_raw<EPL>(vr[u], vf);
+      for (int u = 0; u < UN; ++u) {
+        const int j = j0 + u * DEC_WARPS;
+        float vf[EPL];
+        cvt_raw<EPL>(vr[u], vf);
 #pragma unroll
-      for (int i = 0; i < NQ; ++i) {
-        if (i < n && j < jend && j <= P + i) {          // query i sees keys j <= P + i
-          const float mn = fmaxf(m[i], s[i][u]);
-          const float corr = __expf(m[i] - mn), pj = __expf(s[i][u] - mn);
-          l[i] = l[i] * corr + pj;
+        for (int i = 0; i < NQ; ++i) {
+          if (i < n && j <= P + i) {                    // query i sees keys j <= P + i (< Lk)
+            const float mn = fmaxf(m[i], s[i][u]);
+            const float corr = __expf(m[i] - mn), pj = __expf(s[i][u] - mn);
+            l[i] = l[i] * corr + pj;
 #pragma unroll
-          for (int e = 0; e < EPL; ++e) acc[i][e] = acc[i][e] * corr + pj * vf[e];
-          m[i] = mn;
+            for (int e = 0; e < EPL; ++e) acc[i][e] = acc[i][e] * corr + pj * vf[e];
+            m[i] = mn;
+          }
         }
       }
     }
@@ -406,65 +607,35 @@ __device__ __forceinline__ void stack_attention(const StackParams& p, const __nv
         Ls += s_l[i * DEC_WARPS + w2] * c;
         a += s_acc[(i * DEC_WARPS + w2) * D + d] * c;
       }
-      const int64_t unit = (int64_t(b) * H + h) * n + i;
-      float* part = p.attn_ws + (unit * S + sp) * (D + 2);
-      part[2 + d] = a;
-      if (d == 0) { part[0] = mx; part[1] = Ls; }
+      p.ctx[(int64_t(b) * n + i) * hdim + int64_t(h) * D + d] = __float2bfloat16_rn(Ls > 0.f ? a / Ls : 0.f);
     }
-    __threadfence();                       // this CTA's partials are visible before its arrival is counted
-    consumers_sync();
-    if (tid == 0) *s_last = atomicAdd(p.attn_cnt + (b * H + h), 1) == S - 1;
-    consumers_sync();
-    if (*s_last) {
-      __threadfence();
-      for (int t = tid; t < n * D; t += GV_CONSUMERS) {
-        const int i = t / D, d = t % D;
-        const int64_t unit = (int64_t(b) * H + h) * n + i;
-        const float* all = p.attn_ws + unit * S * (D + 2);
-        float mx = -INFINITY;
-        for (int s2 = 0; s2 < S; ++s2) mx = fmaxf(mx, __ldcg(all + s2 * (D + 2)));
-        float Ls = 0.f, a = 0.f;
-        for (int s2 = 0; s2 < S; ++s2) {
-          const float ms = __ldcg(all + s2 * (D + 2));
-          const float c = ms == -INFINITY ? 0.f : __expf(ms - mx);
-          Ls += __ldcg(all + s2 * (D + 2) + 1) * c;
-          a += __ldcg(all + s2 * (D + 2) + 2 + d) * c;
-        }
-        p.ctx[(int64_t(b) * n + i) * hdim + int64_t(h) * D + d] = __float2bfloat16_rn(Ls > 0.f ? a / Ls : 0.f);
-      }
-      if (tid == 0) p.attn_cnt[b * H + h] = 0;       // re-armed for the next layer / launch
-    }
-    consumers_sync();                      // s_m / s_l / s_acc / s_last are re-used by the next item
+    consumers_sync();                      // s_m / s_l / s_acc are re-used by the next item
   }
 }
 
 template <int MB, int PRO>
-__device__ __forceinline__ void stack_linear_k(const Ring& r, int& it, int& pb, const Deal& deal, float* partial,
-                                               float* red_ss, const __nv_bfloat16* x, int64_t ldx,
-                                               const __nv_bfloat16* ln_w, const __nv_bfloat16* res, int64_t ldr,
-                                               __nv_bfloat16* out, int64_t ldo, int M, int N, int K, float eps) {
-  if (K <= GV_CONSUMERS * 8)
-    stack_linear<MB, 1, 4, PRO>(r, it, pb, deal, partial, red_ss, x, ldx, ln_w, res, ldr, out, ldo, M, N, K, eps);
-  else
-    stack_linear<MB, 3, 2, PRO>(r, it, pb, deal, partial, red_ss, x, ldx, ln_w, res, ldr, out, ldo, M, N, K, eps);
+__device__ __forceinline__ LinRet stack_linear_k(const LinArgs& a, int rpi_big) {
+  if (a.K <= GV_CONSUMERS * 8) return stack_linear<MB, 1, 4, PRO>(a);
+  if (rpi_big == 2) return stack_linear<MB, 3, 2, PRO>(a);
+  return stack_linear<MB, 3, 1, PRO>(a);
 }
 
 template <int MB>
-__global__ void __launch_bounds__(GV_THREADS, 1) decode_stack_kernel(const StackParams p) {
+__global__ void __launch_bounds__(ST_THREADS, 1) decode_stack_kernel(const StackParams p) {
   extern __shared__ uint8_t st_smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(st_smem_raw) + 127) & ~uintptr_t(127));
-  __shared__ uint64_t full_bar[ST_MAX_STAGES], empty_bar[ST_MAX_STAGES];
-  __shared__ float partial[2 * GV_CWARPS * 8];
+  __shared__ uint64_t full_bar[ST_MAX_STAGES], empty_bar[ST_MAX_STAGES], part_bar[ST_MAX_STAGES];
+  __shared__ float partial[2 * ST_MAX_STAGES * GV_CWARPS * 8];
   __shared__ float red_ss[GV_CWARPS * 2];
   __shared__ float s_m[MB * DEC_WARPS], s_l[MB * DEC_WARPS];
-  __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5;
   // attention merge buffer [MB][16][D] fp32: behind the ring
   float* s_acc = reinterpret_cast<float*>(ring + size_t(p.stages) * p.slot_bytes);
   if (tid == 0) {
-    for (int s = 0; s < p.stages; ++s) {
+    for (int s = 0; s < ST_MAX_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], GV_CWARPS);
+      mbar_init(&empty_bar[s], 1);              // the finisher warp hands a slot back
+      mbar_init(&part_bar[s], GV_CWARPS);       // the 16 consumer warps have published their partial sums
     }
     fence_barrier_init();
   }
@@ -475,36 +646,98 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_stack_kernel(const Stack
     return;
   }
   const int M = p.B * p.n, h = p.h, f = p.f, grid = gridDim.x;
-  int it = 0, pb = 0;
   Deal deal{0};
+  GridBar gb{p.bar, 0u};
+  if (warp == GV_CWARPS + 1) {
+    // ---- finisher warp: the same walk over layers and phases as the consumers, one final sum per slot
+    LinArgs fa;
+    fa.empty_bar = smem_u32(empty_bar); fa.part_bar = smem_u32(part_bar); fa.partial = smem_u32(partial);
+    fa.stages = p.stages; fa.M = M; fa.dbg = p.dbg; fa.ldr = h;
+    fa.pos = RingPos{0, 0u};
+    fa.it = 0;
+    auto finish = [&](const __nv_bfloat16* res, __nv_bfloat16* out, int64_t ldo, int N, int K) {
+      fa.res = res; fa.out = out; fa.ldo = ldo; fa.N = N; fa.K = K; fa.deal_off = deal.off;
+      const LinRet lr = stack_finish_k<MB>(fa, p.rpi_big);
+      fa.pos = lr.pos;
+      fa.it = lr.it;
+      const int rpi = rows_per_slot(K, p.rpi_big);
+      deal.next((N + rpi - 1) / rpi, grid);
+      grid_barrier(gb, tid, p.dbg);             // tid != 0: only the two CTA-level syncs
+    };
+    for (int l = 0; l < p.L; ++l) {
+      finish(nullptr, p.qkv, 3 * int64_t(h), 3 * h, h);
+      grid_barrier(gb, tid, p.dbg);             // attention phase
+      finish(p.x, p.xmid, h, h, h);
+      finish(nullptr, p.gu, 2 * int64_t(f), 2 * f, h);
+      finish(p.xmid, p.x, h, h, f);
+    }
+    return;
+  }
+  const AttnArgsDev aa{p.qkv, p.cos, p.sin, p.ctx, p.B, p.n, p.P, p.H, p.scale};
+  LinArgs la;
+  la.ring_base = smem_u32(ring); la.slot_bytes = p.slot_bytes; la.stages = p.stages;
+  la.full_bar = smem_u32(full_bar); la.empty_bar = smem_u32(empty_bar); la.part_bar = smem_u32(part_bar);
+  la.partial = smem_u32(partial); la.red_ss = red_ss;
+  la.M = M; la.eps = p.eps; la.dbg = p.dbg;
+  la.pos = RingPos{0, 0u};
+  la.it = 0;
+  la.wait_acc = p.trace ? p.trace + size_t(gridDim.x) * p.L * 15 + size_t(blockIdx.x) * 4 + 3 : nullptr;
+  if (p.trace && tid == 0) *la.wait_acc = 0;
+  if (tid == 0) {
+    const unsigned sel = ld_acquire_u32(p.bar + 2) & 1u;
+    gb.ctr = p.bar + sel;
+    if (blockIdx.x == 0) p.bar[sel ^ 1u] = 0u;          // the counter the NEXT launch will use
+  }
+  long long* tr = (p.trace && tid == 0) ? p.trace + size_t(blockIdx.x) * p.L * 15 : nullptr;
+#define ST_TRACE(ph, k) do { if (tr) tr[(l * 5 + (ph)) * 3 + (k)] = global_ns(); } while (0)
+  auto linear = [&](auto pro, const __nv_bfloat16* x, int64_t ldx, const __nv_bfloat16* ln_w, const __nv_bfloat16* res,
+                    __nv_bfloat16* out, int64_t ldo, int N, int K) {
+    la.x = x; la.ldx = ldx; la.ln_w = ln_w; la.res = res; la.ldr = h; la.out = out; la.ldo = ldo; la.N = N; la.K = K;
+    la.deal_off = deal.off;
+    const LinRet lr = stack_linear_k<MB, decltype(pro)::value>(la, p.rpi_big);
+    la.pos = lr.pos;
+    la.it = lr.it;
+    const int rpi = rows_per_slot(K, p.rpi_big);
+    deal.next((N + rpi - 1) / rpi, grid);
+  };
   for (int l = 0; l < p.L; ++l) {
     // RMSNorm + QKV projection
-    stack_linear_k<MB, GV_PRO_RMSNORM>(r, it, pb, deal, partial, red_ss, p.x, h, p.ln1[l], nullptr, 0, p.qkv, 3 * int64_t(h),
-                                       M, 3 * h, h, p.eps);
-    deal.next((3 * h + rows_per_slot(h) - 1) / rows_per_slot(h), grid);
-    grid_barrier(p.bar, tid);
+    ST_TRACE(0, 0);
+    linear(std::integral_constant<int, GV_PRO_RMSNORM>{}, p.x, h, p.ln1[l], nullptr, p.qkv, 3 * int64_t(h), 3 * h, h);
+    ST_TRACE(0, 1);
+    grid_barrier(gb, tid, p.dbg);
+    if (l == 0 && tid == 0 && blockIdx.x == 0) p.bar[2] = unsigned(gb.ctr - p.bar) ^ 1u;   // every CTA has read it by now
+    ST_TRACE(0, 2);
     // attention (RoPE of q and of the new keys on the fly)
-    switch (p.D) {
-      case 32: stack_attention<1, MB>(p, p.cache[l], s_m, s_l, s_acc, &s_last); break;
-      case 64: stack_attention<2, MB>(p, p.cache[l], s_m, s_l, s_acc, &s_last); break;
-      default: stack_attention<4, MB>(p, p.cache[l], s_m, s_l, s_acc, &s_last); break;
+    ST_TRACE(1, 0);
+    if (!(p.dbg & 4)) switch (p.D) {
+      case 32: stack_attention<1, MB>(aa, p.cache[l], s_m, s_l, s_acc); break;
+      case 64: stack_attention<2, MB>(aa, p.cache[l], s_m, s_l, s_acc); break;
+      default: stack_attention<4, MB>(aa, p.cache[l], s_m, s_l, s_acc); break;
     }
-    grid_barrier(p.bar, tid);
+    ST_TRACE(1, 1);
+    grid_barrier(gb, tid, p.dbg);
+    ST_TRACE(1, 2);
     // output projection + residual
-    stack_linear_k<MB, GV_PRO_NONE>(r, it, pb, deal, partial, red_ss, p.ctx, h, nullptr, p.x, h, p.xmid, h, M, h, h, p.eps);
-    deal.next((h + rows_per_slot(h) - 1) / rows_per_slot(h), grid);
-    grid_barrier(p.bar, tid);
+    ST_TRACE(2, 0);
+    linear(std::integral_constant<int, GV_PRO_NONE>{}, p.ctx, h, nullptr, p.x, p.xmid, h, h, h);
+    ST_TRACE(2, 1);
+    grid_barrier(gb, tid, p.dbg);
+    ST_TRACE(2, 2);
     // RMSNorm + gate | up projection
-    stack_linear_k<MB, GV_PRO_RMSNORM>(r, it, pb, deal, partial, red_ss, p.xmid, h, p.ln2[l], nullptr, 0, p.gu, 2 * int64_t(f),
-                                       M, 2 * f, h, p.eps);
-    deal.next((2 * f + rows_per_slot(h) - 1) / rows_per_slot(h), grid);
-    grid_barrier(p.bar, tid);
+    ST_TRACE(3, 0);
+    linear(std::integral_constant<int, GV_PRO_RMSNORM>{}, p.xmid, h, p.ln2[l], nullptr, p.gu, 2 * int64_t(f), 2 * f, h);
+    ST_TRACE(3, 1);
+    grid_barrier(gb, tid, p.dbg);
+    ST_TRACE(3, 2);
     // SwiGLU + down projection + residual -> the next layer's input, in place
-    stack_linear_k<MB, GV_PRO_SWIGLU>(r, it, pb, deal, partial, red_ss, p.gu, 2 * int64_t(f), nullptr, p.xmid, h, p.x, h, M, h,
-                                      f, p.eps);
-    deal.next((h + rows_per_slot(f) - 1) / rows_per_slot(f), grid);
-    grid_barrier(p.bar, tid);
+    ST_TRACE(4, 0);
+    linear(std::integral_constant<int, GV_PRO_SWIGLU>{}, p.gu, 2 * int64_t(f), nullptr, p.xmid, p.x, h, h, f);
+    ST_TRACE(4, 1);
+    grid_barrier(gb, tid, p.dbg);
+    ST_TRACE(4, 2);
   }
+#undef ST_TRACE
 }
 
 }  // namespace mla
@@ -512,12 +745,29 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_stack_kernel(const Stack
 using namespace mla;
 
 static int g_stack_coop = -1;
+static int g_stack_dbg = 0;
+static int g_stack_rpi_big = 2;
+extern "C" int mla_decode_stack_set_rows_per_slot_big(int32_t rows) {
+  g_stack_rpi_big = rows == 1 ? 1 : 2;
+  return MLA_OK;
+}
+static int g_stack_ring_kb = 0;
+extern "C" int mla_decode_stack_set_ring_kb(int32_t kb) {
+  g_stack_ring_kb = kb;
+  return MLA_OK;
+}
+static int g_stack_ahead = -1;
+extern "C" int mla_decode_stack_set_ahead(int32_t groups) {
+  g_stack_ahead = groups < 0 ? 0 : groups;
+  return MLA_OK;
+}
+extern "C" int mla_decode_stack_set_debug(int32_t flags) {
+  g_stack_dbg = flags;
+  return MLA_OK;
+}
 
-extern "C" size_t mla_decode_stack_workspace(int32_t batch, int32_t n, int32_t prefix, int32_t heads, int32_t head_dim) {
-  // split-K partials | arrival counters | grid barrier (the last two must be zero before the FIRST launch only)
-  const size_t splits = size_t((prefix + n + ST_SPLIT_KEYS - 1) / ST_SPLIT_KEYS);
-  const size_t ws = size_t(batch) * heads * n * splits * (head_dim + 2) * sizeof(float);
-  return ((ws + 255) & ~size_t(255)) + ((size_t(batch) * heads * sizeof(int) + 255) & ~size_t(255)) + 256;
+extern "C" size_t mla_decode_stack_workspace(int32_t, int32_t, int32_t, int32_t, int32_t) {
+  return 256;       // the grid barrier's words; must be zero before the FIRST launch only
 }
 
 extern "C" int mla_decode_stack(const mla_decode_stack_args* a, void* stream) {
@@ -543,19 +793,23 @@ extern "C" int mla_decode_stack(const mla_decode_stack_args* a, void* stream) {
   p.cos = (const __nv_bfloat16*)a->cos_t; p.sin = (const __nv_bfloat16*)a->sin_t;
   p.L = a->layers; p.B = a->batch; p.n = a->n; p.P = a->prefix; p.H = a->heads; p.D = a->head_dim; p.h = h; p.f = a->ffn;
   p.eps = a->eps; p.scale = a->scale;
-  const size_t splits = size_t((a->prefix + a->n + ST_SPLIT_KEYS - 1) / ST_SPLIT_KEYS);
-  const size_t ws = (size_t(a->batch) * a->heads * a->n * splits * (a->head_dim + 2) * sizeof(float) + 255) & ~size_t(255);
-  const size_t cnt = (size_t(a->batch) * a->heads * sizeof(int) + 255) & ~size_t(255);
-  p.attn_ws = (float*)a->workspace;
-  p.attn_cnt = (int*)((uint8_t*)a->workspace + ws);
-  p.bar = (unsigned*)((uint8_t*)a->workspace + ws + cnt);
+  p.bar = (unsigned*)a->workspace;
+  p.trace = (long long*)a->trace;
+  p.dbg = g_stack_dbg;
+  if (g_stack_ahead < 0) {
+    const char* e = getenv("MLA_DECODE_STACK_AHEAD");
+    g_stack_ahead = e ? atoi(e) : 0;
+  }
+  p.ahead = g_stack_ahead;
+  p.rpi_big = g_stack_rpi_big;
   auto pitch_of = [](int K) { return (size_t(K) * 2 + 127) & ~size_t(127); };
-  auto rpi_of = [](int K) { return K <= GV_CONSUMERS * 8 ? 4 : 2; };
+  auto rpi_of = [](int K) { return K <= GV_CONSUMERS * 8 ? 4 : g_stack_rpi_big; };
   size_t slot = pitch_of(h) * rpi_of(h);
   if (pitch_of(a->ffn) * rpi_of(a->ffn) > slot) slot = pitch_of(a->ffn) * rpi_of(a->ffn);
   const size_t attn_smem = size_t(M <= 1 ? 1 : 2) * DEC_WARPS * a->head_dim * sizeof(float);
-  const size_t budget = 227 * 1024 - 4096 - attn_smem - 128;       // static shared memory + alignment slack
-  int stages = int(budget / slot);
+  size_t ring_bytes = 227 * 1024 - 10240 - attn_smem - 128;          // minus static shared memory + alignment slack
+  if (g_stack_ring_kb > 0 && size_t(g_stack_ring_kb) * 1024 < ring_bytes) ring_bytes = size_t(g_stack_ring_kb) * 1024;
+  int stages = int(ring_bytes / slot);
   if (stages < 2) return set_error(MLA_ERR_ARG, "decode_stack: hidden %d / ffn %d do not fit the shared-memory ring", h, a->ffn);
   p.stages = stages > ST_MAX_STAGES ? ST_MAX_STAGES : stages;
   p.slot_bytes = uint32_t(slot);
@@ -571,7 +825,7 @@ extern "C" int mla_decode_stack(const mla_decode_stack_args* a, void* stream) {
   // refuse the launch instead of deadlocking if that ever does not hold
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(num_sms());
-  cfg.blockDim = dim3(GV_THREADS);
+  cfg.blockDim = dim3(ST_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = (cudaStream_t)stream;
   cudaLaunchAttribute attr[1];

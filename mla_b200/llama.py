@@ -16,6 +16,7 @@ aliases (no autograd-side accumulation buffers).
 from __future__ import annotations
 
 import os
+from types import SimpleNamespace
 from dataclasses import dataclass
 from typing import List, Optional, Tuple
 
@@ -47,8 +48,10 @@ FUSE_GRAD_NORM = {"on": os.environ.get("MLA_FUSE_GRAD_NORM", "1") == "1"}
 # NVTX ranges per decoder layer and phase (MLA_NVTX=1): nsys / ncu --nvtx can then attribute kernels to
 # layer.N.fwd / layer.N.bwd.mlp / layer.N.bwd.attn.  Off by default (two host calls per range).
 NVTX = {"on": os.environ.get("MLA_NVTX", "0") == "1"}
-# inference: all decoder layers of a denoise step in ONE persistent launch (csrc/decode_stack.cu) when batch*rows <= 2
-DECODE_STACK = os.environ.get("MLA_DECODE_STACK", "1") == "1"
+# inference: all decoder layers of a denoise step in ONE persistent launch (csrc/decode_stack.cu) when batch*rows <= 2.
+# Correct and tested, but measured SLOWER than the per-op path it was meant to replace (4.27 vs 3.23 ms per step at 7B:
+# profiles/r02_decode_stack_trace.json), so it is opt-in.
+DECODE_STACK = os.environ.get("MLA_DECODE_STACK", "0") == "1"
 
 
 class _Range:
@@ -496,19 +499,30 @@ class LlamaModel(nn.Module):
 
     def _decode_stack(self, x, caches, B, P, n, cs, sn):
         """One persistent launch for all layers (csrc/decode_stack.cu).  The per-layer pointer table and the workspace
-        are built on the first (eager) call for a set of buffers and re-used afterwards — a CUDA-graph capture of the
-        DDIM loop therefore has to be preceded by an eager pass, which VLM.denoise_session does."""
+        are built on the first (eager) call for a set of weight / cache buffers and re-used afterwards — a CUDA-graph
+        capture of the DDIM loop therefore has to be preceded by an eager pass, which VLM.denoise_session does.  A
+        captured graph holds the table's address: entries seen during a capture are pinned, the others are evicted
+        least-recently-used (eager calls bring a fresh set of caches every time)."""
         ws = [layer.compute_weights() for layer in self.layers]       # refreshes the bf16 copies if a master changed
         ptrs = tuple(t.data_ptr() for w in ws for t in w) + tuple(c.data_ptr() for c in caches)
-        st = self.__dict__.get("_stack_state")
-        if st is None or st[0] != ptrs:
-            L = len(self.layers)
+        tables = self.__dict__.setdefault("_stack_tables", {})
+        st = tables.pop(ptrs, None)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if st is None:
+            if capturing:
+                raise RuntimeError("decode: run the denoise step once eagerly before capturing it into a CUDA graph "
+                                   "(the per-layer pointer table is built on the first call)")
             rows = [[w[i].data_ptr() for w in ws] for i in range(6)] + [[c.data_ptr() for c in caches]]
-            table = torch.tensor(rows, dtype=torch.int64).to(x.device)
-            st = (ptrs, table, {})
-            self.__dict__["_stack_state"] = st
+            st = SimpleNamespace(table=torch.tensor(rows, dtype=torch.int64).to(x.device), ws={}, pinned=False)
+            loose = [k for k, v in tables.items() if not v.pinned]
+            for k in loose[:max(0, len(loose) - 3)]:
+                del tables[k]
+        tables[ptrs] = st                                             # most recently used last
+        st.pinned = st.pinned or capturing
         key = (B, n, P)
-        if key not in st[2]:
-            st[2][key] = ops.decode_stack_workspace(B, n, P, self.heads, self.hidden_size // self.heads, x.device)
-        return ops.decode_stack(x, st[1], cs, sn, st[2][key], B, n, P, self.heads, self.hidden_size // self.heads,
+        if key not in st.ws:
+            if capturing:
+                raise RuntimeError("decode: workspace for this shape was not built before the capture")
+            st.ws[key] = ops.decode_stack_workspace(B, n, P, self.heads, self.hidden_size // self.heads, x.device)
+        return ops.decode_stack(x, st.table, cs, sn, st.ws[key], B, n, P, self.heads, self.hidden_size // self.heads,
                                 self.layers[0].inter, self.eps)

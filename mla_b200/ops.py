@@ -759,7 +759,8 @@ def decode_stack_workspace(B: int, n: int, P: int, H: int, D: int, device) -> to
 
 
 def decode_stack(x: torch.Tensor, table: torch.Tensor, cos_t: torch.Tensor, sin_t: torch.Tensor, workspace: torch.Tensor,
-                 B: int, n: int, P: int, H: int, D: int, f: int, eps: float) -> torch.Tensor:
+                 B: int, n: int, P: int, H: int, D: int, f: int, eps: float,
+                 trace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """All decoder layers over the n suffix rows per sample in ONE persistent launch (see mla_decode_stack).
     x bf16 [B*n, h] (not modified); table int64 [7, L] on the device = per-layer pointers of w_qkv, w_o, w_gate_up,
     w_down, ln1, ln2, kv_cache; returns the last layer's output bf16 [B*n, h] (final norm not applied)."""
@@ -782,6 +783,7 @@ def decode_stack(x: torch.Tensor, table: torch.Tensor, cos_t: torch.Tensor, sin_
     a.cos_t, a.sin_t, a.workspace = cos_t.data_ptr(), sin_t.data_ptr(), workspace.data_ptr()
     a.layers, a.batch, a.n, a.prefix, a.heads, a.head_dim, a.ffn = L, B, n, P, H, D, f
     a.eps, a.scale = float(eps), float(D ** -0.5)
+    a.trace = trace.data_ptr() if trace is not None else None      # int64 [SMs, L, 5, 3] phase timestamps (profiling)
     check(_lib.lib().mla_decode_stack(C.byref(a), _stream()))
     return xb
 

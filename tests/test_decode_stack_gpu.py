@@ -1,7 +1,8 @@
 """The whole decoder stack of a denoise step as ONE persistent launch (csrc/decode_stack.cu, mla_decode_stack) against
 the per-op path it replaces (LlamaDecoderLayer.decode: gemv_fused / decode_attn_rope / gemv_fused x3 per layer).
-The kernel keeps every thread -> k-chunk mapping, reduction tree and rounding point of the per-op kernels (attention =
-the split-K variant), so the comparison is BITWISE; against the default (un-split) attention it is within bf16 noise.
+Same rounding points (bf16 after RMSNorm, after every linear, after the residual adds); the linears accumulate on the
+tensor cores (mma.sync) in another fp32 order than the per-op CUDA-core kernels, so the comparison is within bf16
+noise (and against an fp32 reference it is as close as the per-op path is); repeated launches are bit-identical.
 Also: re-launch without re-zeroing the workspace (self re-arming barrier / counters), capture into a CUDA graph
 (cooperative launch inside a capture), one-row and two-sample shapes."""
 import pytest
@@ -42,6 +43,42 @@ def _per_op(model, x, caches, B, P, n, split_k):
     return x
 
 
+def _fp32_reference(model, x, caches, B, P, n):
+    """The same layers in fp32 torch ops (bf16 weights and caches, no intermediate rounding)."""
+    H = model.heads
+    h = model.hidden_size
+    D = h // H
+    cos, sin = model.rope_tables(P + n, x.device)
+    cs, sn = cos[P:P + n].float(), sin[P:P + n].float()
+
+    def rope(t):                       # t [B, n, H, D]
+        t1, t2 = t[..., :D // 2], t[..., D // 2:]
+        c, s_ = cs[None, :, None, :], sn[None, :, None, :]
+        return torch.cat([t1 * c - t2 * s_, t2 * c + t1 * s_], -1)
+
+    def norm(t, w):
+        return t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + model.eps) * w.float()
+
+    xf = x.float()
+    for layer, cache in zip(model.layers, caches):
+        wqkv, wo, wgu, wd, l1, l2 = (t.float() for t in layer.compute_weights())
+        qkv = (norm(xf, l1) @ wqkv.t()).view(B, n, 3, H, D)
+        q, k, v = rope(qkv[:, :, 0]), rope(qkv[:, :, 1]), qkv[:, :, 2]
+        kc, vc = cache[:, 0].float(), cache[:, 1].float()                     # [B, H, P, D]
+        keys = torch.cat([kc, k.permute(0, 2, 1, 3)], 2)                       # [B, H, P+n, D]
+        vals = torch.cat([vc, v.permute(0, 2, 1, 3)], 2)
+        sc = torch.einsum("bnhd,bhjd->bhnj", q, keys) * D ** -0.5
+        j = torch.arange(P + n, device=x.device)[None, None, None, :]
+        i = torch.arange(n, device=x.device)[None, None, :, None]
+        sc = sc.masked_fill(j > P + i, float("-inf"))
+        ctx = torch.einsum("bhnj,bhjd->bnhd", sc.softmax(-1), vals).reshape(B * n, h)
+        x_mid = xf + ctx @ wo.t()
+        gu = norm(x_mid, l2) @ wgu.t()
+        f = gu.shape[1] // 2
+        xf = x_mid + (torch.nn.functional.silu(gu[:, :f]) * gu[:, f:]) @ wd.t()
+    return xf
+
+
 def _stack(model, x, caches, B, P, n):
     cos, sin = model.rope_tables(P + n, x.device)
     return model._decode_stack(x, caches, B, P, n, cos[P:P + n].contiguous(), sin[P:P + n].contiguous())
@@ -53,44 +90,41 @@ def _caches(model, B, P, scale=1.0):
 
 
 @pytest.mark.parametrize("h,f,L,H,B,n,P", [
-    (256, 512, 3, 4, 1, 2, 37),          # head_dim 64, one attention split
-    (256, 704, 2, 8, 1, 2, 300),         # head_dim 32, three splits
-    (512, 1024, 2, 4, 1, 1, 129),        # head_dim 128, one row (MB = 1), split boundary at 128 | 2
+    (256, 512, 3, 4, 1, 2, 37),          # head_dim 64, one pass over the keys
+    (256, 704, 2, 8, 1, 2, 300),         # head_dim 32, three passes
+    (512, 1024, 2, 4, 1, 1, 129),        # head_dim 128, one row (MB = 1), pass boundary at 128 | 2
     (512, 1024, 2, 4, 2, 1, 200),        # two samples of one row
     (4096, 11008, 2, 32, 1, 2, 545),     # Llama-2-7B width: K = 11008 takes the 3-chunks-per-thread path
 ])
-def test_stack_equals_per_op_path_bitwise(cuda_lib, h, f, L, H, B, n, P):
+def test_stack_equals_per_op_path(cuda_lib, h, f, L, H, B, n, P):
     model = _model(h, f, L, H, seed=h + P)
     caches = _caches(model, B, P)
     torch.manual_seed(1)
     x = torch.randn(B * n, h, device="cuda").bfloat16()
     x0 = x.clone()
-    want = _per_op(model, x, caches, B, P, n, split_k=True)
+    want = _per_op(model, x, caches, B, P, n, split_k=False)
     got = _stack(model, x, caches, B, P, n)
     torch.cuda.synchronize()
     assert torch.equal(x, x0)                                   # the input is not modified
-    assert torch.equal(got, want), rel_err(got, want)
-    plain = _per_op(model, x, caches, B, P, n, split_k=False)   # default per-op attention: same math, other merge order
-    assert rel_err(got, plain) < 1e-2
-    # second launch on the same workspace: the arrival counters and the grid barrier re-armed themselves
+    assert rel_err(got, want) < 6e-3, rel_err(got, want)
+    ref = _fp32_reference(model, x, caches, B, P, n)
+    e_got, e_per_op = rel_err(got, ref), rel_err(want, ref)
+    assert e_got < 1.5 * e_per_op + 2e-3, (e_got, e_per_op)
+    # second launch on the same workspace: the grid barrier re-armed itself; same bits (no timing-dependent sums)
     again = _stack(model, x, caches, B, P, n)
-    assert torch.equal(again, want)
+    assert torch.equal(again, got)
 
 
-def test_stack_in_cuda_graph_and_model_decode(cuda_lib):
+def test_stack_in_cuda_graph_and_model_decode(cuda_lib, monkeypatch):
     from mla_b200 import llama
     h, f, L, H, B, n, P = 512, 1024, 4, 4, 1, 2, 150
     model = _model(h, f, L, H, seed=5)
     caches = _caches(model, B, P)
     x = torch.randn(B * n, h, device="cuda").bfloat16()
-    assert llama.DECODE_STACK
+    per_op = model.decode(x, caches, B, P, n)                   # the default: one launch per op
+    monkeypatch.setattr(llama, "DECODE_STACK", True)
     eager = model.decode(x, caches, B, P, n)                    # builds the pointer table / workspace (never in a capture)
-    llama.DECODE_STACK = False
-    try:
-        per_op = model.decode(x, caches, B, P, n)
-    finally:
-        llama.DECODE_STACK = True
-    assert rel_err(eager, per_op) < 1e-2
+    assert rel_err(eager, per_op) < 6e-3
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -103,6 +137,17 @@ def test_stack_in_cuda_graph_and_model_decode(cuda_lib):
         g.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, eager)
+    # eager calls with other cache sets in between must not invalidate what the graph captured (its pointer table is
+    # pinned; the eager ones are evicted least-recently-used)
+    for i in range(6):
+        other = _caches(model, B, P)
+        model.decode(x, other, B, P, n)
+        del other
+    junk = [torch.full((7, L), 3, dtype=torch.int64, device="cuda") for _ in range(64)]      # recycle freed blocks
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)
+    del junk
     # new activations through the same graph
     x.copy_(torch.randn_like(x))
     g.replay()
