@@ -1,6 +1,8 @@
 // Bandwidth-bound row kernels of the decoder layer: RMSNorm fwd/bwd, RoPE (in place, fwd and transposed for bwd),
 // SwiGLU fwd/bwd.  One pass over HBM each, 16-byte vector accesses, fp32 math, and the reference's bf16 rounding
 // points reproduced (each PyTorch op on the bf16 autocast path rounds its result to bf16).
+#include <cstdlib>
+
 #include "mla_internal.cuh"
 #include "ptx.cuh"
 
@@ -277,6 +279,129 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
   }
 }
 
+// Same arithmetic, loads staged through shared memory with cp.async: a thread copies the 16-byte chunks IT will consume
+// (x, dy, dres of rows r + k*grid) RB_STAGES - 1 rows ahead, so ~70 KB per CTA (two CTAs per SM) are in flight
+// regardless of the register budget — the register-prefetch kernel above keeps one row (24 KB) per CTA in flight and
+// sits at 0.69 of the HBM peak.  No barrier guards the pipeline: every thread only ever reads what it copied itself.
+constexpr int RB_STAGES = 4;
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int VPT>
+__global__ void __launch_bounds__(256, 2)
+rmsnorm_bwd_pipe_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                        const __nv_bfloat16* __restrict__ w, const __nv_bfloat16* __restrict__ dres,
+                        __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, int64_t rows, int h, float eps) {
+  extern __shared__ __align__(16) uint8_t rb_smem[];      // [RB_STAGES][3][h] bf16
+  __shared__ float red[2][32];
+  const int nvec = h >> 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const uint32_t row_bytes = uint32_t(h) * 2u;
+  const uint32_t sbase = uint32_t(__cvta_generic_to_shared(rb_smem));
+  uint4 wp[VPT];
+  float dwacc[VPT][8];
+#pragma unroll
+  for (int v = 0; v < VPT; ++v) {
+    const int i = threadIdx.x + v * blockDim.x;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dwacc[v][j] = 0.f;
+    wp[v] = make_uint4(0, 0, 0, 0);
+    if (i < nvec) wp[v] = *reinterpret_cast<const uint4*>(w + i * 8);
+  }
+  auto issue = [&](int64_t r, int stage) {
+    if (r < rows) {
+      const uint32_t sb = sbase + uint32_t(stage) * 3u * row_bytes;
+#pragma unroll
+      for (int v = 0; v < VPT; ++v) {
+        const int i = threadIdx.x + v * blockDim.x;
+        if (i < nvec) {
+          cp_async16(sb + 16u * i, x + r * h + i * 8);
+          cp_async16(sb + row_bytes + 16u * i, dy + r * h + i * 8);
+          if (dres) cp_async16(sb + 2u * row_bytes + 16u * i, dres + r * h + i * 8);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  int64_t row = blockIdx.x;
+#pragma unroll
+  for (int k = 0; k < RB_STAGES - 1; ++k) issue(row + int64_t(k) * gridDim.x, k);
+  int stage = 0;
+  for (; row < rows; row += gridDim.x) {
+    issue(row + int64_t(RB_STAGES - 1) * gridDim.x, (stage + RB_STAGES - 1) % RB_STAGES);
+    cp_async_wait<RB_STAGES - 1>();
+    const uint8_t* sb = rb_smem + size_t(stage) * 3u * row_bytes;
+    float xf[VPT][8], dyf[VPT][8];
+    uint4 res[VPT];
+    float ss = 0.f, dp = 0.f;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int i = threadIdx.x + v * blockDim.x;
+      float wv[8];
+      uint4 qx = make_uint4(0, 0, 0, 0), qd = qx;
+      res[v] = qx;
+      if (i < nvec) {
+        qx = *reinterpret_cast<const uint4*>(sb + 16u * i);
+        qd = *reinterpret_cast<const uint4*>(sb + row_bytes + 16u * i);
+        if (dres) res[v] = *reinterpret_cast<const uint4*>(sb + 2u * row_bytes + 16u * i);
+      }
+      unpack8(qx, xf[v]);
+      unpack8(qd, dyf[v]);
+      unpack8(wp[v], wv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ss += xf[v][j] * xf[v][j];
+        dp += (dyf[v][j] * wv[j]) * xf[v][j];
+      }
+    }
+    ss = warp_sum(ss);
+    dp = warp_sum(dp);
+    __syncthreads();
+    if (lane == 0) { red[0][warp] = ss; red[1][warp] = dp; }
+    __syncthreads();
+    ss = warp_sum(lane < nw ? red[0][lane] : 0.f);
+    dp = warp_sum(lane < nw ? red[1][lane] : 0.f);
+    const float rstd = rsqrtf(ss / float(h) + eps);
+    const float dot = rstd * dp / float(h);      // mean(dn * n), n = x * rstd
+    __nv_bfloat16* dxr = dx + row * h;
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int i = threadIdx.x + v * blockDim.x;
+      if (i < nvec) {
+        float o[8], wv[8];
+        unpack8(wp[v], wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float n = xf[v][j] * rstd;
+          dwacc[v][j] += dyf[v][j] * bf16_round(n);   // dy * n (n is what forward multiplied by w)
+          o[j] = bf16_round(rstd * (dyf[v][j] * wv[j] - n * dot));
+        }
+        if (dres) {
+          float r[8];
+          unpack8(res[v], r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
+        *reinterpret_cast<uint4*>(dxr + i * 8) = pack8(o);
+      }
+    }
+    stage = (stage + 1) % RB_STAGES;
+  }
+  cp_async_wait<0>();
+  if (dw) {
+#pragma unroll
+    for (int v = 0; v < VPT; ++v) {
+      const int i = threadIdx.x + v * blockDim.x;
+      if (i < nvec)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dw + i * 8 + j, dwacc[v][j]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ RoPE
 // modeling_llama.py:184-208 on the bf16 path: out = bf16(bf16(x*cos) + bf16(rotate_half(x)*sin)), cos/sin bf16.
 // Applied in place to the q and k column blocks of the fused [T, ld] projection buffer.  sign=-1 is the transpose
@@ -429,6 +554,25 @@ extern "C" int mla_rmsnorm_bwd(const void* dy, const void* x, const void* w, con
   const int vpt = (nvec + block - 1) / block;
   int grid = int(rows < int64_t(num_sms()) * 2 ? rows : int64_t(num_sms()) * 2);
   auto s = (cudaStream_t)stream;
+  {
+    // cp.async-staged variant: needs 4 stages x 3 rows in shared memory twice per SM, and enough rows to fill the pipe
+    static int pipe = -1;
+    if (pipe < 0) {
+      const char* e = getenv("MLA_RMSNORM_BWD_PIPE");
+      pipe = (e && e[0] == '0') ? 0 : 1;
+    }
+    const size_t smem = size_t(RB_STAGES) * 3 * size_t(h) * 2;
+    if (pipe && vpt <= 2 && block == 256 && smem <= 100 * 1024 && rows >= int64_t(grid) * RB_STAGES &&
+        ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dres)) & 15) == 0) {
+      auto kern = vpt == 1 ? rmsnorm_bwd_pipe_kernel<1> : rmsnorm_bwd_pipe_kernel<2>;
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+      if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "rmsnorm_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      kern<<<grid, 256, smem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w,
+                                   (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx, (float*)dw, rows, h, eps);
+      MLA_CHECK_LAUNCH("rmsnorm_bwd_pipe");
+      return MLA_OK;
+    }
+  }
 #define LAUNCH_RB(V)                                                                                              \
   rmsnorm_bwd_kernel<V><<<grid, block, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,                 \
                                                 (const __nv_bfloat16*)w, (const __nv_bfloat16*)dres,              \

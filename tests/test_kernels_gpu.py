@@ -53,6 +53,38 @@ def test_rmsnorm_fwd_bwd(cuda_lib, rows, h):
     assert rel_err(dw, wf.grad) < 6e-3
 
 
+@pytest.mark.parametrize("rows,h,with_res", [(4096 + 37, 4096, True), (3000, 2048, False), (17536, 4096, True)])
+def test_rmsnorm_bwd_staged_kernel_matches_register_kernel(cuda_lib, rows, h, with_res):
+    """Large calls stage x / dy / dres through shared memory with cp.async (4 rows ahead per CTA); the arithmetic per row is
+    the register-prefetch kernel's, so dx is bit-identical to what small calls (below the row threshold) produce, and the
+    weight gradient agrees with fp32 autograd."""
+    from mla_b200 import ops
+    from oracle import llama as O
+    torch.manual_seed(rows)
+    x = _bf(torch.randn(rows, h, device="cuda") * 2)
+    w = _bf(1 + 0.1 * torch.randn(h, device="cuda"))
+    dy = _bf(torch.randn(rows, h, device="cuda"))
+    dres = _bf(torch.randn(rows, h, device="cuda")) if with_res else None
+    dw = torch.zeros(h, device="cuda")
+    dx = ops.rmsnorm_bwd(dy, x, w, 1e-5, dres=dres, dw=dw)
+    k = 500                                # < 4 rows per CTA: the register-prefetch kernel
+    for lo in (0, rows - k):
+        sl = slice(lo, lo + k)
+        dx_small = ops.rmsnorm_bwd(dy[sl].contiguous(), x[sl].contiguous(), w, 1e-5,
+                                   dres=dres[sl].contiguous() if with_res else None, dw=torch.zeros(h, device="cuda"))
+        assert torch.equal(dx[sl], dx_small)
+    xf = x[:2048].float().requires_grad_(True)
+    wf = w.float().requires_grad_(True)
+    O.rmsnorm(xf, wf, 1e-5).backward(dy[:2048].float())
+    assert rel_err(dx[:2048], xf.grad + (dres[:2048].float() if with_res else 0)) < 6e-3
+    dw2 = torch.zeros(h, device="cuda")
+    ops.rmsnorm_bwd(dy[:2048].contiguous(), x[:2048].contiguous(), w, 1e-5, dw=dw2)
+    assert rel_err(dw2, wf.grad) < 6e-3
+    # whole-call weight gradient against a chunked fp32 evaluation
+    n = (x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-5)).bfloat16().float()
+    assert rel_err(dw, (dy.float() * n).sum(0)) < 2e-3
+
+
 @pytest.mark.parametrize("B,S,H,D", [(2, 44, 4, 32), (2, 70, 2, 128)])
 def test_rope_matches_reference_rounding(cuda_lib, B, S, H, D):
     from mla_b200 import ops
