@@ -385,6 +385,14 @@ typedef struct mla_gemv_args {
   float eps;
 } mla_gemv_args;
 int mla_gemv_fused(const mla_gemv_args* a, void* stream);
+/* skinny_gemm: the same skinny linear (same arguments and prologues as mla_gemv_fused, m <= 32) on the tensor cores,
+ * "swap-AB": the weights are the 128-row A operand of tcgen05.mma streamed by TMA, the activation rows its 16/32-column
+ * B operand (written by the kernel's prologue warps straight into the swizzled operand layout), split-K over the SMs
+ * with a fixed-order last-arrival sum (csrc/skinny_sm100.cu).  The weights never pass through the CUDA cores.
+ * workspace: mla_skinny_gemm_workspace(n, m) bytes, ZEROED once before the first launch (the arrival counters re-arm
+ * themselves); one workspace per (n, m <= 16 | m <= 32) in flight on a stream. */
+int mla_skinny_gemm(const mla_gemv_args* a, void* workspace, void* stream);
+size_t mla_skinny_gemm_workspace(int32_t n, int32_t m);
 /* The gemv kernels are launched with programmaticStreamSerialization (the weight prefetch of the next kernel overlaps
  * the previous kernel's tail; consumers griddepcontrol.wait before touching activations).  0 turns it off (env
  * MLA_DECODE_PDL=0 does the same). */

@@ -5,6 +5,7 @@ torch is used only for device memory and streams; every computation is a libmla_
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -643,6 +644,40 @@ class CrossEntropyFn(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------------------------- inference (decode)
+# Skinny linears of the denoise step on the tensor cores (csrc/skinny_sm100.cu) instead of the CUDA-core weight-streaming
+# kernels (csrc/decode.cu).  MLA_DECODE_SKINNY=0 selects the latter.
+SKINNY = {"on": os.environ.get("MLA_DECODE_SKINNY", "1") == "1"}
+_skinny_ws = {}
+
+
+def _skinny_gemm(x, w, residual, out, norm, swiglu):
+    m = x.shape[0]
+    n, k = w.shape
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.bfloat16, device=x.device)
+    lib = _lib.lib()
+    key = (x.device, n, m <= 16)
+    ws = _skinny_ws.get(key)
+    if ws is None:
+        lib.mla_skinny_gemm_workspace.restype = C.c_size_t
+        ws = torch.zeros(lib.mla_skinny_gemm_workspace(C.c_int32(n), C.c_int32(m)), dtype=torch.uint8, device=x.device)
+        _skinny_ws[key] = ws
+    a = _lib.GemvArgs()
+    a.x, a.w, a.out = x.data_ptr(), w.data_ptr(), out.data_ptr()
+    a.m, a.n, a.k = m, n, k
+    a.ldx, a.ldw, a.ldo = _rowmajor_2d(x, "x"), _rowmajor_2d(w, "w"), _rowmajor_2d(out, "out")
+    if residual is not None:
+        _req(residual, torch.bfloat16, "residual")
+        a.residual, a.ldr = residual.data_ptr(), _rowmajor_2d(residual, "residual")
+    if norm is not None:
+        _req(norm[0], torch.bfloat16, "ln_weight")
+        a.prologue, a.ln_weight, a.eps = 1, norm[0].data_ptr(), float(norm[1])
+    elif swiglu:
+        a.prologue = 2
+    check(lib.mla_skinny_gemm(C.byref(a), _p(ws), _stream()))
+    return out
+
+
 def gemv(x: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = None,
          out: Optional[torch.Tensor] = None, norm: Optional[tuple] = None, swiglu: bool = False) -> torch.Tensor:
     """Skinny nn.Linear for a handful of rows (HBM-bound weight streaming, csrc/decode.cu): x bf16 [m,k], w bf16 [n,k]
@@ -655,6 +690,8 @@ def gemv(x: torch.Tensor, w: torch.Tensor, residual: Optional[torch.Tensor] = No
     n, k = w.shape
     if x.shape[1] != (2 * k if swiglu else k):
         raise _lib.MlaError(f"gemv: contraction mismatch {x.shape[1]} vs {k}")
+    if SKINNY["on"] and m <= 32 and k % 8 == 0 and w.is_contiguous():
+        return _skinny_gemm(x, w, residual, out, norm, swiglu)
     fused = (m <= 4 and k <= 4096) or (m <= 2 and k <= 12288)      # activations fit the kernel's registers
     if not fused:
         if norm is not None:
