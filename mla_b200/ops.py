@@ -644,9 +644,11 @@ class CrossEntropyFn(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------------------------- inference (decode)
-# Skinny linears of the denoise step on the tensor cores (csrc/skinny_sm100.cu) instead of the CUDA-core weight-streaming
-# kernels (csrc/decode.cu).  MLA_DECODE_SKINNY=0 selects the latter.
-SKINNY = {"on": os.environ.get("MLA_DECODE_SKINNY", "1") == "1"}
+# Skinny linears of the denoise step on the tensor cores (csrc/skinny_sm100.cu, swap-AB tcgen05) instead of the CUDA-core
+# weight-streaming kernels (csrc/decode.cu).  Correct and tested, but measured slower end to end (4.70 vs 3.60 ms per
+# DDIM step at 2 rows, 11.2 vs 7.8 at 17: every launch pays its prologue and a split-K finish with the memory pipe idle;
+# profiles/r02_decode_stack_findings.md), so it is opt-in: MLA_DECODE_SKINNY=1.
+SKINNY = {"on": os.environ.get("MLA_DECODE_SKINNY", "0") == "1"}
 _skinny_ws = {}
 
 

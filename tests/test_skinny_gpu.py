@@ -33,8 +33,9 @@ def _ref(x, w, residual, norm, swiglu):
     (2, 12288, 4096, "norm"), (2, 4096, 4096, "plain"), (2, 22016, 4096, "norm"), (2, 4096, 11008, "swiglu"),
     (17, 4096, 11008, "swiglu"), (17, 12288, 4096, "norm"),
 ])
-def test_skinny_gemm_matches_reference(cuda_lib, m, n, k, mode):
+def test_skinny_gemm_matches_reference(cuda_lib, monkeypatch, m, n, k, mode):
     from mla_b200 import ops
+    monkeypatch.setitem(ops.SKINNY, "on", True)
     torch.manual_seed(m * 1000 + n + k)
     w = (torch.randn(n, k, device="cuda") * k ** -0.5).bfloat16()
     x = torch.randn(m, 2 * k if mode == "swiglu" else k, device="cuda").bfloat16()
@@ -55,10 +56,11 @@ def test_skinny_gemm_matches_reference(cuda_lib, m, n, k, mode):
         assert rel_err(got, old) < 4e-3
 
 
-def test_skinny_gemm_chain_under_pdl(cuda_lib):
+def test_skinny_gemm_chain_under_pdl(cuda_lib, monkeypatch):
     """Back-to-back launches (programmatic dependent launch: the next kernel's producer starts while this one drains) on
     shared workspaces: a 3-linear chain repeated, identical every time and equal to the launch-by-launch result."""
     from mla_b200 import ops
+    monkeypatch.setitem(ops.SKINNY, "on", True)
     torch.manual_seed(3)
     h, f, m = 1024, 2816, 2
     w1 = (torch.randn(2 * f, h, device="cuda") * h ** -0.5).bfloat16()
