@@ -82,6 +82,12 @@ static int encode_nd_uncached(CUtensorMap* map, const void* ptr, int rank, const
 static int encode_nd(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
                      const uint32_t* box) {
   static thread_local TmapEntry* cache = nullptr;
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("MLA_TMAP_CACHE");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (!enabled) return encode_nd_uncached(map, ptr, rank, dims, strides, box);
   if (!cache) cache = static_cast<TmapEntry*>(calloc(kTmapCacheSize, sizeof(TmapEntry)));
   if (!cache || rank > 3) return encode_nd_uncached(map, ptr, rank, dims, strides, box);
   TmapKey k;
