@@ -63,6 +63,26 @@ def main():
     hs = m.run_layers(x, B, S, mask)
     hs[-1].backward(torch.randn_like(hs[-1]))
     torch.cuda.synchronize()
+    # ---- large-call row kernels (cp.async-staged RMSNorm backward) and the inference denoise step: per-op gemv path, the
+    #      one-launch stack kernel and the tcgen05 skinny linears (both opt-in), at small sizes
+    rows, hh = 1300, 1024
+    ops.rmsnorm_bwd(torch.randn(rows, hh, device="cuda").to(bf), torch.randn(rows, hh, device="cuda").to(bf),
+                    torch.ones(hh, device="cuda").to(bf), 1e-5, dres=torch.randn(rows, hh, device="cuda").to(bf),
+                    dw=torch.zeros(hh, device="cuda"))
+    dm = llama.LlamaModel(64, 256, 704, 2, 4, eps=1e-5).cuda().eval()
+    P, n = 150, 2
+    caches = [torch.randn(1, 2, 4, P, 64, device="cuda").to(bf) for _ in dm.layers]
+    xr = torch.randn(n, 256, device="cuda").to(bf)
+    with torch.no_grad():
+        dm.decode(xr, caches, 1, P, n)
+        llama.DECODE_STACK = True
+        dm.decode(xr, caches, 1, P, n)
+        llama.DECODE_STACK = False
+        ops.SKINNY["on"] = True
+        dm.decode(xr, caches, 1, P, n)
+        dm.decode(torch.randn(17, 256, device="cuda").to(bf), caches, 1, P, 17)
+        ops.SKINNY["on"] = False
+    torch.cuda.synchronize()
     # ---- Tiny-MLA training step (tokenizers, splice, embedders, head, loss, optimizer)
     import __graft_entry__ as ge
     ge.smoke()
