@@ -470,6 +470,9 @@ int mla_sumsq_f32(const void* x, int64_t n, void* out, void* stream);
 int mla_clip_coef(const void* sumsq, float max_norm, float inv_world, void* scale, void* stream);
 int mla_adamw_f32(void* p, const void* g, void* m, void* v, void* p_bf16, int64_t n, float lr, float beta1,
                   float beta2, float eps, float weight_decay, int64_t step, const void* grad_scale, void* stream);
+/* n > 0: launch AdamW with n CTAs of 128 threads per SM (small register footprint) so that it can share the SMs with
+ * the persistent GEMM CTAs of the next step's forward (trainer, MLA_ADAM_STREAM=1); 0 = the standalone launch shape. */
+int mla_adamw_set_lean(int32_t ctas_per_sm);
 
 /* ---- vocabulary cross-entropy (modeling_llama.py:1254-1269) ------------------------------------------------------
  * logits bf16 [rows = B*seq, vocab] (pitch ld) from the lm_head GEMM; labels int64 [B, seq] UNshifted: row (b,s) is

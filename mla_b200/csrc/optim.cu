@@ -87,9 +87,58 @@ adamw_vec4_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* 
   }
 }
 
+// Small-footprint variant for running NEXT TO the forward GEMMs of the following step (trainer: MLA_ADAM_STREAM=1): the
+// persistent GEMM CTAs take ~55 K of an SM's 64 K registers and all of its shared memory, so the update may only use
+// what is left — one CTA of 128 threads per SM, two float4 per array and thread in flight (32 KB of loads per SM; the
+// forward lasts ~190 ms, the update needs ~200 GB, i.e. ~1.1 TB/s of the bandwidth the tensor-bound GEMMs leave idle).
+__global__ void __launch_bounds__(128)
+adamw_vec4_lean_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                       uint2* __restrict__ p_bf16, int64_t n4, float lr, float beta1, float beta2, float eps, float wd,
+                       float bc1, float bc2_sqrt, const float* __restrict__ gscale) {
+  const float gs = gscale ? gscale[0] : 1.f;
+  const float step = lr / bc1;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  for (; i + stride < n4; i += 2 * stride) {
+    const int64_t j = i + stride;
+    float4 pv = p[i], mv = m[i], vv = v[i], pw = p[j], mw = m[j], vw = v[j];
+    const float4 gv = g[i], gw = g[j];
+    const float a = adamw_one(pv.x, gv.x, mv.x, vv.x, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    const float b = adamw_one(pv.y, gv.y, mv.y, vv.y, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    const float c = adamw_one(pv.z, gv.z, mv.z, vv.z, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    const float d = adamw_one(pv.w, gv.w, mv.w, vv.w, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    const float a2 = adamw_one(pw.x, gw.x, mw.x, vw.x, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    const float b2 = adamw_one(pw.y, gw.y, mw.y, vw.y, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    const float c2 = adamw_one(pw.z, gw.z, mw.z, vw.z, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    const float d2 = adamw_one(pw.w, gw.w, mw.w, vw.w, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    p[i] = pv; m[i] = mv; v[i] = vv;
+    p[j] = pw; m[j] = mw; v[j] = vw;
+    if (p_bf16) {
+      p_bf16[i] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+      p_bf16[j] = make_uint2(pack_bf16x2(a2, b2), pack_bf16x2(c2, d2));
+    }
+  }
+  if (i < n4) {
+    float4 pv = p[i], mv = m[i], vv = v[i];
+    const float4 gv = g[i];
+    const float a = adamw_one(pv.x, gv.x, mv.x, vv.x, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    const float b = adamw_one(pv.y, gv.y, mv.y, vv.y, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    const float c = adamw_one(pv.z, gv.z, mv.z, vv.z, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    const float d = adamw_one(pv.w, gv.w, mv.w, vv.w, gs, lr, wd, beta1, beta2, eps, step, bc2_sqrt);
+    p[i] = pv; m[i] = mv; v[i] = vv;
+    if (p_bf16) p_bf16[i] = make_uint2(pack_bf16x2(a, b), pack_bf16x2(c, d));
+  }
+}
+
 }  // namespace mla
 
 using namespace mla;
+
+static int g_adamw_lean = 0;
+extern "C" int mla_adamw_set_lean(int32_t on) {
+  g_adamw_lean = on;
+  return MLA_OK;
+}
 
 extern "C" int mla_sumsq_f32(const void* x, int64_t n, void* out, void* stream) {
   if (int rc = device_check()) return rc;
@@ -120,6 +169,15 @@ extern "C" int mla_adamw_f32(void* p, const void* g, void* m, void* v, void* p_b
                        reinterpret_cast<uintptr_t>(v);
   if ((n & 3) == 0 && (al & 15) == 0 && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0) {
     const int64_t n4 = n >> 2;
+    if (g_adamw_lean) {
+      int64_t need = (n4 + 127) / 128;
+      const int64_t cap = int64_t(num_sms()) * g_adamw_lean;
+      adamw_vec4_lean_kernel<<<int(need < cap ? need : cap), 128, 0, (cudaStream_t)stream>>>(
+          (float4*)p, (const float4*)g, (float4*)m, (float4*)v, (uint2*)p_bf16, n4, lr, beta1, beta2, eps, weight_decay,
+          bc1, sqrtf(bc2), (const float*)grad_scale);
+      MLA_CHECK_LAUNCH("adamw_lean");
+      return MLA_OK;
+    }
     int64_t blocks4 = (n4 + 255) / 256;
     int64_t cap4 = int64_t(num_sms()) * 8;
     adamw_vec4_kernel<<<int(blocks4 < cap4 ? blocks4 : cap4), 256, 0, (cudaStream_t)stream>>>(

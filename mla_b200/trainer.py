@@ -28,11 +28,15 @@ from . import _lib, ops
 from ._lib import check
 from .llama import LlamaDecoderLayer, side_stream
 
-# Optional: AdamW of the decoder layers on the side stream (MLA_ADAM_STREAM=1, default OFF).  The update is HBM-bound
-# and layer k's new weights are first needed by layer k's forward, so it can run next to the NEXT step's forward
-# GEMMs, each layer's forward waiting on that layer's event only.  Measured slower on the power-capped B200 (see
-# llama.OVERLAP), so it stays a tested switch.
-ADAM_OVERLAP = {"on": __import__("os").environ.get("MLA_ADAM_STREAM", "0") == "1"}
+# AdamW of the decoder layers on the side stream (MLA_ADAM_STREAM=0 turns it off).  The update is HBM-bound and layer
+# k's new weights are first needed by layer k's forward, so it runs next to the NEXT step's forward GEMMs, each layer's
+# forward waiting on that layer's event only.  On the power-capped B200 the gain is small — the update's HBM power comes
+# out of the GEMMs' clock budget: 647.3 -> 641.0 ms per step on one GPU, 700.2 -> 690.6 ms on two
+# (profiles/r02_adam_overlap.json; round 1 measured it slower with the one-CTA GEMM) — but consistent, so it is on.
+# A small-footprint launch shape (MLA_ADAM_LEAN=1: one 128-thread CTA per SM, fits beside a persistent GEMM CTA) was
+# measured too and is slower than letting the full grid run (645.4).
+ADAM_OVERLAP = {"on": __import__("os").environ.get("MLA_ADAM_STREAM", "1") == "1"}
+ADAM_LEAN_CTAS = int(__import__("os").environ.get("MLA_ADAM_LEAN", "0"))      # CTAs of 128 threads per SM under overlap (0 = full grid)
 
 
 class DataParallelTrainer:
@@ -91,6 +95,9 @@ class DataParallelTrainer:
                         torch.autograd.graph.increment_version(t)
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._scale = torch.zeros(2, dtype=torch.float32, device=dev)
+        # model.state_dict() (a user's own checkpoint code) must not read weights the side-stream optimizer is still writing
+        if hasattr(model, "register_state_dict_pre_hook"):
+            model.register_state_dict_pre_hook(lambda *_a, **_k: self.synchronize())
 
     # ------------------------------------------------------------------ gradient exchange
     def no_sync(self):
@@ -232,6 +239,8 @@ class DataParallelTrainer:
                                              torch.zeros_like(p.data, memory_format=torch.contiguous_format))
         if overlap:
             side.wait_stream(main)
+            # small-footprint launches: one 128-thread CTA per SM fits beside a persistent GEMM CTA (registers)
+            lib.mla_adamw_set_lean(C.c_int32(ADAM_LEAN_CTAS))
         with torch.cuda.stream(side) if overlap else _nullctx():
             for l in self.layers:
                 if l._grads_fresh:
@@ -245,6 +254,8 @@ class DataParallelTrainer:
                 l.mark_grads_fresh()
                 if overlap:
                     l._weights_ready = side.record_event()
+        if overlap:
+            lib.mla_adamw_set_lean(C.c_int32(0))
         for _, p, decay in self.other:
             if p.grad is None:
                 continue
@@ -269,6 +280,12 @@ class DataParallelTrainer:
                 "reduce_dtype": str(self.reduce_dtype).replace("torch.", ""),
                 "busbw_factor": round(2.0 * (self.world - 1) / self.world, 4)}
 
+    def synchronize(self) -> None:
+        """Make the current stream wait for optimizer work still running on the side stream (MLA_ADAM_STREAM): call it
+        before reading or writing parameters / optimizer state outside the model's own forward (checkpoints do)."""
+        if self._sumsq.is_cuda:
+            torch.cuda.current_stream().wait_stream(side_stream(self._sumsq.device))
+
     def grad_norm(self) -> torch.Tensor:
         """Mean-gradient global norm of the last step (device scalar)."""
         return self._scale[1]
@@ -281,6 +298,7 @@ class DataParallelTrainer:
         load_from_checkpoint of the reference read it.  Every data-parallel replica holds the full model: rank 0 writes
         its own copy, no gather.  With save_optimizer the AdamW moments and the step counter go to the `.optimizer`
         file next to it (the path the reference reserves, :158-160, but never writes): resume is exact."""
+        self.synchronize()
         from collections import OrderedDict
         from pathlib import Path
         model = self.model
@@ -312,6 +330,7 @@ class DataParallelTrainer:
     def load_checkpoint(self, path, load_optimizer: bool = True) -> dict:
         """Inverse of save_checkpoint (also reads checkpoints written by the reference's FSDPStrategy: same layout).
         Returns the scheduler record ({"epoch", "global_step"}) when an optimizer file was found, else {}."""
+        self.synchronize()
         from pathlib import Path
         path = Path(path)
         blob = torch.load(path, map_location="cpu", weights_only=True)["model"]

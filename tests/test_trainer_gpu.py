@@ -28,6 +28,7 @@ def _model(seed=0, h=128, f=352, L=3, heads=4):
 
 def _run(steps, wgrad_overlap, adam_overlap, level="none", B=2, S=150, h=128, wd=0.01, record=None):
     from mla_b200 import llama, trainer as T
+    saved = (llama.OVERLAP["wgrad"], T.ADAM_OVERLAP["on"])
     llama.OVERLAP["wgrad"], T.ADAM_OVERLAP["on"] = wgrad_overlap, adam_overlap
     try:
         m = _model()
@@ -48,7 +49,7 @@ def _run(steps, wgrad_overlap, adam_overlap, level="none", B=2, S=150, h=128, wd
         copies = [tuple(c.clone() for c in l.compute_weights()) for l in m.layers]
         return m, params, copies, float(tr.grad_norm())
     finally:
-        llama.OVERLAP["wgrad"], T.ADAM_OVERLAP["on"] = False, False
+        llama.OVERLAP["wgrad"], T.ADAM_OVERLAP["on"] = saved
 
 
 def test_adamw_clip_matches_torch(cuda_lib):
