@@ -41,7 +41,17 @@ struct GemmEpilogue {
   int64_t ld_sb_dgu;
   __nv_bfloat16* sb_act;           // bf16 [M, f] or null
   int64_t ld_sb_act;
+  int stream_stores;               // 1: C / fused outputs are written with the evict-first hint
 };
+
+// Output stores with the evict-first hint (st.global.cs): a GEMM's C tile is not re-read by this kernel, and at 0.4-0.8 GB
+// per launch it would otherwise push the operand panels the other CTAs are still sharing out of the 126 MB L2.
+__device__ __forceinline__ void ep_st16(void* p, const uint4& v, int cs) {
+  if (cs) __stcs(reinterpret_cast<uint4*>(p), v); else *reinterpret_cast<uint4*>(p) = v;
+}
+__device__ __forceinline__ void ep_st16f(void* p, const float4& v, int cs) {
+  if (cs) __stcs(reinterpret_cast<float4*>(p), v); else *reinterpret_cast<float4*>(p) = v;
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
@@ -94,10 +104,10 @@ __device__ __forceinline__ void gemm_store_tile_rope(const GemmEpilogue& ep, uin
           o2[2 * t + u] = bf16_round(x2 * cc[u]) + bf16_round(x1 * ss[u]);
         }
       }
-      *reinterpret_cast<uint4*>(crow + c1 * 32 + j) = make_uint4(pack_bf16x2(o1[0], o1[1]), pack_bf16x2(o1[2], o1[3]),
-                                                                 pack_bf16x2(o1[4], o1[5]), pack_bf16x2(o1[6], o1[7]));
-      *reinterpret_cast<uint4*>(crow + c2 * 32 + j) = make_uint4(pack_bf16x2(o2[0], o2[1]), pack_bf16x2(o2[2], o2[3]),
-                                                                 pack_bf16x2(o2[4], o2[5]), pack_bf16x2(o2[6], o2[7]));
+      ep_st16(crow + c1 * 32 + j, make_uint4(pack_bf16x2(o1[0], o1[1]), pack_bf16x2(o1[2], o1[3]),
+                                                                 pack_bf16x2(o1[4], o1[5]), pack_bf16x2(o1[6], o1[7])), ep.stream_stores);
+      ep_st16(crow + c2 * 32 + j, make_uint4(pack_bf16x2(o2[0], o2[1]), pack_bf16x2(o2[2], o2[3]),
+                                                                 pack_bf16x2(o2[4], o2[5]), pack_bf16x2(o2[6], o2[7])), ep.stream_stores);
     }
   }
 }
@@ -126,17 +136,17 @@ __device__ __forceinline__ void gemm_store_tile_swiglu(const GemmEpilogue& ep, u
     __nv_bfloat16* arow = ep.swiglu_out + row * ep.ld_swiglu + g0 + c * 32;
 #pragma unroll
     for (int j = 0; j < 32; j += 8)
-      *reinterpret_cast<uint4*>(arow + j) = make_uint4(pack_bf16x2(a[j], a[j + 1]), pack_bf16x2(a[j + 2], a[j + 3]),
-                                                      pack_bf16x2(a[j + 4], a[j + 5]), pack_bf16x2(a[j + 6], a[j + 7]));
+      ep_st16(arow + j, make_uint4(pack_bf16x2(a[j], a[j + 1]), pack_bf16x2(a[j + 2], a[j + 3]),
+                                                      pack_bf16x2(a[j + 4], a[j + 5]), pack_bf16x2(a[j + 6], a[j + 7])), ep.stream_stores);
     if (ep.c != nullptr) {
       __nv_bfloat16* grow = reinterpret_cast<__nv_bfloat16*>(ep.c) + row * ep.ldc + g0 + c * 32;
       __nv_bfloat16* urow = grow + ep.swiglu_f;
 #pragma unroll
       for (int j = 0; j < 32; j += 8) {
-        *reinterpret_cast<uint4*>(grow + j) = make_uint4(pack_bf16x2(g[j], g[j + 1]), pack_bf16x2(g[j + 2], g[j + 3]),
-                                                        pack_bf16x2(g[j + 4], g[j + 5]), pack_bf16x2(g[j + 6], g[j + 7]));
-        *reinterpret_cast<uint4*>(urow + j) = make_uint4(pack_bf16x2(u[j], u[j + 1]), pack_bf16x2(u[j + 2], u[j + 3]),
-                                                        pack_bf16x2(u[j + 4], u[j + 5]), pack_bf16x2(u[j + 6], u[j + 7]));
+        ep_st16(grow + j, make_uint4(pack_bf16x2(g[j], g[j + 1]), pack_bf16x2(g[j + 2], g[j + 3]),
+                                                        pack_bf16x2(g[j + 4], g[j + 5]), pack_bf16x2(g[j + 6], g[j + 7])), ep.stream_stores);
+        ep_st16(urow + j, make_uint4(pack_bf16x2(u[j], u[j + 1]), pack_bf16x2(u[j + 2], u[j + 3]),
+                                                        pack_bf16x2(u[j + 4], u[j + 5]), pack_bf16x2(u[j + 6], u[j + 7])), ep.stream_stores);
       }
     }
   }
@@ -185,13 +195,13 @@ __device__ __forceinline__ void gemm_store_tile_swiglu_bwd(const GemmEpilogue& e
           swiglu_bwd_elem(gf.y, uf.y, bf16_round(__uint_as_float(r[q * 8 + 2 * t + 1]) * ep.alpha), dg[2 * t + 1],
                           du[2 * t + 1], ac[2 * t + 1]);
         }
-        *reinterpret_cast<uint4*>(dgrow + q * 8) = make_uint4(pack_bf16x2(dg[0], dg[1]), pack_bf16x2(dg[2], dg[3]),
-                                                             pack_bf16x2(dg[4], dg[5]), pack_bf16x2(dg[6], dg[7]));
-        *reinterpret_cast<uint4*>(dgrow + N + q * 8) = make_uint4(pack_bf16x2(du[0], du[1]), pack_bf16x2(du[2], du[3]),
-                                                                 pack_bf16x2(du[4], du[5]), pack_bf16x2(du[6], du[7]));
+        ep_st16(dgrow + q * 8, make_uint4(pack_bf16x2(dg[0], dg[1]), pack_bf16x2(dg[2], dg[3]),
+                                                             pack_bf16x2(dg[4], dg[5]), pack_bf16x2(dg[6], dg[7])), ep.stream_stores);
+        ep_st16(dgrow + N + q * 8, make_uint4(pack_bf16x2(du[0], du[1]), pack_bf16x2(du[2], du[3]),
+                                                                 pack_bf16x2(du[4], du[5]), pack_bf16x2(du[6], du[7])), ep.stream_stores);
         if (arow)
-          *reinterpret_cast<uint4*>(arow + q * 8) = make_uint4(pack_bf16x2(ac[0], ac[1]), pack_bf16x2(ac[2], ac[3]),
-                                                              pack_bf16x2(ac[4], ac[5]), pack_bf16x2(ac[6], ac[7]));
+          ep_st16(arow + q * 8, make_uint4(pack_bf16x2(ac[0], ac[1]), pack_bf16x2(ac[2], ac[3]),
+                                                              pack_bf16x2(ac[4], ac[5]), pack_bf16x2(ac[6], ac[7])), ep.stream_stores);
       }
     }
     if (more) {
@@ -237,7 +247,7 @@ __device__ __forceinline__ void gemm_store_tile(const GemmEpilogue& ep, uint32_t
             float4 p = *reinterpret_cast<const float4*>(crow + j);
             o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
           }
-          *reinterpret_cast<float4*>(crow + j) = o;
+          ep_st16f(crow + j, o, ep.stream_stores);
           ss += o.x * o.x + o.y * o.y + o.z * o.z + o.w * o.w;
         }
       } else {
@@ -264,8 +274,8 @@ __device__ __forceinline__ void gemm_store_tile(const GemmEpilogue& ep, uint32_t
       if (full && (ep.ldp & 7) == 0) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8)
-          *reinterpret_cast<uint4*>(prow + j) = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                                                          pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+          ep_st16(prow + j, make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+                                                          pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7])), ep.stream_stores);
       } else {
         #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -300,8 +310,8 @@ __device__ __forceinline__ void gemm_store_tile(const GemmEpilogue& ep, uint32_t
     if (full && (ep.ldc & 7) == 0) {
 #pragma unroll
       for (int j = 0; j < 32; j += 8)
-        *reinterpret_cast<uint4*>(crow + j) = make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
-                                                        pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7]));
+        ep_st16(crow + j, make_uint4(pack_bf16x2(v[j], v[j + 1]), pack_bf16x2(v[j + 2], v[j + 3]),
+                                                        pack_bf16x2(v[j + 4], v[j + 5]), pack_bf16x2(v[j + 6], v[j + 7])), ep.stream_stores);
     } else {
       #pragma unroll
       for (int j = 0; j < 32; ++j)
