@@ -77,6 +77,27 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
+// The same with an L2 eviction-priority hint (createpolicy): within a raster group the A row-panels are re-used by every
+// column tile of the sweep (evict_last), each B column-panel only by the few tiles that run next to each other
+// (evict_first).
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                      int32_t c0, int32_t c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
                "r"(ncols)
@@ -203,6 +224,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const uint64_t pol_last = l2_policy_evict_last(), pol_first = l2_policy_evict_first();
+      const uint64_t pol_a = ep.l2_hints == 2 ? pol_first : pol_last, pol_b = ep.l2_hints == 2 ? pol_last : pol_first;
       // Tile sequence: static (cluster_id, +num_clusters, ...) or claimed dynamically by the leader's producer from a
       // global counter (a pair that starts late because an NCCL kernel holds one of its SMs then simply takes fewer
       // tiles) and published to every other role of both CTAs through a small ring of tile ids.
@@ -237,6 +260,22 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
           const int k0 = kb * G2_BK;
+          if (ep.l2_hints) {
+            if (A_MN == 0) {
+              tma_load_2d_pair_hint(sa, &map_a, full_leader, k0, m0, pol_a);
+            } else {
+#pragma unroll
+              for (int j = 0; j < G2_BM / 64; ++j)
+                tma_load_2d_pair_hint(sa + j * (G2_BK * 128), &map_a, full_leader, m0 + j * 64, k0, pol_a);
+            }
+            if (B_MN == 0) {
+              tma_load_2d_pair_hint(sb, &map_b, full_leader, k0, n0, pol_b);
+            } else {
+#pragma unroll
+              for (int j = 0; j < G2_BNH / 64; ++j)
+                tma_load_2d_pair_hint(sb + j * (G2_BK * 128), &map_b, full_leader, n0 + j * 64, k0, pol_b);
+            }
+          } else {
           if (A_MN == 0) {
             tma_load_2d_pair(sa, &map_a, full_leader, k0, m0);              // box {64 k, 128 rows}
           } else {
@@ -250,6 +289,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < G2_BNH / 64; ++j)
               tma_load_2d_pair(sb + j * (G2_BK * 128), &map_b, full_leader, n0 + j * 64, k0);
+          }
           }
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }

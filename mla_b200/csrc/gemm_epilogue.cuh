@@ -42,6 +42,7 @@ struct GemmEpilogue {
   __nv_bfloat16* sb_act;           // bf16 [M, f] or null
   int64_t ld_sb_act;
   int stream_stores;               // 1: C / fused outputs are written with the evict-first hint
+  int l2_hints;                    // CTA-pair kernel: 1 = A loads evict_last / B loads evict_first, 2 = the other way round
 };
 
 // Output stores with the evict-first hint (st.global.cs): a GEMM's C tile is not re-read by this kernel, and at 0.4-0.8 GB

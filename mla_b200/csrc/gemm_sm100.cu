@@ -353,6 +353,13 @@ extern "C" int mla_gemm_bf16(const mla_gemm_args* g, void* stream_) {
     }
     const int64_t out_bytes = g->m * g->n * (g->c_dtype == 1 ? 4 : 2);
     ep.stream_stores = cs && out_bytes >= (int64_t(64) << 20);
+    static int hints = -1;
+    if (hints < 0) {
+      const char* e = getenv("MLA_GEMM_L2_HINTS");
+      hints = e ? atoi(e) : 0;
+    }
+    // operands that fit L2 together need no hint
+    ep.l2_hints = ((g->m + g->n) * g->k * 2 >= (int64_t(96) << 20)) ? hints : 0;
   }
   if (g->swiglu_bwd_gu != nullptr) {
     if (g->swiglu_out || g->c_dtype != 0 || g->bias || g->residual || g->pre_act || g->activation != MLA_ACT_NONE ||
