@@ -462,6 +462,7 @@ __global__ void ddim_step_kernel(const float* __restrict__ x, const EpsT* __rest
 
 using namespace mla;
 #define S_(x) ((cudaStream_t)(x))
+int gemv2_launch(const mla_gemv_args* a, void* stream);      // decode_stack.cu
 
 static int g_gemv_pdl = -1;
 static bool gemv_pdl_enabled() {
@@ -536,6 +537,18 @@ extern "C" int mla_gemv_fused(const mla_gemv_args* a, void* stream) {
   if (a->prologue < GV_PRO_NONE || a->prologue > GV_PRO_SWIGLU) return set_error(MLA_ERR_ARG, "gemv: unknown prologue");
   if (a->prologue == GV_PRO_RMSNORM && (!a->ln_weight || (reinterpret_cast<uintptr_t>(a->ln_weight) & 15)))
     return set_error(MLA_ERR_ARG, "gemv: the RMSNorm prologue needs a 16-byte aligned weight vector");
+  {
+    // m <= 2: consumers without a per-slot CTA barrier + FFMA2 + finisher warp (decode_stack.cu: gemv2_kernel), MLA_GEMV2=1
+    static int v2 = -1;
+    if (v2 < 0) {
+      const char* e = getenv("MLA_GEMV2");
+      v2 = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (v2 && M <= 2) {
+      const int rc = gemv2_launch(a, stream);
+      if (rc <= 0) return rc;
+    }
+  }
   const bool small_k = K <= GV_CONSUMERS * 8;                           // 4096
   const bool fast = (M <= 4 && small_k) || (M <= 2 && K <= GV_CONSUMERS * 8 * 3);   // activations fit the registers
   if (a->prologue != GV_PRO_NONE && !fast)

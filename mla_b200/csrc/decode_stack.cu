@@ -740,9 +740,128 @@ __global__ void __launch_bounds__(ST_THREADS, 1) decode_stack_kernel(const Stack
 #undef ST_TRACE
 }
 
+// ---------------------------------------------------------------------------------------------- one linear, per-op form
+// The same consumer / finisher / producer roles for ONE skinny linear (mla_gemv_fused's fast path, MLA_GEMV2=1): the 16
+// consumer warps are not synchronised per slot (partials published through an mbarrier, a dedicated finisher warp adds
+// them), dot products with FFMA2 — the two changes that took the consumers from ~3.0 to ~2.1 ms-equivalent per step inside
+// the stack kernel.  Programmatic dependent launch as in gemv_ring_kernel: the producer streams weights right away, the
+// consumers and the finisher wait for the previous kernel before touching activations / residual / output.
+struct Gemv2Params {
+  const __nv_bfloat16 *x, *w, *res, *ln_w;
+  __nv_bfloat16* out;
+  int M, N, K;
+  int64_t ldx, ldo, ldr;
+  float eps;
+  int prologue;
+  int stages;
+  uint32_t slot_bytes;
+  int rpi;
+};
+
+template <int MB>
+__global__ void __launch_bounds__(ST_THREADS, 1) gemv2_kernel(const Gemv2Params p) {
+  extern __shared__ uint8_t g2_smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g2_smem_raw) + 127) & ~uintptr_t(127));
+  __shared__ uint64_t full_bar[ST_MAX_STAGES], empty_bar[ST_MAX_STAGES], part_bar[ST_MAX_STAGES];
+  __shared__ float partial[2 * ST_MAX_STAGES * GV_CWARPS * 8];
+  __shared__ float red_ss[GV_CWARPS * 2];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (tid == 0) {
+    for (int s = 0; s < ST_MAX_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&part_bar[s], GV_CWARPS);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int rpi = p.rpi;
+  if (warp == GV_CWARPS) {
+    if ((tid & 31) == 0) {
+      // ---- producer: this CTA's groups, one bulk copy per slot where the pitch needs no padding
+      const uint32_t row_bytes = uint32_t(p.K) * 2u, pitch = (row_bytes + 127u) & ~127u;
+      const int groups = (p.N + rpi - 1) / rpi, full_groups = p.N / rpi;
+      const uint32_t group_bytes = row_bytes * uint32_t(rpi);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.w) + size_t(blockIdx.x) * group_bytes;
+      const size_t stride = size_t(gridDim.x) * group_bytes;
+      RingPos pos{0, 0u};
+      for (int g = blockIdx.x; g < groups; g += gridDim.x, src += stride) {
+        mbar_wait_a(smem_u32(&empty_bar[pos.s]), pos.par ^ 1u);
+        const uint32_t bytes = g < full_groups ? group_bytes : row_bytes * uint32_t(p.N - g * rpi);
+        mbar_arrive_expect_tx(&full_bar[pos.s], bytes);
+        uint8_t* dst = ring + size_t(pos.s) * p.slot_bytes;
+        if (pitch == row_bytes) {
+          bulk_load_row(dst, src, bytes, &full_bar[pos.s]);
+        } else {
+          for (uint32_t o = 0, q = 0; o < bytes; o += row_bytes, q += pitch) bulk_load_row(dst + q, src + o, row_bytes, &full_bar[pos.s]);
+        }
+        pos.next(p.stages);
+      }
+    }
+    return;
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  LinArgs la;
+  la.ring_base = smem_u32(ring); la.slot_bytes = p.slot_bytes; la.stages = p.stages;
+  la.full_bar = smem_u32(full_bar); la.empty_bar = smem_u32(empty_bar); la.part_bar = smem_u32(part_bar);
+  la.partial = smem_u32(partial); la.red_ss = red_ss;
+  la.x = p.x; la.ln_w = p.ln_w; la.res = p.res; la.out = p.out;
+  la.ldx = p.ldx; la.ldr = p.ldr; la.ldo = p.ldo;
+  la.M = p.M; la.N = p.N; la.K = p.K; la.eps = p.eps; la.dbg = 0; la.deal_off = 0;
+  la.pos = RingPos{0, 0u};
+  la.it = 0;
+  la.wait_acc = nullptr;
+  if (warp == GV_CWARPS + 1) {
+    stack_finish_k<MB>(la, rpi);
+    return;
+  }
+  if (p.prologue == GV_PRO_RMSNORM) stack_linear_k<MB, GV_PRO_RMSNORM>(la, rpi);
+  else if (p.prologue == GV_PRO_SWIGLU) stack_linear_k<MB, GV_PRO_SWIGLU>(la, rpi);
+  else stack_linear_k<MB, GV_PRO_NONE>(la, rpi);
+}
+
 }  // namespace mla
 
 using namespace mla;
+
+// mla_gemv_fused's fast path (m <= 2) through gemv2_kernel; returns MLA_ERR_ARG-free 1 when the shape is not taken
+int gemv2_launch(const mla_gemv_args* a, void* stream) {
+  const int M = a->m, N = a->n, K = a->k;
+  if (M > 2 || K > GV_CONSUMERS * 8 * 3 || (K & 7) || a->ldw != K) return 1;
+  Gemv2Params p;
+  p.x = (const __nv_bfloat16*)a->x; p.w = (const __nv_bfloat16*)a->w; p.res = (const __nv_bfloat16*)a->residual;
+  p.ln_w = (const __nv_bfloat16*)a->ln_weight; p.out = (__nv_bfloat16*)a->out;
+  p.M = M; p.N = N; p.K = K; p.ldx = a->ldx; p.ldo = a->ldo; p.ldr = a->ldr; p.eps = a->eps; p.prologue = a->prologue;
+  p.rpi = K <= GV_CONSUMERS * 8 ? 4 : 2;
+  const size_t pitch = (size_t(K) * 2 + 127) & ~size_t(127);
+  const size_t slot = pitch * p.rpi;
+  const size_t ring_bytes = 227 * 1024 - 10240 - 128;
+  int stages = int(ring_bytes / slot);
+  if (stages < 2) return 1;
+  p.stages = stages > ST_MAX_STAGES ? ST_MAX_STAGES : stages;
+  p.slot_bytes = uint32_t(slot);
+  const size_t smem = slot * p.stages + 128;
+  auto kern = M <= 1 ? gemv2_kernel<1> : gemv2_kernel<2>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "cudaFuncSetAttribute(gemv2 smem %zu): %s", smem, cudaGetErrorString(e));
+  const int groups = (N + p.rpi - 1) / p.rpi;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(groups < num_sms() ? groups : num_sms());
+  cfg.blockDim = dim3(ST_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  const char* env = getenv("MLA_DECODE_PDL");
+  cfg.numAttrs = (env && env[0] == '0') ? 0 : 1;
+  e = cudaLaunchKernelEx(&cfg, kern, p);
+  if (e != cudaSuccess) return set_error(MLA_ERR_CUDA, "gemv2 launch: %s", cudaGetErrorString(e));
+  MLA_CHECK_LAUNCH("gemv2");
+  return MLA_OK;
+}
 
 static int g_stack_coop = -1;
 static int g_stack_dbg = 0;
