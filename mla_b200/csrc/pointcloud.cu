@@ -193,19 +193,28 @@ __global__ void group_pose_kernel(const float* __restrict__ xyz, const void* __r
   __syncthreads();
   const __nv_bfloat16* fb = static_cast<const __nv_bfloat16*>(feat);
   const float* ff = static_cast<const float*>(feat);
-  for (int e = threadIdx.x; e < K * out_dim; e += blockDim.x) {
-    const int k = e / out_dim, ch = e % out_dim;
-    const int src = ch < C ? knn_idx[int64_t(bg) * K + k] : center;
-    const int cc = ch < C ? ch : ch - C;
-    const int64_t fo = (int64_t(b) * N + src) * C + cc;
-    const float fv = feat_is_bf16 ? __bfloat162float(fb[fo]) : ff[fo];
-    const int c3 = ch / (2 * fd), j = ch % (2 * fd);
-    const float arg = (beta * nrm[k * 3 + c3]) / dim_embed[j < fd ? j : j - fd];
-    const float pe = j < fd ? sinf(arg) : cosf(arg);
-    const float v = fv + pe;
-    const int64_t o = (int64_t(bg) * K + k) * out_dim + ch;
-    xf[o] = v;
-    xb[o] = __float2bfloat16_rn(v);
+  // channel ch = c3 * 2fd + j carries sin(arg) for j < fd and cos(arg) of the SAME arg at j + fd: one sincosf per pair
+  // (the kernel is bound by the two accurate transcendentals per element, not by its 6 bytes of output)
+  const int half = out_dim / 2;                    // = 3 * fd pairs per neighbour
+  for (int e = threadIdx.x; e < K * half; e += blockDim.x) {
+    const int k = e / half, pr = e % half;
+    const int c3 = pr / fd, jj = pr % fd;
+    const float arg = (beta * nrm[k * 3 + c3]) / dim_embed[jj];
+    float sn, cs;
+    sincosf(arg, &sn, &cs);
+    const int nb = knn_idx[int64_t(bg) * K + k];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int ch = c3 * 2 * fd + jj + q * fd;
+      const int src = ch < C ? nb : center;
+      const int cc = ch < C ? ch : ch - C;
+      const int64_t fo = (int64_t(b) * N + src) * C + cc;
+      const float fv = feat_is_bf16 ? __bfloat162float(fb[fo]) : ff[fo];
+      const float v = fv + (q == 0 ? sn : cs);
+      const int64_t o = (int64_t(bg) * K + k) * out_dim + ch;
+      xf[o] = v;
+      xb[o] = __float2bfloat16_rn(v);
+    }
   }
 }
 
