@@ -249,6 +249,76 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, float* __rest
   if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
   if (running_var) running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * (n / fmaxf(n - 1.f, 1.f));
 }
+// 16-byte vectors (C % 8 == 0): the scalar kernels above/below move 2 bytes per thread and pay a 64-bit modulo per element
+// (0.22 / 0.32 ms per call at 1.3 M x 96..192 against ~0.05 / 0.08 ms of HBM time).
+__global__ void __launch_bounds__(256)
+bn_stats_vec_kernel(const __nv_bfloat16* __restrict__ y, float* __restrict__ sums, int64_t rows, int C, int rows_per_block) {
+  __shared__ float red[256 * 16];
+  const int cpr = C >> 3;                         // 16-byte chunks per row
+  const int lanes = blockDim.x / cpr;             // rows processed per step
+  const int cc = threadIdx.x % cpr, rr = threadIdx.x / cpr;
+  const int64_t r0 = int64_t(blockIdx.x) * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  if (rr < lanes) {
+    auto add = [&](const uint4& u) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float2 f = __bfloat1622float2(h[t]);
+        s[2 * t] += f.x; q[2 * t] += f.x * f.x;
+        s[2 * t + 1] += f.y; q[2 * t + 1] += f.y * f.y;
+      }
+    };
+    int64_t r = r0 + rr;
+    for (; r + 3 * lanes < r1; r += 4 * lanes) {       // four loads in flight per thread
+      const uint4 u0 = *reinterpret_cast<const uint4*>(y + r * C + cc * 8);
+      const uint4 u1 = *reinterpret_cast<const uint4*>(y + (r + lanes) * C + cc * 8);
+      const uint4 u2 = *reinterpret_cast<const uint4*>(y + (r + 2 * lanes) * C + cc * 8);
+      const uint4 u3 = *reinterpret_cast<const uint4*>(y + (r + 3 * lanes) * C + cc * 8);
+      add(u0); add(u1); add(u2); add(u3);
+    }
+    for (; r < r1; r += lanes) add(*reinterpret_cast<const uint4*>(y + r * C + cc * 8));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s[j]; red[threadIdx.x * 16 + 8 + j] = q[j]; }
+  __syncthreads();
+  // thread (cc, j) with rr == 0 folds the row lanes of its column
+  for (int idx = threadIdx.x; idx < cpr * 16; idx += blockDim.x) {
+    const int c2 = idx / 16, j = idx % 16;
+    float t = 0.f;
+    for (int l = 0; l < lanes; ++l) t += red[(l * cpr + c2) * 16 + j];
+    atomicAdd(sums + (j < 8 ? 0 : C) + c2 * 8 + (j & 7), t);
+  }
+}
+__global__ void __launch_bounds__(256)
+bn_relu_vec_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ coef, const float* __restrict__ w,
+                   const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int64_t total8, int C) {
+  // the launcher makes gridDim * blockDim a multiple of the chunks per row, so a thread meets the same 8 columns in every
+  // iteration and keeps their coefficients in registers
+  const int cpr = C >> 3;
+  const int64_t i0 = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  const int c0 = int(i0 % cpr) * 8;
+  float mean[8], inv[8], ww[8], bb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { mean[j] = coef[c0 + j]; inv[j] = coef[C + c0 + j]; ww[j] = w[c0 + j]; bb[j] = bias[c0 + j]; }
+  for (int64_t i = i0; i < total8; i += int64_t(gridDim.x) * blockDim.x) {
+    const uint4 u = *reinterpret_cast<const uint4*>(y + i * 8);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    float o[8];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 f = __bfloat1622float2(h[t]);
+      o[2 * t] = f.x; o[2 * t + 1] = f.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaxf((o[j] - mean[j]) * inv[j] * ww[j] + bb[j], 0.f);
+    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                        pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  }
+}
 // out = bf16(relu(bn(y)))   (in place allowed)
 __global__ void bn_relu_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ coef,
                                const float* __restrict__ w, const float* __restrict__ bias,
@@ -341,6 +411,13 @@ extern "C" int mla_bn_stats(const void* y, void* sums, int64_t rows, int32_t c, 
   int rpb = int((rows + target_blocks - 1) / target_blocks);
   if (rpb < 8) rpb = 8;
   const int blocks = int((rows + rpb - 1) / rpb);
+  if ((c & 7) == 0 && c <= 2048 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && rows >= 4096) {
+    int rpb2 = rpb < 64 ? 64 : rpb;
+    const int blocks2 = int((rows + rpb2 - 1) / rpb2);
+    bn_stats_vec_kernel<<<blocks2, 256, 0, S_(stream)>>>((const __nv_bfloat16*)y, (float*)sums, rows, c, rpb2);
+    MLA_CHECK_LAUNCH("bn_stats_vec");
+    return MLA_OK;
+  }
   bn_stats_kernel<<<blocks, c >= 256 ? 256 : (c + 31) / 32 * 32, 0, S_(stream)>>>((const __nv_bfloat16*)y, (float*)sums, rows, c, rpb);
   MLA_CHECK_LAUNCH("bn_stats");
   return MLA_OK;
@@ -360,6 +437,21 @@ extern "C" int mla_bn_relu(const void* y, const void* coef, const void* w, const
   if (int rc = device_check()) return rc;
   if (rows <= 0) return MLA_OK;
   const int64_t total = rows * c;
+  if ((c & 7) == 0 && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const int64_t total8 = total >> 3;
+    int grid8 = int((total8 + 255) / 256 < int64_t(num_sms()) * 16 ? (total8 + 255) / 256 : int64_t(num_sms()) * 16);
+    {   // gridDim * 256 must be a multiple of the chunks per row (c / 8)
+      const int cpr = c >> 3;
+      int a = cpr, b = 256;
+      while (b) { const int t = a % b; a = b; b = t; }
+      const int need = cpr / a;
+      grid8 = (grid8 + need - 1) / need * need;
+    }
+    bn_relu_vec_kernel<<<grid8, 256, 0, S_(stream)>>>((const __nv_bfloat16*)y, (const float*)coef, (const float*)w,
+                                                      (const float*)bias, (__nv_bfloat16*)out, total8, c);
+    MLA_CHECK_LAUNCH("bn_relu_vec");
+    return MLA_OK;
+  }
   int grid = int((total + 255) / 256 < int64_t(num_sms()) * 16 ? (total + 255) / 256 : int64_t(num_sms()) * 16);
   bn_relu_kernel<<<grid, 256, 0, S_(stream)>>>((const __nv_bfloat16*)y, (const float*)coef, (const float*)w,
                                                (const float*)bias, (__nv_bfloat16*)out, total, c);
